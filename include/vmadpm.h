@@ -1,0 +1,193 @@
+/*
+ * vmadpm.h -- C ABI of libvmadpm.so, the B200 (sm_100a) particle-mesh backend that
+ * replaces the pmesh calls made by vmad's FastPM operator library.
+ *
+ * Every entry point names the reference interface it stands in for, as
+ *   vmad/lib/fastpm.py:<line>  (the call site in /root/reference)  and the pmesh
+ * method that call site delegates to (pmesh is an un-vendored dependency of the
+ * reference; SURVEY.md Appendix A lists the protocol).
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on failure; vpm_last_error() then
+ *     returns a message (thread-local, valid until the next failing call);
+ *   - all pointers except `host_*` / `out_host` are DEVICE pointers owned by the
+ *     caller; the library never frees or retains them beyond the call's kernels;
+ *   - all work is enqueued on the context's stream and is asynchronous; the only
+ *     calls that wait for the device are vpm_sync, vpm_layout_count (returns a
+ *     host integer) and the vpm_reduce_* family (return host scalars);
+ *   - fp64 throughout ("f8"), complex128 stored interleaved (re, im);
+ *   - meshes are 3-D, C order, last axis contiguous.  A 2-D mesh [N1, N2] is passed
+ *     as [1, N1, N2] with scale[0] = 1 and positions' first coordinate = 0;
+ *   - slab decomposition: a rank holds planes [start0, start0 + nloc0) of axis 0 of
+ *     the real mesh.  Single-rank: start0 = 0, nloc0 = n[0], ghost = 0.
+ */
+#ifndef VMADPM_H
+#define VMADPM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vpm_ctx vpm_ctx;
+
+/* Geometry of the (local slab of the) real mesh. */
+typedef struct vpm_mesh {
+    int64_t n[3];      /* global mesh size Nmesh                                  */
+    double scale[3];   /* Nmesh / BoxSize: u = x * scale (one rounded multiply)   */
+    int64_t start0;    /* first plane of axis 0 held locally                      */
+    int64_t nloc0;     /* number of planes held locally                           */
+    int64_t stride0;   /* element stride between planes of the real array         */
+    int64_t stride1;   /* element stride between rows   (>= n[2]; n[2]+2 when the
+                          array is the padded in-place c2r output)                */
+    int32_t ghost;     /* 0: periodic single slab; 1: slab with a lower ghost
+                          plane of *particles* (cell keys count nloc0 + 1 planes) */
+    int32_t reserved;
+} vpm_mesh;
+
+/* ---- context -------------------------------------------------------------- */
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream), 0 = legacy
+ * default stream. */
+int vpm_ctx_create(vpm_ctx** out, int device, void* stream);
+int vpm_ctx_destroy(vpm_ctx* ctx);
+int vpm_ctx_set_stream(vpm_ctx* ctx, void* stream);
+int vpm_sync(vpm_ctx* ctx);
+const char* vpm_last_error(void);
+int vpm_version(void);
+/* number of kernels (own kernels + cuFFT executions) launched by this library */
+int64_t vpm_launch_count(void);
+int vpm_device_sm_count(vpm_ctx* ctx, int* out_host);
+
+/* ---- decompose / exchange / gather  (fastpm.py:272,286,289,301,304; pmesh
+ *      ParticleMesh.decompose, Layout.exchange, Layout.gather) ---------------- */
+/* cell key of every particle: ((i0' * n1) + i1) * n2 + i2 of the wrapped floor cell,
+ * i0' = i0 (ghost = 0) or (i0 - start0 + 1) mod n0 (ghost = 1). int32. */
+int vpm_cell_keys(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_t np,
+                  int32_t* keys);
+/* number of cells keyed by vpm_cell_keys for this mesh (host value, no sync) */
+int64_t vpm_layout_ncell(const vpm_mesh* mesh);
+/* stable counting sort by cell key.  Outputs: keys[np], perm[np] (slot -> input
+ * index; equal keys keep input order), cell_start[ncell + 1] (first slot of each
+ * cell; cell_start[ncell] = np). */
+int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_t np,
+                     int32_t* keys, int32_t* perm, int32_t* cell_start);
+/* dst[i, :] = src[perm[i], :]            (Layout.exchange on one rank) */
+int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
+                  int ncomp, double* dst);
+/* dst[perm[i], :] = src[i, :]  for a permutation (Layout.gather on one rank) */
+int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
+                     int ncomp, double* dst);
+/* dst[idx[i], :] += src[i, :]  (gather with duplicated copies; dst pre-zeroed) */
+int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n,
+                         int ncomp, double* dst);
+
+/* ---- paint  (fastpm.py:224,238,256; pmesh ParticleMesh.paint / paint_jvp and the
+ *      mesh half of RealField.readout_vjp) ---------------------------------- */
+/* Particles sorted by cell key (xs = x[perm]); writes EVERY local cell exactly once
+ * (no zero-fill needed, no atomics, run-to-run deterministic).
+ * mass: per-particle array (sorted like xs) or NULL -> mass0. */
+int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
+                     const double* mass, double mass0, int64_t np,
+                     const int32_t* cell_start, double* out);
+/* sum_d mass * vpos[:, d] * dW/dx_d  (+ vmass * W when vmass != NULL) */
+int vpm_paint_jvp_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
+                         const double* mass, double mass0, const double* vpos,
+                         const double* vmass, int64_t np, const int32_t* cell_start,
+                         double* out);
+/* Baseline scatter for unsorted particles: zero-fill + 8 RED.F64 per particle. */
+int vpm_paint_atomic(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x,
+                     const double* mass, double mass0, int64_t np, double* out);
+
+/* ---- readout  (fastpm.py:229,252,256,263; pmesh RealField.readout / readout_vjp /
+ *      readout_jvp and the particle half of ParticleMesh.paint_vjp) ------------ */
+/* value[p] = sum_c field[c] W(x_p - c) */
+int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const double* x,
+                int64_t np, double* value);
+/* three fields at once, written interleaved [np, 3] (fuses linalg.stack,
+ * fastpm.py:349,437) */
+int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                 const double* f2, const double* x, int64_t np, double* value3);
+/* value[p] (optional, may be NULL) and grad[p, d] = w_p * sum_c field[c] dW/dx_d,
+ * w_p = weight[p] or weight0 when weight == NULL. */
+int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
+                     const double* x, const double* weight, double weight0, int64_t np,
+                     double* value, double* grad);
+/* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);
+ * either term may be absent (NULL). */
+int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
+                    const double* field_dot, const double* x, const double* xdot,
+                    int64_t np, double* value);
+
+/* ---- FFT  (fastpm.py:50,53,56,64,67,70; pmesh RealField.r2c / c2r_vjp,
+ *      ComplexField.c2r / r2c_vjp).  cuFFT does the transform; `scale` is applied
+ *      by a fused pass (1.0 skips it).  n = real mesh shape (n[0] = 1 for 2-D). --- */
+int vpm_r2c(vpm_ctx* ctx, const int64_t n[3], const double* real_in, double* cplx_out,
+            double scale);
+/* preserves cplx_in (copies into the context workspace first) */
+int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
+            double scale);
+
+/* ---- k-space  (fastpm.py:79,83,87 apply_transfer; :310-334 filters; pmesh
+ *      ComplexField.apply) ---------------------------------------------------- */
+/* out = in * scale * L * a0[i] * a1[j] * a2[k]
+ *   L      = -1 / (kk0[i]^2 + kk1[j]^2 + kk2[k]^2)  (0 where the sum is 0) when
+ *            laplace != 0, else 1                      (fourier_space_laplace)
+ *   a_d    = complex table of length n_d (nh for d = 2) or NULL (= 1); conj_tables
+ *            conjugates them (apply_transfer.vjp, fastpm.py:81-83)
+ * nc = complex array shape [n0, n1, nh]. */
+int vpm_transfer(vpm_ctx* ctx, const int64_t nc[3], const double* in, double* out,
+                 double scale, int laplace, const double* kk0, const double* kk1,
+                 const double* kk2, const double* a0, const double* a1, const double* a2,
+                 int conj_tables);
+/* out = in * table (general, broadcast strides in complex elements; table real or
+ * complex; conj optional) -- arbitrary tf(k) evaluated once on the host. */
+int vpm_transfer_table(vpm_ctx* ctx, const int64_t nc[3], const double* in, double* out,
+                       const double* table, const int64_t tstride[3], int table_is_complex,
+                       int conj_table);
+/* Fused force pass of `gravity` (fastpm.py:424-431): from rho_k (un-normalised cuFFT
+ * output allowed via `scale`) produce p = scale * L * rho_k (optional, may be NULL) and
+ * the three gradient fields g_d = p * a_d[.] in one read of rho_k. */
+int vpm_force_kspace(vpm_ctx* ctx, const int64_t nc[3], const double* rhok, double scale,
+                     const double* kk0, const double* kk1, const double* kk2,
+                     const double* a0, const double* a1, const double* a2,
+                     double* p_out, double* g0, double* g1, double* g2);
+
+/* ---- elementwise and reductions on flat fp64 arrays (the stdlib arithmetic that
+ *      vmad applies to fields / particle arrays: vmad/core/stdlib/operators.py:14-152;
+ *      kick / drift of fastpm.py:459-471) ------------------------------------- */
+/* out = a * x + b * y + c   (y may be NULL) */
+int vpm_axpby(vpm_ctx* ctx, int64_t n, double a, const double* x, double b,
+              const double* y, double c, double* out);
+/* out = x * y */
+int vpm_mul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
+/* out = x / y */
+int vpm_div(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
+/* out[i, :] = x[i, :] * w[i]   (row scaling of an [n, ncomp] array) */
+int vpm_mul_rows(vpm_ctx* ctx, int64_t n, int ncomp, const double* x, const double* w,
+                 double* out);
+/* complex: out = x * y or x * conj(y) */
+int vpm_cmul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, int conj_y,
+             double* out);
+int vpm_fill(vpm_ctx* ctx, int64_t n, double value, double* out);
+/* [n] x ncomp separate arrays -> interleaved [n, ncomp]  (linalg.stack axis=-1) */
+int vpm_stack(vpm_ctx* ctx, int64_t n, int ncomp, const double* const* cols_host,
+              double* out);
+/* out[i] = x[i, col] of an [n, ncomp] array  (numpy.take(..., axis=-1)) */
+int vpm_take_col(vpm_ctx* ctx, int64_t n, int ncomp, int col, const double* x, double* out);
+
+/* deterministic two-stage reductions; result delivered to the host (synchronises) */
+int vpm_reduce_sum(vpm_ctx* ctx, int64_t n, const double* x, double* out_host);
+int vpm_reduce_dot(vpm_ctx* ctx, int64_t n, const double* x, const double* y,
+                   double* out_host);
+/* sum over stored modes of w_k * x conj(y): out_host[0] = real, [1] = imag.
+ * w_k = 2 except on the planes k = 0 and (n_last even) k = n_last/2 of the half axis
+ * (pmesh ComplexField.cnorm / cdot, fastpm.py:15,519). nc = [n0, n1, nh]. */
+int vpm_reduce_cdot(vpm_ctx* ctx, const int64_t nc[3], int64_t n_last, const double* x,
+                    const double* y, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMADPM_H */

@@ -1,0 +1,281 @@
+"""Parity of every CUDA kernel (through the C ABI / device pm) with the numpy oracle.
+
+Bars (BASELINE.json north_star): bit-exact for cell keys, sort permutations and cell offsets;
+fp64 fields and particle values within 1e-12 relative L2.
+"""
+import numpy
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def edge_positions(rng, Nmesh, BoxSize, n):
+    """random positions plus every nasty case: 0, L, -eps, L-eps, exact cell edges, far outside"""
+    nd = len(Nmesh)
+    L = numpy.empty(nd)
+    L[...] = BoxSize
+    x = rng.uniform(0, 1, size=(n, nd)) * L
+    cell = L / numpy.array(Nmesh)
+    eps = numpy.finfo('f8').eps
+    special = []
+    for d in range(nd):
+        for v in [0.0, L[d], -eps * L[d], L[d] * (1 - eps), -L[d] * 0.3, L[d] * 1.7, -5.25 * L[d],
+                  7.5 * L[d], cell[d], 3 * cell[d], cell[d] * (1 - eps), cell[d] * (1 + eps)]:
+            p = rng.uniform(0, 1, size=nd) * L
+            p[d] = v
+            special.append(p)
+    lattice = (numpy.indices(Nmesh).reshape(nd, -1).T * cell)[:min(n, 4096)]
+    return numpy.concatenate([x, numpy.array(special), lattice], axis=0)
+
+
+CASES = [([8, 8, 8], 16.0, 500), ([32, 32, 32], 100.0, 40000), ([20, 12, 36], [7.0, 3.0, 11.0], 9000),
+         ([64, 64, 64], 200.0, 1 << 20)]
+
+
+@pytest.mark.parametrize("Nmesh,BoxSize,n", CASES)
+def test_keys_and_layout_bit_exact(oracle_pm, device_pm, Nmesh, BoxSize, n):
+    rng = numpy.random.default_rng(1)
+    opm = oracle_pm(Nmesh, BoxSize)
+    dpm = device_pm(Nmesh, BoxSize)
+    x = edge_positions(rng, Nmesh, BoxSize, n)
+    okeys = opm.cell_keys(x)
+    dkeys = dpm.cell_keys(x).cpu().numpy()
+    assert numpy.array_equal(okeys, dkeys)
+    olay = opm.decompose(x)
+    dlay = dpm.decompose(x)
+    assert numpy.array_equal(dlay.keys.cpu().numpy(), okeys)
+    assert numpy.array_equal(dlay.indices.cpu().numpy(), olay.indices)
+    cs = dlay.cell_start.cpu().numpy()
+    ref = numpy.concatenate([[0], numpy.cumsum(numpy.bincount(okeys, minlength=opm.Ntot))])
+    assert numpy.array_equal(cs[:opm.Ntot + 1], ref)
+    assert cs[-1] == len(x)
+    # exchange / gather routing
+    ex = dlay.exchange(x).numpy()
+    assert numpy.array_equal(ex, olay.exchange(x))
+    v = rng.standard_normal(len(x))
+    assert numpy.array_equal(dlay.gather(dlay.exchange(v)).numpy(), v)
+    assert numpy.array_equal(dlay.gather(v).numpy(), olay.gather(v))
+
+
+def test_layout_crowded_cells(oracle_pm, device_pm):
+    """many particles per cell (beyond the insertion-sort limit) keep the stable order"""
+    rng = numpy.random.default_rng(2)
+    opm = oracle_pm([4, 4, 4], 4.0)
+    dpm = device_pm([4, 4, 4], 4.0)
+    x = rng.uniform(0, 4, size=(50000, 3))
+    x[:20000] = [1.5, 2.5, 3.5]            # 20000 particles in one cell
+    x[20000:20100] = [0.5, 0.5, 0.5]
+    olay = opm.decompose(x)
+    dlay = dpm.decompose(x)
+    assert numpy.array_equal(dlay.indices.cpu().numpy(), olay.indices)
+
+
+@pytest.mark.parametrize("Nmesh,BoxSize,n", CASES)
+def test_paint_parity(oracle_pm, device_pm, Nmesh, BoxSize, n):
+    rng = numpy.random.default_rng(3)
+    opm = oracle_pm(Nmesh, BoxSize)
+    dpm = device_pm(Nmesh, BoxSize)
+    x = edge_positions(rng, Nmesh, BoxSize, n)
+    m = rng.uniform(0.5, 1.5, size=len(x))
+    ref = opm.paint(x, 1.0).value
+    got = dpm.paint(x, 1.0).numpy()
+    assert rel_l2(got, ref) < TOL
+    assert abs(got.sum() - len(x)) < 1e-9 * len(x)
+    ref = opm.paint(x, m).value
+    assert rel_l2(dpm.paint(x, m).numpy(), ref) < TOL
+    # with an explicit layout, and through exchange (tagged, no re-sort)
+    lay = dpm.decompose(x)
+    assert rel_l2(dpm.paint(x, m, layout=lay).numpy(), ref) < TOL
+    assert rel_l2(dpm.paint(lay.exchange(x), lay.exchange(m)).numpy(), ref) < TOL
+    # atomic baseline kernel
+    assert rel_l2(dpm.paint_atomic(x, m).numpy(), ref) < TOL
+    # run-to-run determinism of the sorted kernel
+    a = dpm.paint(x, m).numpy()
+    b = dpm.paint(x, m).numpy()
+    assert numpy.array_equal(a, b)
+
+
+def test_paint_uniform_grid_is_one(device_pm):
+    """test_fastpm.py:158-159,176-177: one particle per cell paints exactly 1 per cell"""
+    for shift in (0.0, 0.1, 0.5):
+        dpm = device_pm([16, 16, 16], 50.0)
+        q = dpm.generate_uniform_particle_grid(shift=shift)
+        mesh = dpm.paint(q, 1.0).numpy()
+        assert numpy.abs(mesh - 1.0).max() < 1e-13
+
+
+@pytest.mark.parametrize("Nmesh,BoxSize,n", CASES[:3])
+def test_readout_family_parity(oracle_pm, device_pm, Nmesh, BoxSize, n):
+    rng = numpy.random.default_rng(4)
+    opm = oracle_pm(Nmesh, BoxSize)
+    dpm = device_pm(Nmesh, BoxSize)
+    x = edge_positions(rng, Nmesh, BoxSize, n)
+    f = rng.standard_normal(Nmesh)
+    fdot = rng.standard_normal(Nmesh)
+    v = rng.standard_normal(len(x))
+    xdot = rng.standard_normal(x.shape)
+    m = rng.uniform(0.5, 1.5, size=len(x))
+    of = opm.create('real', value=f)
+    df = dpm.create('real', value=f)
+    assert rel_l2(df.readout(x).numpy(), of.readout(x)) < TOL
+    lay = dpm.decompose(x)
+    assert rel_l2(df.readout(x, layout=lay).numpy(), of.readout(x)) < TOL
+    # readout_vjp
+    omesh, opos = of.readout_vjp(x, v)
+    dmesh, dpos = df.readout_vjp(x, v)
+    assert rel_l2(dmesh.numpy(), omesh.value) < TOL
+    assert rel_l2(dpos.numpy(), opos) < TOL
+    dmesh, dpos = df.readout_vjp(x, v, layout=lay)
+    assert rel_l2(dmesh.numpy(), omesh.value) < TOL
+    assert rel_l2(dpos.numpy(), opos) < TOL
+    # readout_jvp (both terms, each alone)
+    ref = of.readout_jvp(x, v_self=opm.create('real', value=fdot), v_pos=xdot)
+    assert rel_l2(df.readout_jvp(x, v_self=fdot, v_pos=xdot).numpy(), ref) < TOL
+    assert rel_l2(df.readout_jvp(x, v_pos=xdot).numpy(), of.readout_jvp(x, v_pos=xdot)) < TOL
+    assert rel_l2(df.readout_jvp(x, v_self=fdot).numpy(),
+                  of.readout_jvp(x, v_self=opm.create('real', value=fdot))) < TOL
+    # paint_vjp
+    opos, omass = opm.paint_vjp(of, x, mass=m)
+    dpos, dmass = dpm.paint_vjp(df, x, mass=m)
+    assert rel_l2(dpos.numpy(), opos) < TOL
+    assert rel_l2(dmass.numpy(), omass) < TOL
+    opos, omass = opm.paint_vjp(of, x, mass=1.0)
+    dpos, dmass = dpm.paint_vjp(df, x, mass=1.0, layout=lay)
+    assert rel_l2(dpos.numpy(), opos) < TOL
+    assert rel_l2(dmass.numpy(), omass) < TOL
+    # paint_jvp
+    ref = opm.paint_jvp(x, v_mass=v, mass=m, v_pos=xdot).value
+    assert rel_l2(dpm.paint_jvp(x, v_mass=v, mass=m, v_pos=xdot).numpy(), ref) < TOL
+    ref = opm.paint_jvp(x, mass=1.0, v_pos=xdot).value
+    assert rel_l2(dpm.paint_jvp(x, mass=1.0, v_pos=xdot).numpy(), ref) < TOL
+    ref = opm.paint_jvp(x, v_mass=v, mass=m).value
+    assert rel_l2(dpm.paint_jvp(x, v_mass=v, mass=m).numpy(), ref) < TOL
+    # fused three-field readout
+    fs = [rng.standard_normal(Nmesh) for _ in range(3)]
+    got = dpm.readout3(*[dpm.create('real', value=a) for a in fs], x).numpy()
+    ref = numpy.stack([opm.create('real', value=a).readout(x) for a in fs], axis=-1)
+    assert rel_l2(got, ref) < TOL
+
+
+@pytest.mark.parametrize("Nmesh", [[4, 4], [8, 8], [4, 4, 4], [32, 32, 32], [20, 12, 36], [128, 128, 128]])
+def test_fft_parity(oracle_pm, device_pm, Nmesh):
+    rng = numpy.random.default_rng(5)
+    opm = oracle_pm(Nmesh, 8.0)
+    dpm = device_pm(Nmesh, 8.0)
+    r = rng.standard_normal(Nmesh)
+    c = rng.standard_normal(opm.cshape) + 1j * rng.standard_normal(opm.cshape)  # NOT hermitian-consistent
+    orf, dr = opm.create('real', value=r), dpm.create('real', value=r)
+    oc, dc = opm.create('complex', value=c), dpm.create('complex', value=c)
+    assert rel_l2(dr.r2c().numpy(), orf.r2c().value) < TOL
+    assert rel_l2(dr.c2r_vjp().numpy(), orf.c2r_vjp().value) < TOL
+    assert rel_l2(dc.c2r().numpy(), oc.c2r().value) < TOL
+    assert rel_l2(dc.r2c_vjp().numpy(), oc.r2c_vjp().value) < TOL
+    assert numpy.array_equal(dc.numpy(), c)  # c2r must not clobber its input
+    # round trip identity (test_fastpm.py:25-37)
+    assert rel_l2(dr.r2c().c2r().numpy(), r) < TOL
+    # reductions
+    assert abs(dr.cnorm() - orf.cnorm()) < 1e-12 * abs(orf.cnorm())
+    assert abs(dc.cnorm() - oc.cnorm()) < 1e-12 * abs(oc.cnorm())
+    c2 = rng.standard_normal(opm.cshape) + 1j * rng.standard_normal(opm.cshape)
+    assert abs(dc.cdot(c2) - oc.cdot(c2)) < 1e-12 * abs(oc.cdot(c2))
+    # Parseval (test_fastpm.py:142)
+    r2 = rng.standard_normal(Nmesh)
+    lhs = dr.r2c().cdot(dpm.create('real', value=r2).r2c()).real
+    assert abs(lhs - (r * r2).sum() / opm.Ntot) < 1e-12 * abs(lhs) + 1e-15
+
+
+@pytest.mark.parametrize("Nmesh", [[8, 8], [8, 8, 8], [20, 12, 36]])
+def test_transfer_parity(oracle_pm, device_pm, Nmesh):
+    rng = numpy.random.default_rng(6)
+    BoxSize = 13.0
+    opm = oracle_pm(Nmesh, BoxSize)
+    dpm = device_pm(Nmesh, BoxSize)
+    c = rng.standard_normal(opm.cshape) + 1j * rng.standard_normal(opm.cshape)
+    oc, dc = opm.create('complex', value=c), dpm.create('complex', value=c)
+
+    def laplace(k):
+        k2 = k.normp(2)
+        bad = k2 == 0
+        k2[bad] = 1
+        k2 = -1 / k2
+        k2[bad] = 0
+        return k2
+
+    def grad(d):
+        def f(k):
+            h = BoxSize / Nmesh[d]
+            w = k[d] * h
+            return -1j * (1 / (6.0 * h) * (8 * numpy.sin(w) - numpy.sin(2 * w)))
+        return f
+
+    def mixed(k):
+        return (1.0 + sum(ki ** 2 for ki in k)) ** -0.5 + 0.25j * k[0]
+
+    for tf in [laplace, grad(0), grad(len(Nmesh) - 1), mixed]:
+        ref = oc.apply(lambda k, v: v * tf(k)).value
+        got = dc.apply(lambda k, v: v * tf(k)).numpy()
+        assert rel_l2(got, ref) < TOL
+        ref = oc.apply(lambda k, v: v * numpy.conj(tf(k))).value
+        got = dc.apply(lambda k, v: v * numpy.conj(tf(k))).numpy()
+        assert rel_l2(got, ref) < TOL
+    # the fused Green's function kernel reproduces numpy's -1/k^2 to the bit
+    got = dpm._transfer(dc, laplace=True).numpy()
+    ref = oc.apply(lambda k, v: v * laplace(k)).value
+    assert numpy.array_equal(got, ref)
+    for kind in ('circular', 'index'):
+        ref = oc.apply(lambda k, v: v * (1 + k[0] + 2 * k[-1]), kind=kind).value
+        got = dc.apply(lambda k, v: v * (1 + k[0] + 2 * k[-1]), kind=kind).numpy()
+        assert rel_l2(got, ref) < TOL
+
+
+def test_elementwise_and_numpy_protocol(device_pm):
+    from vmad_b200.pm import DeviceArray
+    rng = numpy.random.default_rng(7)
+    a = rng.standard_normal((1000, 3))
+    b = rng.standard_normal((1000, 3))
+    w = rng.standard_normal(1000)
+    A, B, W = DeviceArray.from_host(a), DeviceArray.from_host(b), DeviceArray.from_host(w)
+    assert numpy.array_equal((A + B).numpy(), a + b)
+    assert numpy.array_equal((A - B).numpy(), a - b)
+    assert numpy.array_equal((A * B).numpy(), a * b)
+    assert numpy.array_equal((A / B).numpy(), a / b)
+    assert numpy.array_equal((A * 2.5).numpy(), a * 2.5)
+    assert numpy.array_equal((2.5 * A).numpy(), a * 2.5)
+    assert numpy.array_equal((numpy.float64(2.5) * A).numpy(), a * 2.5)
+    assert numpy.array_equal((-A).numpy(), -a)
+    assert (A + 0) is A and (0 + A) is A
+    assert numpy.array_equal((A + 1.5).numpy(), a + 1.5)
+    assert numpy.array_equal((1.5 - A).numpy(), 1.5 - a)
+    assert numpy.array_equal((A * W).numpy(), a * w[:, None])
+    assert numpy.allclose((A ** 2).numpy(), a ** 2, rtol=0, atol=0)
+    assert abs(A.sum() - a.sum()) < 1e-10
+    assert abs(numpy.sum(A * B) - (a * b).sum()) < 1e-10
+    cols = [DeviceArray.from_host(a[:, i].copy()) for i in range(3)]
+    S = numpy.stack(cols, axis=-1)
+    assert isinstance(S, DeviceArray) and numpy.array_equal(S.numpy(), a)
+    T = numpy.take(A, 1, axis=-1)
+    assert isinstance(T, DeviceArray) and numpy.array_equal(T.numpy(), a[:, 1])
+    assert numpy.array_equal((A + b).numpy(), a + b)  # host operand is uploaded
+
+
+def test_paint_readout_adjoint_large(device_pm):
+    """size-independent property at a BASELINE-size problem: <paint(x, m), g> == <m, readout(g, x)>"""
+    from vmad_b200.pm import DeviceArray
+    import torch
+    N = 256
+    dpm = device_pm([N, N, N], 800.0)
+    g = torch.Generator(device='cuda').manual_seed(11)
+    n = 1 << 24
+    x = DeviceArray(torch.rand((n, 3), generator=g, device='cuda', dtype=torch.float64) * 800.0)
+    m = DeviceArray(torch.rand((n,), generator=g, device='cuda', dtype=torch.float64) + 0.5)
+    f = dpm.create('real')
+    f.t.copy_(torch.randn((N, N, N), generator=g, device='cuda', dtype=torch.float64))
+    lhs = dpm.paint(x, m).dot(f)
+    rhs = f.readout(x).dot(m)
+    assert abs(lhs - rhs) < 1e-11 * abs(lhs)
+    total = dpm.paint(x, m).sum()
+    assert abs(total - m.sum()) < 1e-11 * total

@@ -1,0 +1,111 @@
+"""ctypes binding of libvmadpm.so (declared in include/vmadpm.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a
+context without a CUDA device, raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libvmadpm.so')
+
+
+class VpmError(RuntimeError):
+    pass
+
+
+class vpm_mesh(Structure):
+    _fields_ = [
+        ('n', c_int64 * 3),
+        ('scale', c_double * 3),
+        ('start0', c_int64),
+        ('nloc0', c_int64),
+        ('stride0', c_int64),
+        ('stride1', c_int64),
+        ('ghost', c_int32),
+        ('reserved', c_int32),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise VpmError(
+            "libvmadpm.so is not built (%s). Run `python -m vmad_b200.build` (needs nvcc). "
+            "vmad_b200 has no CPU path." % LIB_PATH)
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_P = c_void_p  # device pointers travel as integers
+_I3 = c_int64 * 3
+
+# name -> (restype, argtypes); every name here must be declared in include/vmadpm.h
+SIGNATURES = {
+    'vpm_ctx_create': (c_int, [POINTER(c_void_p), c_int, c_void_p]),
+    'vpm_ctx_destroy': (c_int, [c_void_p]),
+    'vpm_ctx_set_stream': (c_int, [c_void_p, c_void_p]),
+    'vpm_sync': (c_int, [c_void_p]),
+    'vpm_last_error': (c_char_p, []),
+    'vpm_version': (c_int, []),
+    'vpm_launch_count': (c_int64, []),
+    'vpm_device_sm_count': (c_int, [c_void_p, POINTER(c_int)]),
+    'vpm_cell_keys': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P]),
+    'vpm_layout_ncell': (c_int64, [POINTER(vpm_mesh)]),
+    'vpm_layout_build': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P, _P, _P]),
+    'vpm_take_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
+    'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
+    'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
+    'vpm_paint_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
+    'vpm_paint_jvp_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, _P, _P,
+                                     c_int64, _P, _P]),
+    'vpm_paint_atomic': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P]),
+    'vpm_readout': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int64, _P]),
+    'vpm_readout3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
+    'vpm_readout_grad': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, c_double, c_int64,
+                                 _P, _P]),
+    'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
+    'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
+    'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
+    'vpm_transfer': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double, c_int, _P, _P, _P,
+                             _P, _P, _P, c_int]),
+    'vpm_transfer_table': (c_int, [c_void_p, POINTER(c_int64), _P, _P, _P, POINTER(c_int64),
+                                   c_int, c_int]),
+    'vpm_force_kspace': (c_int, [c_void_p, POINTER(c_int64), _P, c_double, _P, _P, _P, _P, _P,
+                                 _P, _P, _P, _P, _P]),
+    'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),
+    'vpm_mul': (c_int, [c_void_p, c_int64, _P, _P, _P]),
+    'vpm_div': (c_int, [c_void_p, c_int64, _P, _P, _P]),
+    'vpm_mul_rows': (c_int, [c_void_p, c_int64, c_int, _P, _P, _P]),
+    'vpm_cmul': (c_int, [c_void_p, c_int64, _P, _P, c_int, _P]),
+    'vpm_fill': (c_int, [c_void_p, c_int64, c_double, _P]),
+    'vpm_stack': (c_int, [c_void_p, c_int64, c_int, POINTER(c_void_p), _P]),
+    'vpm_take_col': (c_int, [c_void_p, c_int64, c_int, c_int, _P, _P]),
+    'vpm_reduce_sum': (c_int, [c_void_p, c_int64, _P, POINTER(c_double)]),
+    'vpm_reduce_dot': (c_int, [c_void_p, c_int64, _P, _P, POINTER(c_double)]),
+    'vpm_reduce_cdot': (c_int, [c_void_p, POINTER(c_int64), c_int64, _P, _P, POINTER(c_double)]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(lib, _name)  # AttributeError here means header and library disagree
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def last_error():
+    msg = lib.vpm_last_error()
+    return msg.decode() if msg else ''
+
+
+def check(status):
+    if status != 0:
+        raise VpmError(last_error() or ('vmadpm call failed with status %d' % status))
+
+
+def launch_count():
+    return int(lib.vpm_launch_count())
+
+
+def i3(values):
+    return _I3(*[int(v) for v in values])

@@ -1,0 +1,1052 @@
+"""Device (B200) implementation of the pmesh object protocol that vmad's FastPM library calls.
+
+This is the host-side mirror of the reference-facing interface: ``ParticleMesh``, ``RealField``,
+``ComplexField``, ``Layout`` answer to the same methods, argument names and return conventions
+that ``/root/reference/vmad/lib/fastpm.py`` uses on pmesh objects (SURVEY.md Appendix A lists
+every call site), so that file -- or ``vmad_b200.lib.fastpm`` -- runs on top of it.  All
+arithmetic happens in libvmadpm.so (hand-written sm_100a kernels + cuFFT) through the C ABI in
+``include/vmadpm.h``; torch is used only to own device buffers and to name the stream.
+
+There is no CPU path: constructing a ParticleMesh without a CUDA device raises.
+"""
+import ctypes
+import numbers
+
+import numpy
+import torch
+
+from . import _capi as C
+
+_F8 = torch.float64
+_C16 = torch.complex128
+
+
+# ---------------------------------------------------------------------------------------------
+# runtime: one context per process / device
+# ---------------------------------------------------------------------------------------------
+class Runtime(object):
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise C.VpmError("vmad_b200 needs a CUDA device (B200, sm_100a); it has no CPU path")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device)
+        self._stream = torch.cuda.current_stream(self.device).cuda_stream
+        h = ctypes.c_void_p()
+        C.check(C.lib.vpm_ctx_create(ctypes.byref(h), device, ctypes.c_void_p(self._stream)))
+        self.ctx = h
+
+    def sync_stream(self):
+        """Follow torch's current stream (cheap when unchanged)."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != self._stream:
+            C.check(C.lib.vpm_ctx_set_stream(self.ctx, ctypes.c_void_p(s)))
+            self._stream = s
+
+    def synchronize(self):
+        C.check(C.lib.vpm_sync(self.ctx))
+
+    def empty(self, shape, dtype=_F8):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+
+_runtime = None
+
+
+def runtime():
+    global _runtime
+    if _runtime is None:
+        _runtime = Runtime()
+    return _runtime
+
+
+def synchronize():
+    runtime().synchronize()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _is_zero_literal(x):
+    # vmad's ZeroGradient is an int subclass equal to 0; the literal 0 marks "no gradient"
+    return isinstance(x, numbers.Number) and not isinstance(x, bool) and x == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# device arrays
+# ---------------------------------------------------------------------------------------------
+def _upload(a, dtype=None):
+    rt = runtime()
+    a = numpy.asarray(a)
+    if dtype is None:
+        dtype = numpy.complex128 if numpy.iscomplexobj(a) else numpy.float64
+    a = numpy.ascontiguousarray(a, dtype=dtype)
+    return torch.from_numpy(a).to(rt.device)
+
+
+class DeviceArray(object):
+    """fp64 (or complex128) array resident in HBM.
+
+    Satisfies what vmad's stdlib needs of a value on the tape (vmad/core/stdlib/operators.py
+    :14-152): ``+ - * /`` and negation with another array, a python scalar, or the literal
+    ``0``; plus ``len``, ``shape`` and the numpy functions the operator library applies to
+    particle arrays (``numpy.stack`` / ``numpy.take`` / ``numpy.sum``, vmad/lib/linalg.py:145-149,
+    256-262) via the ``__array_function__`` protocol.  Arrays are immutable by the operator
+    contract (the tape aliases them), so ``x + 0`` returns ``x`` itself.
+    """
+    __array_priority__ = 1000.0
+
+    def __init__(self, t, cellindex=None):
+        assert isinstance(t, torch.Tensor) and t.is_cuda
+        if not t.is_contiguous():
+            t = t.contiguous()
+        self.t = t
+        # set by Layout.exchange: the rows of this array are in cell-sorted order of `cellindex`
+        self._cellindex = cellindex
+
+    # -- construction helpers ---------------------------------------------------------
+    @classmethod
+    def from_host(kls, a):
+        return kls(_upload(a))
+
+    def _like(self, t):
+        r = DeviceArray(t)
+        return r
+
+    def _coerce(self, other):
+        """other -> torch tensor on device with this array's kind, or None if unsupported"""
+        if isinstance(other, DeviceArray):
+            return other.t
+        if isinstance(other, numpy.ndarray) and other.ndim > 0:
+            return _upload(other)
+        return None
+
+    # -- ndarray-ish surface ------------------------------------------------------------
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def ndim(self):
+        return self.t.dim()
+
+    @property
+    def size(self):
+        return self.t.numel()
+
+    @property
+    def dtype(self):
+        return numpy.dtype('c16') if self.t.is_complex() else numpy.dtype('f8')
+
+    @property
+    def is_complex(self):
+        return self.t.is_complex()
+
+    def __len__(self):
+        return self.t.shape[0]
+
+    def numpy(self):
+        return self.t.cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def copy(self):
+        return self._like(self.t.clone())
+
+    @property
+    def _ndouble(self):
+        return self.t.numel() * (2 if self.t.is_complex() else 1)
+
+    # -- arithmetic ---------------------------------------------------------------------
+    def _axpby(self, a, b=0.0, y=None, c=0.0):
+        rt = runtime()
+        rt.sync_stream()
+        out = torch.empty_like(self.t)
+        C.check(C.lib.vpm_axpby(rt.ctx, self._ndouble, a, _ptr(self.t), b, _ptr(y), c, _ptr(out)))
+        return self._like(out)
+
+    def _binary_same(self, o, fn, conj=0):
+        rt = runtime()
+        rt.sync_stream()
+        out = torch.empty_like(self.t)
+        if self.t.is_complex():
+            C.check(C.lib.vpm_cmul(rt.ctx, self.t.numel(), _ptr(self.t), _ptr(o), conj, _ptr(out)))
+        else:
+            C.check(fn(rt.ctx, self.t.numel(), _ptr(self.t), _ptr(o), _ptr(out)))
+        return self._like(out)
+
+    def _rows(self, w):
+        """self[n, k] * w[n]"""
+        rt = runtime()
+        rt.sync_stream()
+        out = torch.empty_like(self.t)
+        n = self.t.shape[0]
+        C.check(C.lib.vpm_mul_rows(rt.ctx, n, self.t.numel() // n, _ptr(self.t), _ptr(w), _ptr(out)))
+        return self._like(out)
+
+    @staticmethod
+    def _scalar(o):
+        if isinstance(o, numbers.Real) and not isinstance(o, bool):
+            return float(o)
+        if isinstance(o, numpy.ndarray) and o.ndim == 0 and o.dtype.kind in 'fiu':
+            return float(o)
+        return None
+
+    def __add__(self, o):
+        s = self._scalar(o)
+        if s is not None:
+            if s == 0.0:
+                return self
+            if self.t.is_complex():
+                raise TypeError("complex array + non-zero scalar is not supported")
+            return self._axpby(1.0, c=s)
+        y = self._coerce(o)
+        if y is None:
+            return NotImplemented
+        if y.shape != self.t.shape or y.is_complex() != self.t.is_complex():
+            raise ValueError("shape/dtype mismatch in add: %s vs %s" % (self.shape, tuple(y.shape)))
+        return self._axpby(1.0, 1.0, y)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        s = self._scalar(o)
+        if s is not None:
+            if s == 0.0:
+                return self
+            return self._axpby(1.0, c=-s)
+        y = self._coerce(o)
+        if y is None:
+            return NotImplemented
+        if y.shape != self.t.shape:
+            raise ValueError("shape mismatch in sub")
+        return self._axpby(1.0, -1.0, y)
+
+    def __rsub__(self, o):
+        s = self._scalar(o)
+        if s is not None:
+            return self._axpby(-1.0, c=s)
+        y = self._coerce(o)
+        if y is None:
+            return NotImplemented
+        return self._like(y)._axpby(1.0, -1.0, self.t)
+
+    def __neg__(self):
+        return self._axpby(-1.0)
+
+    def __pos__(self):
+        return self
+
+    def __mul__(self, o):
+        s = self._scalar(o)
+        if s is not None:
+            return self._axpby(s)
+        if isinstance(o, numbers.Complex):
+            raise TypeError("multiplication by a complex scalar is not supported")
+        y = self._coerce(o)
+        if y is None:
+            return NotImplemented
+        if y.shape == self.t.shape and y.is_complex() == self.t.is_complex():
+            return self._binary_same(y, C.lib.vpm_mul)
+        if (not y.is_complex()) and (not self.t.is_complex()):
+            # row scaling [n, k] * [n] or [n, k] * [n, 1]
+            if self.t.dim() == 2 and y.numel() == self.t.shape[0]:
+                return self._rows(y)
+            if y.dim() == 2 and self.t.numel() == y.shape[0]:
+                return self._like(y)._rows(self.t)
+        raise ValueError("unsupported shapes in mul: %s vs %s" % (self.shape, tuple(y.shape)))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        s = self._scalar(o)
+        if s is not None:
+            return self._axpby(1.0 / s)
+        y = self._coerce(o)
+        if y is None:
+            return NotImplemented
+        if y.shape != self.t.shape or self.t.is_complex():
+            raise ValueError("unsupported shapes in div")
+        return self._binary_same(y, C.lib.vpm_div)
+
+    def __rtruediv__(self, o):
+        s = self._scalar(o)
+        if s is None or self.t.is_complex():
+            return NotImplemented
+        rt = runtime()
+        rt.sync_stream()
+        num = torch.empty_like(self.t)
+        C.check(C.lib.vpm_fill(rt.ctx, num.numel(), s, _ptr(num)))
+        return self._like(num)._binary_same(self.t, C.lib.vpm_div)
+
+    def __pow__(self, p):
+        if p == 2:
+            return self * self
+        if p == 1:
+            return self
+        raise TypeError("only ** 1 and ** 2 are supported on device arrays")
+
+    def conj(self):
+        if not self.t.is_complex():
+            return self
+        rt = runtime()
+        rt.sync_stream()
+        out = torch.empty_like(self.t)
+        # conj(x) = 1 * conj(x): multiply the constant 1 by conj(x)
+        one = torch.empty_like(self.t)
+        C.check(C.lib.vpm_fill(rt.ctx, one.numel() * 2, 0.0, _ptr(one)))
+        one_r = torch.view_as_real(one)
+        one_r[..., 0] = 1.0
+        C.check(C.lib.vpm_cmul(rt.ctx, self.t.numel(), _ptr(one), _ptr(self.t), 1, _ptr(out)))
+        return self._like(out)
+
+    # -- reductions (synchronise: they return host scalars) -------------------------------
+    def sum(self, axis=None, dtype=None, out=None, **kw):
+        if axis is not None:
+            raise TypeError("only full reductions are supported on device arrays")
+        if self.t.is_complex():
+            raise TypeError("sum of a complex device array is not supported")
+        rt = runtime()
+        rt.sync_stream()
+        r = ctypes.c_double()
+        C.check(C.lib.vpm_reduce_sum(rt.ctx, self.t.numel(), _ptr(self.t), ctypes.byref(r)))
+        return r.value
+
+    def dot(self, o):
+        y = self._coerce(o)
+        rt = runtime()
+        rt.sync_stream()
+        r = ctypes.c_double()
+        C.check(C.lib.vpm_reduce_dot(rt.ctx, self._ndouble, _ptr(self.t), _ptr(y), ctypes.byref(r)))
+        return r.value
+
+    # -- stack / take ---------------------------------------------------------------------
+    def take(self, i, axis=-1):
+        if self.t.dim() != 2 or axis not in (-1, 1):
+            raise TypeError("take is supported along the last axis of [n, k] arrays")
+        rt = runtime()
+        rt.sync_stream()
+        n, k = self.t.shape
+        out = rt.empty((n,))
+        C.check(C.lib.vpm_take_col(rt.ctx, n, k, int(i), _ptr(self.t), _ptr(out)))
+        return DeviceArray(out, cellindex=self._cellindex)
+
+    # -- numpy protocol glue ----------------------------------------------------------------
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != '__call__' or kwargs.get('out') is not None:
+            return NotImplemented
+        if ufunc is numpy.multiply:
+            a, b = inputs
+            return b.__rmul__(a) if b is self and not isinstance(a, DeviceArray) else a.__mul__(b)
+        if ufunc is numpy.add:
+            a, b = inputs
+            return b.__radd__(a) if b is self and not isinstance(a, DeviceArray) else a.__add__(b)
+        if ufunc is numpy.subtract:
+            a, b = inputs
+            return b.__rsub__(a) if b is self and not isinstance(a, DeviceArray) else a.__sub__(b)
+        if ufunc in (numpy.true_divide, numpy.divide):
+            a, b = inputs
+            return b.__rtruediv__(a) if b is self and not isinstance(a, DeviceArray) else a.__truediv__(b)
+        if ufunc is numpy.negative:
+            return -inputs[0]
+        if ufunc is numpy.conjugate:
+            return inputs[0].conj()
+        return NotImplemented
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func is numpy.stack:
+            return stack(args[0], **kwargs) if len(args) == 1 else stack(*args, **kwargs)
+        if func is numpy.take:
+            a = args[0]
+            i = args[1] if len(args) > 1 else kwargs['indices']
+            axis = args[2] if len(args) > 2 else kwargs.get('axis', None)
+            return a.take(i, axis=axis)
+        if func is numpy.sum:
+            return args[0].sum(**{k: v for k, v in kwargs.items() if k == 'axis'})
+        if func is numpy.shape:
+            return args[0].shape
+        if func is numpy.conj or func is numpy.conjugate:
+            return args[0].conj()
+        if func is numpy.copy:
+            return args[0].copy()
+        return NotImplemented
+
+
+def stack(arrays, axis=-1):
+    """``numpy.stack`` of k ``[n]`` device arrays along the last axis -> ``[n, k]``."""
+    arrays = list(arrays)
+    if axis not in (-1, 1) or not all(isinstance(a, DeviceArray) and a.t.dim() == 1 for a in arrays):
+        raise TypeError("device stack supports 1-D arrays along the last axis")
+    rt = runtime()
+    rt.sync_stream()
+    n = arrays[0].t.shape[0]
+    k = len(arrays)
+    out = rt.empty((n, k))
+    cols = (ctypes.c_void_p * k)(*[a.t.data_ptr() for a in arrays])
+    C.check(C.lib.vpm_stack(rt.ctx, n, k, cols, _ptr(out)))
+    ci = arrays[0]._cellindex
+    if not all(a._cellindex is ci for a in arrays):
+        ci = None
+    return DeviceArray(out, cellindex=ci)
+
+
+def asdevice(x):
+    """numpy / DeviceArray -> DeviceArray (scalars and the literal 0 pass through)."""
+    if isinstance(x, DeviceArray):
+        return x
+    if isinstance(x, numpy.ndarray) and x.ndim > 0:
+        return DeviceArray.from_host(x)
+    return x
+
+
+def ashost(x):
+    if isinstance(x, DeviceArray):
+        return x.numpy()
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+# communicator shim (fastpm.py:196,251,422,596; lib/mpi.py:24,30,53,57; chisquare.py:32)
+# ---------------------------------------------------------------------------------------------
+class SelfComm(object):
+    rank = 0
+    size = 1
+
+    def allreduce(self, x, op=None):
+        return x
+
+    def barrier(self):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------
+# k-space filters recognised by the fused kernels
+# ---------------------------------------------------------------------------------------------
+class KList(list):
+    """``k`` argument of ``Field.apply`` callbacks; ``normp`` as in pmesh (fastpm.py:141,329)."""
+
+    def normp(self, p=2, zeromode=None):
+        r = 0
+        for ki in self:
+            r = r + numpy.abs(ki) ** p
+        r = numpy.array(r, dtype='f8')
+        if zeromode is not None:
+            r[r == 0] = zeromode
+        return r
+
+
+# ---------------------------------------------------------------------------------------------
+# fields
+# ---------------------------------------------------------------------------------------------
+class Field(DeviceArray):
+    def __init__(self, pm, t):
+        DeviceArray.__init__(self, t)
+        self.pm = pm
+
+    def _like(self, t):
+        return type(self)(self.pm, t)
+
+    @property
+    def value(self):
+        """Host copy of the field (read-only view semantics are not provided)."""
+        return self.numpy()
+
+    def __getitem__(self, index):
+        return self.numpy()[index]
+
+    def __setitem__(self, index, v):
+        if index is not Ellipsis and index != slice(None):
+            raise TypeError("device fields only support whole-array assignment")
+        self.t.copy_(self.pm._as_field_tensor(v, self.t.is_complex()))
+
+    def apply(self, func, kind='wavenumber', out=None):
+        """``Field.apply(func(k, v), kind=, out=)`` (fastpm.py:79,83,87; test_fastpm.py:56).
+
+        ``func`` is evaluated ONCE on the host with numpy coordinate vectors and ``v = 1``
+        to obtain the (broadcastable) multiplier table; the multiply itself is one device pass.
+        This covers every ``func`` that is linear in ``v`` (all transfer functions are).
+        """
+        if out is not None and out is not Ellipsis:
+            raise TypeError("device Field.apply supports out=None or Ellipsis")
+        table = func(self._coords(kind), 1.0)
+        r = self._apply_table(table)
+        if out is Ellipsis:
+            self.t = r.t
+            return self
+        return r
+
+
+class RealField(Field):
+    def _coords(self, kind):
+        pm = self.pm
+        xs = []
+        for d in range(pm.ndim):
+            shape = [1] * pm.ndim
+            shape[d] = int(pm.Nmesh[d])
+            i = numpy.arange(pm.Nmesh[d])
+            x = i if kind == 'index' else i * (pm.BoxSize[d] / pm.Nmesh[d])
+            xs.append(x.reshape(shape))
+        return KList(xs)
+
+    def _apply_table(self, table):
+        table = numpy.broadcast_to(numpy.asarray(table, dtype='f8'), self.pm.rshape)
+        return self * table
+
+    def r2c(self, out=None):
+        """fastpm.py:50,56: ``rfftn / Ntot``."""
+        return self.pm._r2c(self, 1.0 / self.pm.Ntot)
+
+    def c2r_vjp(self, out=None):
+        """fastpm.py:67: ``Ntot * r2c`` (plain forward transform; cotangent convention as in
+        the oracle, pinned by test_fastpm.py:101-116)."""
+        return self.pm._r2c(self, 1.0)
+
+    def cnorm(self):
+        """fastpm.py:15."""
+        return self.pm.comm.allreduce(self.dot(self))
+
+    def cdot(self, other):
+        """fastpm.py:21."""
+        return self.pm.comm.allreduce(self.dot(self.pm._as_field(other, False)))
+
+    def cdot_vjp(self, v):
+        return self * v
+
+    def readout(self, pos, layout=None, resampler=None, out=None):
+        """fastpm.py:252."""
+        return self.pm._readout(self, pos, layout)
+
+    def readout_vjp(self, pos, v, layout=None, resampler=None):
+        """fastpm.py:256: returns ``(_mesh, _pos)``."""
+        return self.pm._readout_vjp(self, pos, v, layout)
+
+    def readout_jvp(self, pos, v_self=None, v_pos=None, layout=None, resampler=None):
+        """fastpm.py:263."""
+        return self.pm._readout_jvp(self, pos, v_self, v_pos, layout)
+
+
+class ComplexField(Field):
+    def _coords(self, kind):
+        pm = self.pm
+        ks = []
+        for d in range(pm.ndim):
+            shape = [1] * pm.ndim
+            shape[d] = pm.cshape[d]
+            j = pm.freq_index(d)
+            if kind == 'index':
+                k = j
+            elif kind == 'circular':
+                k = j * (2 * numpy.pi / pm.Nmesh[d])
+            elif kind == 'wavenumber':
+                k = j * (2 * numpy.pi / pm.BoxSize[d])
+            else:
+                raise ValueError("kind must be wavenumber, circular or index")
+            ks.append(k.reshape(shape))
+        return KList(ks)
+
+    def _apply_table(self, table, conj=False):
+        return self.pm._transfer_table(self, numpy.asarray(table), conj)
+
+    def c2r(self, out=None):
+        """fastpm.py:64,70: un-normalised inverse."""
+        return self.pm._c2r(self, 1.0)
+
+    def r2c_vjp(self, out=None):
+        """fastpm.py:53: ``c2r / Ntot``."""
+        return self.pm._c2r(self, 1.0 / self.pm.Ntot)
+
+    def _cdot_raw(self, other):
+        pm = self.pm
+        rt = runtime()
+        rt.sync_stream()
+        o = pm._as_field(other, True)
+        r = (ctypes.c_double * 2)()
+        C.check(C.lib.vpm_reduce_cdot(rt.ctx, C.i3(pm._cshape3), int(pm.Nmesh[-1]), _ptr(self.t),
+                                      _ptr(o.t), r))
+        return complex(r[0], r[1])
+
+    def cnorm(self):
+        return self.pm.comm.allreduce(self._cdot_raw(self).real)
+
+    def cdot(self, other):
+        """fastpm.py:519,527: sum over the full spectrum of ``x conj(y)``."""
+        return self.pm.comm.allreduce(self._cdot_raw(other))
+
+    def cdot_vjp(self, v):
+        """fastpm.py:522-523."""
+        return self * v
+
+    def _expand_hermitian(self, i, v):
+        N = int(self.pm.Nmesh[-1])
+        mask = (i[-1] != 0) & (numpy.abs(i[-1]) != N // 2)
+        return v * (1 + mask)
+
+
+# ---------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------
+class Layout(object):
+    """Result of ``pm.decompose`` (fastpm.py:272): the stable cell-key sort of the particles.
+
+    ``exchange`` delivers rows in cell-sorted order (and tags them so ``paint`` can use the
+    sorted kernel without re-sorting); ``gather`` is its adjoint (fastpm.py:281-308).
+    """
+
+    def __init__(self, pm, keys, perm, cell_start, oldlength):
+        self.pm = pm
+        self.keys = keys            # int32 [np]   cell key of every input particle
+        self.indices = perm         # int32 [np]   slot -> input particle (stable)
+        self.cell_start = cell_start  # int32 [ncell + 1]
+        self.oldlength = oldlength
+        self.newlength = int(perm.shape[0])
+
+    def exchange(self, data):
+        """fastpm.py:289,301,308."""
+        data = asdevice(data)
+        if not isinstance(data, DeviceArray):
+            raise TypeError("exchange needs an array")
+        rt = runtime()
+        rt.sync_stream()
+        t = data.t
+        n = self.newlength
+        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        out = rt.empty((n,) + tuple(t.shape[1:]))
+        C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, _ptr(out)))
+        return DeviceArray(out, cellindex=self)
+
+    def gather(self, data, mode='sum'):
+        """fastpm.py:286,293,304."""
+        data = asdevice(data)
+        if not isinstance(data, DeviceArray):
+            raise TypeError("gather needs an array")
+        rt = runtime()
+        rt.sync_stream()
+        t = data.t
+        n = self.newlength
+        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        # single rank: the permutation is a bijection, every output row is written once
+        out = rt.empty((self.oldlength,) + tuple(t.shape[1:]))
+        C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, _ptr(out)))
+        return DeviceArray(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# particle mesh
+# ---------------------------------------------------------------------------------------------
+class ParticleMesh(object):
+    """``ParticleMesh(Nmesh, BoxSize, comm, dtype='f8', resampler='cic')`` (fastpm.py:542-546)."""
+
+    def __init__(self, Nmesh, BoxSize, comm=None, dtype='f8', resampler='cic', np=None):
+        Nmesh = numpy.array(Nmesh, dtype='i8').ravel()
+        ndim = len(Nmesh)
+        if ndim not in (2, 3):
+            raise ValueError("only 2-D and 3-D meshes")
+        box = numpy.empty(ndim, dtype='f8')
+        box[...] = BoxSize
+        if numpy.dtype(dtype) != numpy.dtype('f8'):
+            raise ValueError("vmad_b200 computes in fp64 only")
+        if resampler != 'cic':
+            raise ValueError("only the CIC resampler is implemented")
+        self.rt = runtime()
+        self.Nmesh = Nmesh
+        self.BoxSize = box
+        self.ndim = ndim
+        self.comm = comm if comm is not None else SelfComm()
+        self.dtype = numpy.dtype(dtype)
+        self.resampler = resampler
+        self.rshape = tuple(int(n) for n in Nmesh)
+        self.cshape = tuple(int(n) for n in Nmesh[:-1]) + (int(Nmesh[-1]) // 2 + 1,)
+        self.Ntot = int(Nmesh.prod())
+        self.scale = self.Nmesh / self.BoxSize  # the one rounded fp64 scale (as in the oracle)
+
+        # 3-D geometry handed to the C ABI (2-D meshes are [1, N1, N2])
+        n3 = [1] * (3 - ndim) + [int(n) for n in Nmesh]
+        s3 = [1.0] * (3 - ndim) + [float(s) for s in self.scale]
+        self._n3 = n3
+        self._cshape3 = [n3[0], n3[1], n3[2] // 2 + 1]
+        m = C.vpm_mesh()
+        for d in range(3):
+            m.n[d] = n3[d]
+            m.scale[d] = s3[d]
+        m.start0 = 0
+        m.nloc0 = n3[0]
+        m.stride1 = n3[2]
+        m.stride0 = n3[1] * n3[2]
+        m.ghost = 0
+        self._mesh = m
+        self._ncell = int(C.lib.vpm_layout_ncell(ctypes.byref(m)))
+        self._tables = {}
+
+    # -- host-side tables ---------------------------------------------------------------
+    def freq_index(self, d):
+        N = int(self.Nmesh[d])
+        j = numpy.arange(self.cshape[d], dtype='i8')
+        j[j >= N // 2] -= N
+        return j
+
+    def _k_table(self, d3):
+        """device wavenumber vector along 3-D axis d3 (zeros for the dummy axis of 2-D)"""
+        key = ('k', d3)
+        if key not in self._tables:
+            d = d3 - (3 - self.ndim)
+            if d < 0:
+                k = numpy.zeros(1)
+            else:
+                k = self.freq_index(d) * (2 * numpy.pi / self.BoxSize[d])
+            self._tables[key] = _upload(k)
+        return self._tables[key]
+
+    def _axis_table(self, key, d, values):
+        """device complex table along mesh axis d (cached under key)"""
+        if key not in self._tables:
+            v = numpy.ascontiguousarray(values, dtype='c16')
+            assert v.shape == (self.cshape[d],)
+            self._tables[key] = _upload(v)
+        return self._tables[key]
+
+    # -- conversions ----------------------------------------------------------------------
+    def _as_field_tensor(self, value, is_complex):
+        shape = self.cshape if is_complex else self.rshape
+        dtype = _C16 if is_complex else _F8
+        if isinstance(value, DeviceArray):
+            t = value.t
+            if tuple(t.shape) != shape:
+                raise ValueError("field shape mismatch: %s vs %s" % (tuple(t.shape), shape))
+            return t
+        if isinstance(value, numbers.Number):
+            return torch.full(shape, value, dtype=dtype, device=self.rt.device)
+        a = numpy.broadcast_to(numpy.asarray(value), shape)
+        return _upload(a, numpy.complex128 if is_complex else numpy.float64)
+
+    def _as_field(self, value, is_complex):
+        kls = ComplexField if is_complex else RealField
+        if isinstance(value, kls) and value.pm is self:
+            return value
+        return kls(self, self._as_field_tensor(value, is_complex))
+
+    def create(self, type=None, value=None, mode=None):
+        """fastpm.py:29,39,52,55,66,69,228,262."""
+        type = type if type is not None else mode
+        if type not in ('real', 'complex'):
+            raise ValueError("type must be 'real' or 'complex'")
+        is_complex = type == 'complex'
+        if value is None:
+            value = 0.0
+        if isinstance(value, DeviceArray) and not (isinstance(value, Field) and value.pm is self):
+            return (ComplexField if is_complex else RealField)(
+                self, self._as_field_tensor(value, is_complex))
+        return self._as_field(value, is_complex)
+
+    def generate_uniform_particle_grid(self, shift=0.5, dtype='f8', return_host=False):
+        """``(i + shift) * BoxSize / Nmesh``, C order, ``[Np, ndim]`` (fastpm.py:532)."""
+        cell = self.BoxSize / self.Nmesh
+        axes = [(numpy.arange(n) + shift) * cell[d] for d, n in enumerate(self.rshape)]
+        grid = numpy.meshgrid(*axes, indexing='ij')
+        q = numpy.stack([g.ravel() for g in grid], axis=-1).astype('f8')
+        return q if return_host else DeviceArray.from_host(q)
+
+    def generate_whitenoise(self, seed, unitary=False, type='complex', mean=0.0, mode=None,
+                            return_host=False):
+        """Seeded white noise with unit variance per complex mode (numpy ``default_rng``; pmesh's
+        own generator is not reproducible here).  Generated on the host."""
+        type = mode if mode is not None else type
+        rng = numpy.random.default_rng(seed)
+        g = rng.standard_normal(self.rshape)
+        c = numpy.fft.rfftn(g) / self.Ntot ** 0.5
+        if unitary:
+            a = numpy.abs(c)
+            a[a == 0] = 1.0
+            c = c / a
+        c[(0,) * self.ndim] = mean
+        if type == 'real':
+            r = numpy.fft.irfftn(c, s=self.rshape) * self.Ntot
+            return r if return_host else self.create('real', value=r)
+        return c if return_host else self.create('complex', value=c)
+
+    # -- positions --------------------------------------------------------------------------
+    def _pos3(self, pos):
+        """positions as a contiguous [Np, 3] device tensor (2-D gets a zero first column)"""
+        pos = asdevice(pos)
+        if not isinstance(pos, DeviceArray):
+            raise TypeError("positions must be an array")
+        t = pos.t
+        if t.dim() != 2 or t.shape[1] != self.ndim:
+            raise ValueError("positions must be [Np, %d]" % self.ndim)
+        if self.ndim == 2:
+            t3 = torch.zeros((t.shape[0], 3), dtype=_F8, device=t.device)
+            t3[:, 1:] = t
+            return pos, t3
+        return pos, t
+
+    def _grad_from3(self, g3):
+        if self.ndim == 2:
+            return g3[:, 1:].contiguous()
+        return g3
+
+    # -- decompose (fastpm.py:272) ------------------------------------------------------------
+    def cell_keys(self, pos):
+        rt = self.rt
+        rt.sync_stream()
+        _, x3 = self._pos3(pos)
+        n = x3.shape[0]
+        keys = rt.empty((n,), torch.int32)
+        C.check(C.lib.vpm_cell_keys(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), n, _ptr(keys)))
+        return keys
+
+    def decompose(self, pos, smoothing=None):
+        rt = self.rt
+        rt.sync_stream()
+        _, x3 = self._pos3(pos)
+        n = x3.shape[0]
+        keys = rt.empty((n,), torch.int32)
+        perm = rt.empty((n,), torch.int32)
+        cell_start = rt.empty((self._ncell + 1,), torch.int32)
+        C.check(C.lib.vpm_layout_build(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), n, _ptr(keys),
+                                       _ptr(perm), _ptr(cell_start)))
+        return Layout(self, keys, perm, cell_start, n)
+
+    def _sorted(self, pos, layout, extras=()):
+        """Return (layout, xs3, extras_sorted): particles in cell-sorted order.
+
+        ``pos`` already tagged by ``Layout.exchange`` of a layout of this mesh is used as is.
+        """
+        pos = asdevice(pos)
+        if layout is None and isinstance(pos, DeviceArray) and pos._cellindex is not None \
+                and pos._cellindex.pm is self:
+            lay = pos._cellindex
+            _, x3 = self._pos3(pos)
+            return lay, x3, [asdevice(e) for e in extras], False
+        if layout is None:
+            layout = self.decompose(pos)
+        xs = layout.exchange(pos)
+        _, x3 = self._pos3(xs)
+        ex = []
+        for e in extras:
+            e = asdevice(e)
+            ex.append(layout.exchange(e) if isinstance(e, DeviceArray) else e)
+        return layout, x3, ex, True
+
+    # -- paint family (fastpm.py:224,229,238) ---------------------------------------------------
+    def paint(self, pos, mass=1.0, layout=None, hold=False, out=None, resampler=None):
+        rt = self.rt
+        lay, x3, (mass,), _ = self._sorted(pos, layout, (mass,))
+        rt.sync_stream()
+        marr = mass.t if isinstance(mass, DeviceArray) else None
+        m0 = 1.0 if marr is not None else float(mass)
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_paint_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr), m0,
+                                       x3.shape[0], _ptr(lay.cell_start), _ptr(o)))
+        return RealField(self, o)
+
+    def paint_vjp(self, v, pos, layout=None, mass=1.0, resampler=None):
+        """returns ``(_pos, _mass)`` (fastpm.py:229)."""
+        rt = self.rt
+        v = self._as_field(v, False)
+        pos = asdevice(pos)
+        mass = asdevice(mass)
+        if layout is not None:
+            xs = layout.exchange(pos)
+            ms = layout.exchange(mass) if isinstance(mass, DeviceArray) else mass
+        else:
+            xs, ms = pos, mass
+        _, x3 = self._pos3(xs)
+        rt.sync_stream()
+        n = x3.shape[0]
+        marr = ms.t if isinstance(ms, DeviceArray) else None
+        m0 = 1.0 if marr is not None else float(ms)
+        val = rt.empty((n,))
+        g3 = rt.empty((n, 3))
+        C.check(C.lib.vpm_readout_grad(rt.ctx, ctypes.byref(self._mesh), _ptr(v.t), _ptr(x3),
+                                       _ptr(marr), m0, n, _ptr(val), _ptr(g3)))
+        _pos = DeviceArray(self._grad_from3(g3))
+        _mass = DeviceArray(val)
+        if layout is not None:
+            _pos = layout.gather(_pos)
+            _mass = layout.gather(_mass)
+        return _pos, _mass
+
+    def paint_jvp(self, pos, v_mass=None, mass=1.0, v_pos=None, layout=None, resampler=None):
+        """fastpm.py:238."""
+        rt = self.rt
+        if v_pos is None and v_mass is None:
+            return self.create('real')
+        if v_pos is None:
+            return self.paint(pos, mass=v_mass, layout=layout)
+        extras = (mass, v_pos, v_mass)
+        lay, x3, (mass, v_pos, v_mass), _ = self._sorted(pos, layout, extras)
+        rt.sync_stream()
+        _, vp3 = self._pos3(v_pos)
+        marr = mass.t if isinstance(mass, DeviceArray) else None
+        m0 = 1.0 if marr is not None else float(mass)
+        if v_mass is not None and not isinstance(v_mass, DeviceArray):
+            vm = torch.full((x3.shape[0],), float(v_mass), dtype=_F8, device=rt.device)
+        else:
+            vm = v_mass.t if v_mass is not None else None
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_paint_jvp_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr),
+                                           m0, _ptr(vp3), _ptr(vm), x3.shape[0],
+                                           _ptr(lay.cell_start), _ptr(o)))
+        return RealField(self, o)
+
+    def paint_atomic(self, pos, mass=1.0):
+        """Baseline scatter with global fp64 atomics (for the atomic-throughput comparison)."""
+        rt = self.rt
+        _, x3 = self._pos3(pos)
+        mass = asdevice(mass)
+        rt.sync_stream()
+        marr = mass.t if isinstance(mass, DeviceArray) else None
+        m0 = 1.0 if marr is not None else float(mass)
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_paint_atomic(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr), m0,
+                                       x3.shape[0], _ptr(o)))
+        return RealField(self, o)
+
+    # -- readout family (fastpm.py:252,256,263) ----------------------------------------------------
+    def _readout(self, field, pos, layout):
+        rt = self.rt
+        pos = asdevice(pos)
+        xs = layout.exchange(pos) if layout is not None else pos
+        _, x3 = self._pos3(xs)
+        rt.sync_stream()
+        n = x3.shape[0]
+        val = rt.empty((n,))
+        C.check(C.lib.vpm_readout(rt.ctx, ctypes.byref(self._mesh), _ptr(field.t), _ptr(x3), n,
+                                  _ptr(val)))
+        r = DeviceArray(val, cellindex=xs._cellindex if layout is None else None)
+        if layout is not None:
+            r = layout.gather(r)
+        return r
+
+    def readout3(self, f0, f1, f2, pos):
+        """Three fields read at once into ``[Np, 3]`` (readout x3 + linalg.stack fused)."""
+        rt = self.rt
+        pos = asdevice(pos)
+        _, x3 = self._pos3(pos)
+        rt.sync_stream()
+        n = x3.shape[0]
+        val = rt.empty((n, 3))
+        C.check(C.lib.vpm_readout3(rt.ctx, ctypes.byref(self._mesh), _ptr(f0.t), _ptr(f1.t),
+                                   _ptr(f2.t), _ptr(x3), n, _ptr(val)))
+        return DeviceArray(val, cellindex=pos._cellindex)
+
+    def _readout_vjp(self, field, pos, v, layout):
+        rt = self.rt
+        pos = asdevice(pos)
+        v = asdevice(v)
+        if layout is not None:
+            xs = layout.exchange(pos)
+            vs = layout.exchange(v)
+        else:
+            xs, vs = pos, v
+        # mesh half: paint with mass = v (sorted kernel; sorts here if xs is not tagged)
+        _mesh = self.paint(xs, mass=vs, layout=None)
+        _, x3 = self._pos3(xs)
+        rt.sync_stream()
+        n = x3.shape[0]
+        g3 = rt.empty((n, 3))
+        C.check(C.lib.vpm_readout_grad(rt.ctx, ctypes.byref(self._mesh), _ptr(field.t), _ptr(x3),
+                                       _ptr(vs.t), 1.0, n, None, _ptr(g3)))
+        _pos = DeviceArray(self._grad_from3(g3))
+        if layout is not None:
+            _pos = layout.gather(_pos)
+        return _mesh, _pos
+
+    def _readout_jvp(self, field, pos, v_self, v_pos, layout):
+        rt = self.rt
+        pos = asdevice(pos)
+        if v_self is None and v_pos is None:
+            return 0
+        if layout is not None:
+            xs = layout.exchange(pos)
+            v_pos = layout.exchange(v_pos) if v_pos is not None else None
+        else:
+            xs = pos
+        _, x3 = self._pos3(xs)
+        fdot = self._as_field(v_self, False).t if v_self is not None else None
+        xdot = self._pos3(v_pos)[1] if v_pos is not None else None
+        rt.sync_stream()
+        n = x3.shape[0]
+        val = rt.empty((n,))
+        C.check(C.lib.vpm_readout_jvp(rt.ctx, ctypes.byref(self._mesh), _ptr(field.t), _ptr(fdot),
+                                      _ptr(x3), _ptr(xdot), n, _ptr(val)))
+        r = DeviceArray(val)
+        if layout is not None:
+            r = layout.gather(r)
+        return r
+
+    # -- FFT (fastpm.py:50,53,56,64,67,70) ------------------------------------------------------------
+    def _r2c(self, real, scale):
+        rt = self.rt
+        rt.sync_stream()
+        o = rt.empty(self.cshape, _C16)
+        C.check(C.lib.vpm_r2c(rt.ctx, C.i3(self._n3), _ptr(real.t), _ptr(o), float(scale)))
+        return ComplexField(self, o)
+
+    def _c2r(self, cplx, scale):
+        rt = self.rt
+        rt.sync_stream()
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_c2r(rt.ctx, C.i3(self._n3), _ptr(cplx.t), _ptr(o), float(scale)))
+        return RealField(self, o)
+
+    # -- k-space (fastpm.py:79,83,87) ---------------------------------------------------------------
+    def _transfer(self, cplx, scale=1.0, laplace=False, tables=(None, None, None), conj=False):
+        """out = in * scale * [-1/k^2] * prod_d tables[d][i_d]; tables indexed by mesh axis"""
+        rt = self.rt
+        rt.sync_stream()
+        o = rt.empty(self.cshape, _C16)
+        off = 3 - self.ndim
+        a = [None, None, None]
+        for d, t in enumerate(tables[:self.ndim]):
+            a[d + off] = t
+        C.check(C.lib.vpm_transfer(rt.ctx, C.i3(self._cshape3), _ptr(cplx.t), _ptr(o), float(scale),
+                                   1 if laplace else 0, _ptr(self._k_table(0)),
+                                   _ptr(self._k_table(1)), _ptr(self._k_table(2)), _ptr(a[0]),
+                                   _ptr(a[1]), _ptr(a[2]), 1 if conj else 0))
+        return ComplexField(self, o)
+
+    def _transfer_table(self, cplx, table, conj=False):
+        """generic multiplier: a broadcastable host table (any axis may have length 1)"""
+        rt = self.rt
+        table = numpy.asarray(table)
+        if table.ndim == 0:
+            table = table.reshape((1,) * self.ndim)
+        if table.ndim != self.ndim:
+            raise ValueError("transfer table must be broadcastable to %s" % (self.cshape,))
+        is_c = numpy.iscomplexobj(table)
+        tt = _upload(table, numpy.complex128 if is_c else numpy.float64)
+        strides = []
+        acc = 1
+        for d in reversed(range(self.ndim)):
+            if table.shape[d] == 1:
+                strides.append(0)
+            elif table.shape[d] == self.cshape[d]:
+                strides.append(acc)
+                acc *= table.shape[d]
+            else:
+                raise ValueError("transfer table shape %s does not broadcast to %s"
+                                 % (table.shape, self.cshape))
+        strides = [0] * (3 - self.ndim) + list(reversed(strides))
+        rt.sync_stream()
+        o = rt.empty(self.cshape, _C16)
+        C.check(C.lib.vpm_transfer_table(rt.ctx, C.i3(self._cshape3), _ptr(cplx.t), _ptr(o),
+                                         _ptr(tt), C.i3(strides), 1 if is_c else 0,
+                                         1 if conj else 0))
+        return ComplexField(self, o)
+
+    def force_kspace(self, rhok, scale, grad_tables, want_p=True):
+        """fused ``gravity`` k-space pass (fastpm.py:424-431); 3-D only"""
+        rt = self.rt
+        rt.sync_stream()
+        assert self.ndim == 3
+        p = rt.empty(self.cshape, _C16) if want_p else None
+        g = [rt.empty(self.cshape, _C16) for _ in range(3)]
+        C.check(C.lib.vpm_force_kspace(rt.ctx, C.i3(self._cshape3), _ptr(rhok.t), float(scale),
+                                       _ptr(self._k_table(0)), _ptr(self._k_table(1)),
+                                       _ptr(self._k_table(2)), _ptr(grad_tables[0]),
+                                       _ptr(grad_tables[1]), _ptr(grad_tables[2]), _ptr(p),
+                                       _ptr(g[0]), _ptr(g[1]), _ptr(g[2])))
+        return (ComplexField(self, p) if want_p else None), [ComplexField(self, t) for t in g]
