@@ -17,7 +17,7 @@ With ' = d/dlna:   D1'' + (2 + dlnE/dlna) D1' = 3/2 Om(a) D1
 started at a0 = 1e-7 on the matter-dominated solution D1 = a, D2 = -3/7 a^2.
 fastpm-python integrates with scipy ``odeint`` at default tolerance (~1e-8) and
 interpolates linearly in ``ln a`` between the support points; here the
-tolerance is tightened to 1e-13 so that the oracle and the product (which use
+tolerance is tightened (rtol 1e-13, no absolute floor: D2 starts at 1e-14) so that the oracle and the product (which use
 different integrators) agree far below the 1e-10 parity bar.
 """
 import numpy as np
@@ -47,7 +47,7 @@ class MatterDominated(object):
 
         a0 = np.exp(lna[0])
         y0 = [a0, a0, -3. / 7 * a0 ** 2, -6. / 7 * a0 ** 2]
-        y = odeint(self._ode, y0, lna, tfirst=False, rtol=1e-13, atol=1e-13, mxstep=100000)
+        y = odeint(self._ode, y0, lna, tfirst=False, rtol=1e-13, atol=1e-30, mxstep=100000)
 
         v1 = [y[:, 0], y[:, 1]]
         v1.append(np.array([self._ode(yi, li)[1] for yi, li in zip(y, lna)]))

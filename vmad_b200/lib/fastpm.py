@@ -1,0 +1,509 @@
+"""FastPM operator library: the names, signatures and semantics of ``vmad.lib.fastpm``.
+
+Every operator here answers to the same name, argument order, ``ain`` / ``aout`` and vjp / jvp
+conventions as its counterpart in ``/root/reference/vmad/lib/fastpm.py`` (cited per operator),
+so model / autooperator graphs written against the reference library run unchanged.  The
+operators speak the pmesh object protocol and therefore run on any
+backend that implements it; on ``vmad_b200.pm`` (the B200 backend) the k-space operators take
+fused single-pass kernels because the library's own filters (``fourier_space_laplace``,
+``fourier_space_neg_gradient``) are recognisable objects rather than anonymous closures.
+
+Additions named by BASELINE.json ``north_star`` (absent from the reference):
+the fused operators ``force``, ``kick`` and ``drift`` -- see the end of this file.
+"""
+import numpy
+
+from ..background import MatterDominated
+from ..pm import ParticleMesh  # noqa: F401  (same re-export as the reference, fastpm.py:6)
+from ..vm import autooperator, operator
+from ..vm.ops import ZeroGradient
+from . import linalg
+
+
+def _is_zero(x):
+    return ZeroGradient.is_zero(x)
+
+
+def _localize(q, pm):
+    """particle arrays enter the graph once: put them where the mesh lives"""
+    f = getattr(pm, 'asparticles', None)
+    return f(q) if f is not None else q
+
+
+# ---------------------------------------------------------------------------------------------
+# field <-> scalar, entry points
+# ---------------------------------------------------------------------------------------------
+@operator
+class to_scalar:
+    """fastpm.py:9-21 -- ``y = sum x^2`` (``Field.cnorm``)"""
+    ain = {'x': 'RealField'}
+    aout = {'y': '*'}
+
+    def apl(node, x):
+        return dict(y=x.cnorm())
+
+    def vjp(node, _y, x):
+        return dict(_x=x * (2 * _y))
+
+    def jvp(node, x_, x):
+        return dict(y_=x.cdot(x_) * 2)
+
+
+@operator
+class as_complex_field:
+    """fastpm.py:23-42 -- ``[..., 2]`` real pairs -> ComplexField"""
+    ain = {'x': '*'}
+    aout = {'y': 'ComplexField'}
+
+    def apl(node, x, pm):
+        x = numpy.asarray(x)
+        return dict(y=pm.create(type='complex', value=x[..., 0] + 1j * x[..., 1]))
+
+    def vjp(node, _y, pm):
+        _y = numpy.asarray(_y)
+        return dict(_x=numpy.stack([_y.real, _y.imag], axis=-1))
+
+    def jvp(node, x_, pm):
+        x_ = numpy.asarray(x_)
+        return dict(y_=pm.create(type='complex', value=x_[..., 0] + 1j * x_[..., 1]))
+
+
+# ---------------------------------------------------------------------------------------------
+# transforms
+# ---------------------------------------------------------------------------------------------
+@operator
+class r2c:
+    """fastpm.py:44-56"""
+    ain = {'x': 'RealField'}
+    aout = {'y': 'ComplexField'}
+
+    def apl(node, x):
+        return dict(y=x.r2c(), pm=x.pm)
+
+    def vjp(node, _y, pm):
+        return dict(_x=pm.create(type='complex', value=_y).r2c_vjp())
+
+    def jvp(node, x_, pm):
+        return dict(y_=pm.create(type='real', value=x_).r2c())
+
+
+@operator
+class c2r:
+    """fastpm.py:58-70"""
+    ain = {'x': 'ComplexField'}
+    aout = {'y': 'RealField'}
+
+    def apl(node, x):
+        return dict(y=x.c2r(), pm=x.pm)
+
+    def vjp(node, _y, pm):
+        return dict(_x=pm.create(type='real', value=_y).c2r_vjp())
+
+    def jvp(node, x_, pm):
+        return dict(y_=pm.create(type='complex', value=x_).c2r())
+
+
+# ---------------------------------------------------------------------------------------------
+# transfer functions
+# ---------------------------------------------------------------------------------------------
+class Filter(object):
+    """A transfer function of ``k`` that the device backend can apply with a fused kernel.
+
+    Calling the object with the ``k`` list (what ``Field.apply`` hands to its callback) returns
+    the multiplier like any plain function would, so it also works on a generic backend.
+    """
+
+    def __call__(self, k):
+        raise NotImplementedError
+
+    def apply_device(self, x, conj):
+        """``x * self(k)`` (or its conjugate) on a device ComplexField"""
+        raise NotImplementedError
+
+
+class _Laplace(Filter):
+    """fastpm.py:328-334 -- the Green's function ``-1 / k^2`` with the zero mode set to 0"""
+
+    def __call__(self, k):
+        k2 = k.normp(2)
+        bad = k2 == 0
+        k2[bad] = 1
+        k2 = -1 / k2
+        k2[bad] = 0
+        return k2
+
+    def apply_device(self, x, conj):
+        return x.pm._transfer(x, laplace=True)  # real multiplier: its own conjugate
+
+
+fourier_space_laplace = _Laplace()
+
+
+class _NegGradient(Filter):
+    """fastpm.py:310-326 -- ``-i k_d`` (order 0, with the Nyquist mask) or the 4-point finite
+    difference kernel ``-i (8 sin w - sin 2w) / (6 h)``, ``w = k_d h`` (order 1)"""
+
+    def __init__(self, dir, pm, order):
+        if order not in (0, 1):
+            raise ValueError("only order 0 and 1 are supported")
+        self.dir = dir
+        self.order = order
+        self.BoxSize = float(pm.BoxSize[dir])
+        self.Nmesh = int(pm.Nmesh[dir])
+
+    def __call__(self, k):
+        kd = k[self.dir]
+        if self.order == 0:
+            nyquist = numpy.pi / self.BoxSize * (self.Nmesh - 0.01)
+            return -1j * kd * (abs(kd) < nyquist)
+        cellsize = self.BoxSize / self.Nmesh
+        w = kd * cellsize
+        a = 1 / (6.0 * cellsize) * (8 * numpy.sin(w) - numpy.sin(2 * w))
+        return -1j * a
+
+    def apply_device(self, x, conj):
+        pm = x.pm
+        d = self.dir
+        key = ('neg_gradient', d, self.order, self.BoxSize, self.Nmesh)
+        if key not in pm._tables:
+            k1 = [None] * pm.ndim
+            k1[d] = pm.freq_index(d) * (2 * numpy.pi / pm.BoxSize[d])
+            pm._axis_table(key, d, self(k1))
+        tables = [None] * pm.ndim
+        tables[d] = pm._tables[key]
+        return pm._transfer(x, tables=tables, conj=conj)
+
+
+def fourier_space_neg_gradient(dir, pm, order):
+    return _NegGradient(dir, pm, order)
+
+
+def _apply_tf(x, tf, kind, conj):
+    if isinstance(tf, Filter) and kind == 'wavenumber' and hasattr(x.pm, '_transfer'):
+        return tf.apply_device(x, conj)
+    if conj:
+        return x.apply(lambda k, v: v * numpy.conj(tf(k)), kind=kind)
+    return x.apply(lambda k, v: v * tf(k), kind=kind)
+
+
+@operator
+class apply_transfer:
+    """fastpm.py:72-87 -- ``y_k = x_k tf(k)``; the vjp multiplies by ``conj(tf)``"""
+    ain = {'x': 'ComplexField'}
+    aout = {'y': 'ComplexField'}
+
+    def apl(node, x, tf, kind='wavenumber'):
+        return dict(y=_apply_tf(x, tf, kind, False))
+
+    def vjp(node, _y, tf, kind):
+        return dict(_x=_apply_tf(_y, tf, kind, True))
+
+    def jvp(node, x_, tf, kind):
+        return dict(y_=_apply_tf(x_, tf, kind, False))
+
+
+# ---------------------------------------------------------------------------------------------
+# particles <-> mesh
+# ---------------------------------------------------------------------------------------------
+@operator
+class paint:
+    """fastpm.py:215-240 -- CIC deposit of ``mass`` at ``x``"""
+    aout = {'mesh': 'RealField'}
+    ain = {'x': 'ndarray', 'layout': 'Layout', 'mass': 'ndarray'}
+
+    def apl(node, x, mass, layout, pm):
+        return dict(mesh=pm.paint(x, mass=mass, layout=layout, hold=False))
+
+    def vjp(node, _mesh, x, mass, layout, pm):
+        _mesh = pm.create(type='real', value=_mesh)
+        _x, _mass = pm.paint_vjp(_mesh, x, layout=layout, mass=mass)
+        return dict(_layout=0, _x=_x, _mass=_mass)
+
+    def jvp(node, x_, x, layout, mass, layout_, mass_, pm):
+        if _is_zero(x_):
+            x_ = None
+        if _is_zero(mass_):
+            mass_ = None
+        return dict(mesh_=pm.paint_jvp(x, v_mass=mass_, mass=mass, v_pos=x_, layout=layout))
+
+
+@operator
+class readout:
+    """fastpm.py:242-264 -- CIC interpolation of ``mesh`` at ``x`` (the reference's host-side
+    ``allreduce(len(x))`` at :251 is dropped: its result is unused and it is a sync point)"""
+    aout = {'value': 'ndarray'}
+    ain = {'x': 'ndarray', 'mesh': 'RealField', 'layout': 'Layout'}
+
+    def apl(node, mesh, x, layout, resampler=None):
+        return dict(value=mesh.readout(x, layout=layout, resampler=resampler), pm=mesh.pm)
+
+    def vjp(node, _value, x, layout, mesh, pm, resampler=None):
+        _mesh, _x = mesh.readout_vjp(x, _value, layout=layout, resampler=resampler)
+        return dict(_mesh=_mesh, _x=_x, _layout=0)
+
+    def jvp(node, x_, mesh_, x, layout, layout_, mesh, pm, resampler=None):
+        if _is_zero(mesh_):
+            mesh_ = None
+        if _is_zero(x_):
+            x_ = None
+        mesh = pm.create(type='real', value=mesh)
+        return dict(value_=mesh.readout_jvp(x, v_self=mesh_, v_pos=x_, layout=layout,
+                                            resampler=resampler))
+
+
+@operator
+class decompose:
+    """fastpm.py:266-278 -- particle routing; carries no gradient"""
+    aout = {'layout': 'Layout'}
+    ain = {'x': 'ndarray'}
+
+    def apl(node, x, pm):
+        return dict(layout=pm.decompose(x))
+
+    def vjp(node, _layout):
+        return dict(_x=0)
+
+    def jvp(node, x_):
+        return dict(layout_=0)
+
+
+@operator
+class gather:
+    """fastpm.py:280-293 -- return exchanged values to their home order, summing copies"""
+    aout = 'y'
+    ain = 'x', 'layout'
+
+    def apl(node, x, layout):
+        return dict(y=layout.gather(x))
+
+    def vjp(node, _y, layout):
+        return dict(_layout=0, _x=layout.exchange(_y))
+
+    def jvp(node, layout, layout_, x_):
+        return dict(y_=layout.gather(x_))
+
+
+@operator
+class exchange:
+    """fastpm.py:295-308 -- send values to the ranks (and the order) that own their cells"""
+    aout = 'y'
+    ain = 'x', 'layout'
+
+    def apl(node, x, layout):
+        return dict(y=layout.exchange(x))
+
+    def vjp(node, _y, layout):
+        return dict(_layout=0, _x=layout.gather(_y))
+
+    def jvp(node, layout, layout_, x_):
+        return dict(y_=layout.exchange(x_))
+
+
+# ---------------------------------------------------------------------------------------------
+# Lagrangian perturbation theory
+# ---------------------------------------------------------------------------------------------
+@autooperator('rhok,q->dx1')
+def lpt1(rhok, q, pm):
+    """fastpm.py:336-351 -- Zel'dovich displacement at ``q``; note that ``q`` is a
+    differentiable input of this operator"""
+    p = apply_transfer(rhok, fourier_space_laplace)
+    layout = decompose(q, pm)
+    r1 = []
+    for d in range(pm.ndim):
+        dx1_c = apply_transfer(p, fourier_space_neg_gradient(d, pm, order=1))
+        dx1_r = c2r(dx1_c)
+        r1.append(readout(dx1_r, q, layout))
+    return dict(dx1=linalg.stack(r1, axis=-1))
+
+
+@autooperator('rhok->rho_lpt2')
+def lpt2src(rhok, pm):
+    """fastpm.py:353-387 -- source of the second-order displacement,
+    ``3/7 (sum_{i<j} P_ii P_jj - P_ij^2)`` with ``P_ij`` the second derivatives of the potential"""
+    if pm.ndim != 3:
+        raise ValueError("LPT 2 only works in 3d")
+    D1 = [1, 2, 0]
+    D2 = [2, 0, 1]
+    potk = apply_transfer(rhok, fourier_space_laplace)
+
+    def second_derivative(i, j):
+        t = apply_transfer(potk, fourier_space_neg_gradient(i, pm, order=1))
+        t = apply_transfer(t, fourier_space_neg_gradient(j, pm, order=1))
+        return c2r(t)
+
+    Pii = [second_derivative(d, d) for d in range(pm.ndim)]
+    source = None
+    for d in range(pm.ndim):
+        term = Pii[D1[d]] * Pii[D2[d]]
+        source = term if source is None else source + term
+    for d in range(pm.ndim):
+        Pij = second_derivative(D1[d], D2[d])
+        source = source + (-Pij * Pij)
+    return dict(rho_lpt2=(3.0 / 7) * source)
+
+
+@autooperator('wnk->c')
+def induce_correlation(wnk, powerspectrum, pm):
+    """fastpm.py:389-396 -- colour white noise with ``sqrt(P(k) / V)``"""
+    volume = pm.BoxSize.prod()
+
+    def tf(k):
+        kk = sum(ki ** 2 for ki in k) ** 0.5
+        return (powerspectrum(kk) / volume) ** 0.5
+
+    return dict(c=apply_transfer(wnk, tf))
+
+
+@autooperator('rhok->dx1,dx2')
+def lpt(rhok, q, pm):
+    """fastpm.py:398-406"""
+    q = _localize(q, pm)
+    dx1 = lpt1(rhok, q, pm)
+    rhok2 = r2c(lpt2src(rhok, pm))
+    dx2 = lpt1(rhok2, q, pm)
+    return dict(dx1=dx1, dx2=dx2)
+
+
+# ---------------------------------------------------------------------------------------------
+# force, leapfrog, n-body
+# ---------------------------------------------------------------------------------------------
+def _gravity_body(dx, q, pm):
+    """shared by ``gravity`` (fastpm.py:409-438) and ``FastPMSimulation.gravity`` (:582-612)"""
+    q = _localize(q, pm)
+    x = q + dx
+    layout = decompose(x, pm)
+    xl = exchange(x, layout)
+    rho = paint(xl, 1.0, None, pm)
+    # mean density 1 (the particle count is reduced once, when the graph is built)
+    fac = 1.0 * pm.Nmesh.prod() / pm.comm.allreduce(len(q))
+    rho = rho * fac
+    rhok = r2c(rho)
+    p = apply_transfer(rhok, fourier_space_laplace)
+    r1 = []
+    for d in range(pm.ndim):
+        dx1_c = apply_transfer(p, fourier_space_neg_gradient(d, pm, order=1))
+        dx1_r = c2r(dx1_c)
+        dx1l = readout(dx1_r, xl, None)
+        r1.append(gather(dx1l, layout))
+    return dict(f=linalg.stack(r1, axis=-1), potk=p)
+
+
+@autooperator('dx->f,potk')
+def gravity(dx, q, pm):
+    return _gravity_body(dx, q, pm)
+
+
+def KickFactor(pt, ai, ac, af):
+    """fastpm.py:440-441"""
+    return 1 / (ac ** 2 * pt.E(ac)) * (pt.Gf(af) - pt.Gf(ai)) / pt.gf(ac)
+
+
+def DriftFactor(pt, ai, ac, af):
+    """fastpm.py:443-444"""
+    return 1 / (ac ** 3 * pt.E(ac)) * (pt.Gp(af) - pt.Gp(ai)) / pt.gp(ac)
+
+
+def _leapfrog_body(dx, p, stages, pt, force_fn):
+    """kick-drift-kick stepping of fastpm.py:455-473 around a force callback"""
+    Om0 = pt.Om0
+    f, potk = force_fn(dx)
+    for ai, af in zip(stages[:-1], stages[1:]):
+        ac = (ai * af) ** 0.5
+        p = p + f * (KickFactor(pt, ai, ai, ac) * 1.5 * Om0)       # kick
+        dx = dx + p * DriftFactor(pt, ai, ac, af)                  # drift
+        f, potk = force_fn(dx)                                     # force
+        p = p + f * (KickFactor(pt, ac, af, af) * 1.5 * Om0)       # kick
+    f = f * (1.5 * Om0)
+    return dict(dx=dx, p=p, f=f)
+
+
+@autooperator('dx_i,p_i->dx,p,f')
+def leapfrog(dx_i, p_i, q, stages, pt, pm):
+    """fastpm.py:446-474"""
+    q = _localize(q, pm)
+    return _leapfrog_body(dx_i, p_i, stages, pt, lambda dx: gravity(dx, q, pm))
+
+
+def _firststep_body(rhok, q, a, pt, pm):
+    """2LPT initial displacement and momentum at ``a`` (fastpm.py:479-495)"""
+    dx1, dx2 = lpt(rhok, q, pm)
+    E, D1, D2, f1, f2 = pt.E(a), pt.D1(a), pt.D2(a), pt.f1(a), pt.f2(a)
+    dx1 = dx1 * D1
+    dx2 = dx2 * D2
+    p = dx1 * (a ** 2 * f1 * E) + dx2 * (a ** 2 * f2 * E)
+    return dict(dx=dx1 + dx2, p=p)
+
+
+@autooperator('rhok->dx,p')
+def firststep(rhok, q, a, pt, pm):
+    """fastpm.py:476-495"""
+    return _firststep_body(rhok, q, a, pt, pm)
+
+
+def _support(stages):
+    stages = numpy.array(stages)
+    mid = (stages[1:] * stages[:-1]) ** 0.5
+    support = numpy.concatenate([mid, stages])
+    support.sort()
+    return stages, support
+
+
+@autooperator('rhok->dx,p,f')
+def nbody(rhok, q, stages, cosmology, pm):
+    """fastpm.py:497-510"""
+    stages, support = _support(stages)
+    pt = MatterDominated(cosmology.Om0, a=support)
+    q = _localize(q, pm)
+    dx, p = firststep(rhok, q, stages[0], pt, pm)
+    dx, p, f = leapfrog(dx, p, q, stages, pt, pm)
+    return dict(dx=dx, p=p, f=f)
+
+
+@operator
+class cdot:
+    """fastpm.py:512-527 -- real part of ``sum_k x1 conj(x2)`` over the full spectrum"""
+    ain = {'x1': 'ComplexField', 'x2': 'ComplexField'}
+    aout = {'y': '*'}
+
+    def apl(node, x1, x2):
+        return dict(y=x1.cdot(x2).real)
+
+    def vjp(node, x1, x2, _y):
+        return dict(_x1=x2.cdot_vjp(_y), _x2=x1.cdot_vjp(_y))
+
+    def jvp(node, x1_, x2_, x1, x2):
+        return dict(y_=x1.cdot(x2_).real + x2.cdot(x1_).real)
+
+
+class FastPMSimulation(object):
+    """fastpm.py:529-646 -- the same pipeline as ``nbody`` with the force mesh ``B`` times finer"""
+
+    def __init__(self, stages, cosmology, pm, B=1, q=None):
+        if q is None:
+            q = pm.generate_uniform_particle_grid()
+        stages, support = _support(stages)
+        self.pt = MatterDominated(cosmology.Om0, a=support)
+        self.stages = stages
+        self.pm = pm
+        self.fpm = type(pm)(Nmesh=pm.Nmesh * B, BoxSize=pm.BoxSize, dtype=pm.dtype,
+                            comm=pm.comm, resampler=pm.resampler)
+        self.q = _localize(q, pm)
+
+    def KickFactor(self, ai, ac, af):
+        return KickFactor(self.pt, ai, ac, af)
+
+    def DriftFactor(self, ai, ac, af):
+        return DriftFactor(self.pt, ai, ac, af)
+
+    @autooperator('rhok->dx, p')
+    def firststep(self, rhok):
+        return _firststep_body(rhok, self.q, self.stages[0], self.pt, self.pm)
+
+    @autooperator('dx->f,potk')
+    def gravity(self, dx):
+        return _gravity_body(dx, self.q, self.fpm)
+
+    @autooperator('rhok->dx,p,f')
+    def run(self, rhok):
+        dx, p = self.firststep(rhok)
+        return _leapfrog_body(dx, p, self.stages, self.pt, lambda dx: self.gravity(dx))

@@ -766,6 +766,10 @@ class ParticleMesh(object):
             return r if return_host else self.create('real', value=r)
         return c if return_host else self.create('complex', value=c)
 
+    def asparticles(self, x):
+        """particle array (host or device) -> device array; done once when a graph is built"""
+        return asdevice(numpy.asarray(x) if isinstance(x, (list, tuple)) else x)
+
     # -- positions --------------------------------------------------------------------------
     def _pos3(self, pos):
         """positions as a contiguous [Np, 3] device tensor (2-D gets a zero first column)"""
