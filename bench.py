@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- FastPM forward+vjp steps/s on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--nmesh 128] [--nsteps 10]
+    python bench.py --impl reference ...        # the CPU path (numpy/C oracle) on the host cores
+
+Workload (BASELINE.json configs[1]): white noise -> induce_correlation -> ``nbody`` with
+``nsteps`` FastPM steps (``len(stages) = nsteps + 1``) on ``nmesh^3`` particles / mesh, fp64;
+one bench "step" = ONE ``Model.compute_with_vjp`` of that graph (forward + reverse sweep with a
+cotangent on ``dx``).  ``value`` = nsteps / (seconds per bench step), inputs resident in HBM;
+``e2e`` = the same call with HOST numpy inputs (white noise + cotangent copied host->device
+inside the timed region, the gradient copied back device->host).
+
+Timing: W untimed warm-up steps, then K steps each bracketed by CUDA events on the stream the
+kernels are launched on, an L2 flush (256 MiB write) between steps outside the events, a
+barrier + synchronize on both sides, max over ranks.  N > 1 (torchrun): every rank runs the
+same problem on its own GPU ("replicas only" this round) -- weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = "FastPM forward+vjp steps/s"
+UNIT = "steps/s"
+
+
+def workload_name(nmesh, nsteps):
+    return ("FastPM %d-step forward+vjp, %d^3 particles / %d^3 mesh, fp64, white noise -> "
+            "induce_correlation -> nbody (BASELINE.json configs[1] shape)" % (nsteps, nmesh, nmesh))
+
+
+class Cosmology(object):
+    Om0 = 0.3075
+
+
+def power(k):
+    k = numpy.where(k == 0, 1.0, k)
+    return 1.5e6 * k / (1.0 + (k / 0.05) ** 2) ** 2
+
+
+def make_inputs(nmesh, seed=None):
+    """synthetic Gaussian initial conditions (host arrays)"""
+    N = nmesh
+    rng = numpy.random.default_rng(300 + N if seed is None else seed)
+    wn = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5
+    cot = rng.standard_normal((N ** 3, 3))
+    return wn, cot
+
+
+def build_model(pm, q, stages):
+    from vmad_b200 import Builder
+    from vmad_b200.lib import fastpm
+    with Builder() as m:
+        x = m.input('x')
+        rhok = fastpm.induce_correlation(x, power, pm)
+        dx, p, f = fastpm.nbody(rhok, q, stages, Cosmology, pm)
+        m.output(dx=dx, p=p, f=f)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.FIELDS,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [l.strip().split(', ') for l in open(self.path) if l.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower() == 'active':
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(numpy.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU path (oracle): cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------
+def cpu_fwd_vjp_seconds(nmesh, nsteps, threads, repeats=1):
+    """seconds per forward+vjp of the same graph on the numpy/C oracle backend"""
+    import oracle
+    oracle.activate(shims=False)
+    from pmesh import pm as opm
+    from pmesh.pm import ParticleMesh as OraclePM
+    opm.set_cic_threads(threads)
+    opm.set_fft_workers(threads)
+    N = nmesh
+    pm = OraclePM([N] * 3, 100.0 * N / 32)
+    wn, cot = make_inputs(N)
+    q = pm.generate_uniform_particle_grid(shift=0.0)
+    stages = numpy.linspace(0.1, 1.0, nsteps + 1)
+    m = build_model(pm, q, stages)
+    x = pm.create('complex', value=wn)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        m.compute_with_vjp(init=dict(x=x), v=dict(_dx=cot))
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return  # under torchrun only rank 0 runs the CPU arm
+    threads = host_threads()
+    nmesh = min(args.nmesh, args.cpu_nmesh)
+    ts = cpu_fwd_vjp_seconds(nmesh, args.nsteps, threads, repeats=args.warmup + args.steps)
+    timed = ts[args.warmup:]
+    sec = float(numpy.mean(timed))
+    value = args.nsteps / sec
+    sample = ("full %d-step forward+vjp at %d^3 on the numpy + C(OpenMP) oracle, %d threads"
+              % (args.nsteps, nmesh, threads))
+    if nmesh != args.nmesh:
+        sample += " (bounded sample: the GPU arm runs %d^3)" % args.nmesh
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.nmesh, args.nsteps), "nmesh": args.nmesh,
+                   "nsteps": args.nsteps, "cpu_nmesh": nmesh},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        return float(json.load(open(path))['hbm_gbs']), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(kernel):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture"""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        return d.get(kernel)
+    except Exception:
+        return None
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vmad_b200 import _capi as C
+    from vmad_b200.pm import DeviceArray, ParticleMesh
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    N = args.nmesh
+    pm = ParticleMesh([N] * 3, 100.0 * N / 32)
+    wn_h, cot_h = make_inputs(N)
+    q = pm.generate_uniform_particle_grid(shift=0.0)
+    stages = numpy.linspace(0.1, 1.0, args.nsteps + 1)
+    model = build_model(pm, q, stages)
+
+    # resident inputs
+    wn_d = pm.create('complex', value=wn_h)
+    cot_d = DeviceArray.from_host(cot_h)
+    # pinned host staging for the end-to-end leg
+    wn_pin = torch.from_numpy(wn_h.copy()).pin_memory()
+    cot_pin = torch.from_numpy(cot_h.copy()).pin_memory()
+    grad_pin = torch.empty(wn_pin.shape, dtype=wn_pin.dtype).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def step_resident():
+        (dx,), (g,) = model.compute_with_vjp(init=dict(x=wn_d), v=dict(_dx=cot_d))
+        return dx, g
+
+    def step_e2e():
+        x = pm.create('complex')
+        x.t.copy_(wn_pin, non_blocking=True)
+        c = DeviceArray(cot_pin.to('cuda', non_blocking=True))
+        (dx,), (g,) = model.compute_with_vjp(init=dict(x=x), v=dict(_dx=c))
+        grad_pin.copy_(g.t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return dx, g
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = C.launch_count()
+        total_ms = 0.0
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = C.launch_count() - l0
+        t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, wall
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches, wall = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    ms_per_step = total_ms / args.steps
+    value = world * args.nsteps / (ms_per_step * 1e-3)
+    e2e_value = world * args.nsteps / (e2e_ms / args.steps * 1e-3)
+
+    # ---- roofline of the dominant hand-written kernel, measured live with CUDA events on the
+    # ---- launching stream, on the particle distribution the run ended with
+    dx, _ = step_resident()
+    x_final = q + dx
+    lay = pm.decompose(x_final)
+    xs = lay.exchange(x_final)
+    Np, Nc = N ** 3, N ** 3
+    peak, peak_src = measured_peak()
+
+    def kernel_time(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return float(numpy.mean(ts))
+
+    field = pm.paint(xs, 1.0)
+    kernels = {}
+    for name, fn, nbytes in [
+            ('k_paint_rows', lambda: pm.paint(xs, 1.0), 24.0 * Np + 8.0 * Nc),
+            ('k_readout', lambda: field.readout(xs), 32.0 * Np + 8.0 * Nc),
+            ('k_readout_grad', lambda: pm.paint_vjp(field, xs, mass=1.0), 56.0 * Np + 8.0 * Nc),
+            ('layout_build', lambda: pm.decompose(x_final), 48.0 * Np),
+            ('cufft_r2c', lambda: field.r2c(), 16.06 * Nc)]:
+        t = kernel_time(fn)
+        kernels[name] = dict(ms=t * 1e3, achieved_gbs=nbytes / t / 1e9, frac=nbytes / t / 1e9 / peak,
+                             gparticles_s=Np / t / 1e9)
+    dom = 'k_paint_rows'
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]['achieved_gbs'],
+                "peak": peak, "unit": "GB/s", "frac": kernels[dom]['frac'],
+                "traffic": recorded_traffic(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 24.0 * Np + 8.0 * Nc,
+                "other_kernels": kernels}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        nm = min(N, args.cpu_nmesh)
+        sec = cpu_fwd_vjp_seconds(nm, args.nsteps, threads, repeats=1)[0]
+        sample = ("one full %d-step forward+vjp at %d^3 on the numpy + C(OpenMP) oracle, "
+                  "%d threads (%.1f s)" % (args.nsteps, nm, threads, sec))
+        if nm != N:
+            sample += "; bounded sample: the GPU arm runs %d^3" % N
+        cpu_baseline = {"value": args.nsteps / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(N, args.nsteps), "nmesh": N, "nsteps": args.nsteps,
+                   "np": N ** 3, "boxsize": 100.0 * N / 32,
+                   "parallelism": "replicas x%d" % world if world > 1 else "1 gpu",
+                   "l2": "256 MiB flush write between timed steps",
+                   "step": "one Model.compute_with_vjp = %d FastPM steps forward + reverse" % args.nsteps},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(wn_h.nbytes + cot_h.nbytes),
+                "d2h_bytes_per_step": int(wn_h.nbytes)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "host_wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--nmesh', type=int, default=128)
+    ap.add_argument('--nsteps', type=int, default=10)
+    ap.add_argument('--cpu-nmesh', type=int, default=128,
+                    help='largest mesh the CPU arm / cpu_baseline leg will run')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -40,6 +40,71 @@ def set_fft_workers(n):
         _FFT_KW['workers'] = n
 
 
+# ---------------------------------------------------------------------------------------------
+# optional C restatement of the CIC loops (oracle/cic.c, built by oracle/Makefile).  Same
+# formulas; used when present so the CPU baseline is a compiled loop.  ``set_cic_threads(1)``
+# (the default) keeps the strictly sequential particle order; the numpy versions below remain
+# the fallback and the cross-check (tests/test_oracle.py).
+# ---------------------------------------------------------------------------------------------
+import ctypes as _ct
+import os as _os
+
+_CIC = None
+_CIC_THREADS = 1
+
+
+def _load_cic():
+    global _CIC
+    path = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                         '_build', 'libcic_oracle.so')
+    if _CIC is None and _os.path.exists(path) and not _os.environ.get('ORACLE_NO_C'):
+        lib = _ct.CDLL(path)
+        P, L, D, I = _ct.c_void_p, _ct.c_int64, _ct.c_double, _ct.c_int
+        lib.cic_paint.argtypes = [P, P, D, L, P, P, P, I]
+        lib.cic_paint_gradient.argtypes = [P, P, D, P, L, P, P, P, I]
+        lib.cic_readout.argtypes = [P, P, L, P, P, P, I]
+        lib.cic_readout_gradient.argtypes = [P, P, L, P, P, P, I]
+        lib.scatter_add_rows.argtypes = [P, P, L, L, P]
+        lib.cic_cell_keys.argtypes = [P, L, P, P, P]
+        for f in (lib.cic_paint, lib.cic_paint_gradient, lib.cic_readout,
+                  lib.cic_readout_gradient, lib.scatter_add_rows, lib.cic_cell_keys):
+            f.restype = None
+        _CIC = lib
+    return _CIC
+
+
+def set_cic_threads(n):
+    """OpenMP threads for the C loops (1 = sequential, deterministic)."""
+    global _CIC_THREADS
+    _CIC_THREADS = max(1, int(n))
+
+
+def use_c(flag):
+    """force the numpy (False) or C (True, if built) implementation of the CIC loops"""
+    global _CIC
+    if flag:
+        _os.environ.pop('ORACLE_NO_C', None)
+        _load_cic()
+    else:
+        _os.environ['ORACLE_NO_C'] = '1'
+        _CIC = None
+
+
+def _c3(pm, pos):
+    """3-D geometry + contiguous [np, 3] positions for the C loops"""
+    pos = numpy.ascontiguousarray(pos, dtype='f8').reshape(-1, pm.ndim)
+    pad = 3 - pm.ndim
+    if pad:
+        pos = numpy.concatenate([numpy.zeros((len(pos), pad)), pos], axis=1)
+    n = numpy.array([1] * pad + list(pm.Nmesh), dtype='i8')
+    sc = numpy.array([1.0] * pad + list(pm.scale), dtype='f8')
+    return pos, n, sc
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
 class SelfComm(object):
     """A one-rank stand-in for ``MPI.COMM_SELF`` (fastpm.py:196,251,422,596)."""
     rank = 0
@@ -347,6 +412,13 @@ class Layout(object):
         """fastpm.py:286,293,304."""
         data = numpy.asarray(data)
         out = numpy.zeros((self.oldlength,) + data.shape[1:], dtype=data.dtype)
+        lib = _load_cic()
+        if lib is not None and data.dtype == numpy.dtype('f8'):
+            d = numpy.ascontiguousarray(data)
+            idx = numpy.ascontiguousarray(self.indices, dtype='i8')
+            ncomp = int(numpy.prod(data.shape[1:])) if data.ndim > 1 else 1
+            lib.scatter_add_rows(_ptr(d), _ptr(idx), len(d), ncomp, _ptr(out))
+            return out
         numpy.add.at(out, self.indices, data)
         return out
 
@@ -447,6 +519,12 @@ class ParticleMesh(object):
         return fl.astype('i8'), u - fl
 
     def cell_keys(self, pos):
+        lib = _load_cic()
+        if lib is not None:
+            p3, n, sc = _c3(self, pos)
+            keys = numpy.empty(len(p3), dtype='i8')
+            lib.cic_cell_keys(_ptr(p3), len(p3), _ptr(n), _ptr(sc), _ptr(keys))
+            return keys
         i, _ = self.cell_index(pos)
         key = numpy.zeros(len(i), dtype='i8')
         for d in range(self.ndim):
@@ -538,6 +616,14 @@ def _corner_iter(pm, pos):
 
 
 def _cic_paint(pm, pos, mass):
+    lib = _load_cic()
+    if lib is not None:
+        p3, n, sc = _c3(pm, pos)
+        marr = numpy.ascontiguousarray(mass, dtype='f8') if numpy.ndim(mass) != 0 else None
+        out = numpy.zeros(pm.Ntot, dtype='f8')
+        lib.cic_paint(_ptr(p3), _ptr(marr), 1.0 if marr is not None else float(mass), len(p3),
+                      _ptr(n), _ptr(sc), _ptr(out), _CIC_THREADS)
+        return out.reshape(pm.rshape)
     pos = numpy.asarray(pos, dtype='f8').reshape(-1, pm.ndim)
     mass = numpy.asarray(mass, dtype='f8') if numpy.ndim(mass) != 0 else float(mass)
     out = numpy.zeros(pm.Ntot, dtype='f8')
@@ -547,6 +633,15 @@ def _cic_paint(pm, pos, mass):
 
 
 def _cic_paint_gradient(pm, pos, mass, v_pos):
+    lib = _load_cic()
+    if lib is not None:
+        p3, n, sc = _c3(pm, pos)
+        v3 = _c3(pm, v_pos)[0]
+        marr = numpy.ascontiguousarray(mass, dtype='f8') if numpy.ndim(mass) != 0 else None
+        out = numpy.zeros(pm.Ntot, dtype='f8')
+        lib.cic_paint_gradient(_ptr(p3), _ptr(marr), 1.0 if marr is not None else float(mass),
+                               _ptr(v3), len(p3), _ptr(n), _ptr(sc), _ptr(out), _CIC_THREADS)
+        return out.reshape(pm.rshape)
     pos = numpy.asarray(pos, dtype='f8').reshape(-1, pm.ndim)
     mass = numpy.asarray(mass, dtype='f8') if numpy.ndim(mass) != 0 else float(mass)
     out = numpy.zeros(pm.Ntot, dtype='f8')
@@ -559,6 +654,13 @@ def _cic_paint_gradient(pm, pos, mass, v_pos):
 
 
 def _cic_readout(pm, mesh, pos):
+    lib = _load_cic()
+    if lib is not None:
+        p3, n, sc = _c3(pm, pos)
+        m = numpy.ascontiguousarray(mesh, dtype='f8')
+        out = numpy.empty(len(p3), dtype='f8')
+        lib.cic_readout(_ptr(m), _ptr(p3), len(p3), _ptr(n), _ptr(sc), _ptr(out), _CIC_THREADS)
+        return out
     pos = numpy.asarray(pos, dtype='f8').reshape(-1, pm.ndim)
     m = numpy.asarray(mesh, dtype='f8').ravel()
     out = numpy.zeros(len(pos), dtype='f8')
@@ -568,6 +670,14 @@ def _cic_readout(pm, mesh, pos):
 
 
 def _cic_readout_gradient(pm, mesh, pos):
+    lib = _load_cic()
+    if lib is not None:
+        p3, n, sc = _c3(pm, pos)
+        m = numpy.ascontiguousarray(mesh, dtype='f8')
+        out = numpy.empty((len(p3), 3), dtype='f8')
+        lib.cic_readout_gradient(_ptr(m), _ptr(p3), len(p3), _ptr(n), _ptr(sc), _ptr(out),
+                                 _CIC_THREADS)
+        return out[:, 3 - pm.ndim:]
     pos = numpy.asarray(pos, dtype='f8').reshape(-1, pm.ndim)
     m = numpy.asarray(mesh, dtype='f8').ravel()
     out = numpy.zeros((len(pos), pm.ndim), dtype='f8')

@@ -181,6 +181,9 @@ def fourier_space_neg_gradient(dir, pm, order):
 def _apply_tf(x, tf, kind, conj):
     if isinstance(tf, Filter) and kind == 'wavenumber' and hasattr(x.pm, '_transfer'):
         return tf.apply_device(x, conj)
+    cached = getattr(x, 'apply_transfer_function', None)
+    if cached is not None:
+        return cached(tf, kind, conj)
     if conj:
         return x.apply(lambda k, v: v * numpy.conj(tf(k)), kind=kind)
     return x.apply(lambda k, v: v * tf(k), kind=kind)

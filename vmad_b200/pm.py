@@ -550,6 +550,10 @@ class ComplexField(Field):
     def _apply_table(self, table, conj=False):
         return self.pm._transfer_table(self, numpy.asarray(table), conj)
 
+    def apply_transfer_function(self, tf, kind='wavenumber', conj=False):
+        """``self * tf(k)`` (or ``conj(tf(k))``) with the table of ``tf`` cached on the device"""
+        return self.pm._transfer_callable(self, tf, kind, conj)
+
     def c2r(self, out=None):
         """fastpm.py:64,70: un-normalised inverse."""
         return self.pm._c2r(self, 1.0)
@@ -679,6 +683,7 @@ class ParticleMesh(object):
         self._mesh = m
         self._ncell = int(C.lib.vpm_layout_ncell(ctypes.byref(m)))
         self._tables = {}
+        self._tf_cache = {}
 
     # -- host-side tables ---------------------------------------------------------------
     def freq_index(self, d):
@@ -1012,9 +1017,9 @@ class ParticleMesh(object):
                                    _ptr(a[1]), _ptr(a[2]), 1 if conj else 0))
         return ComplexField(self, o)
 
-    def _transfer_table(self, cplx, table, conj=False):
-        """generic multiplier: a broadcastable host table (any axis may have length 1)"""
-        rt = self.rt
+    def _prepare_table(self, table):
+        """host multiplier table (broadcastable to the complex shape) -> (device tensor,
+        element strides with 0 on broadcast axes, is_complex)"""
         table = numpy.asarray(table)
         if table.ndim == 0:
             table = table.reshape((1,) * self.ndim)
@@ -1034,12 +1039,32 @@ class ParticleMesh(object):
                 raise ValueError("transfer table shape %s does not broadcast to %s"
                                  % (table.shape, self.cshape))
         strides = [0] * (3 - self.ndim) + list(reversed(strides))
+        return tt, strides, is_c
+
+    def _transfer_table(self, cplx, table, conj=False, prepared=None):
+        """generic multiplier: a broadcastable host table (any axis may have length 1)"""
+        rt = self.rt
+        tt, strides, is_c = prepared if prepared is not None else self._prepare_table(table)
         rt.sync_stream()
         o = rt.empty(self.cshape, _C16)
         C.check(C.lib.vpm_transfer_table(rt.ctx, C.i3(self._cshape3), _ptr(cplx.t), _ptr(o),
                                          _ptr(tt), C.i3(strides), 1 if is_c else 0,
                                          1 if conj else 0))
         return ComplexField(self, o)
+
+    def _transfer_callable(self, cplx, tf, kind, conj):
+        """``x * tf(k)`` for an arbitrary python ``tf``: the table is evaluated on the host the
+        first time this very function object is seen and then stays on the device (a model
+        built once keeps calling the same closure, e.g. ``induce_correlation``'s)."""
+        key = (id(tf), kind)
+        hit = self._tf_cache.get(key)
+        if hit is None or hit[0] is not tf:
+            prepared = self._prepare_table(tf(cplx._coords(kind)))
+            if len(self._tf_cache) >= 32:
+                self._tf_cache.pop(next(iter(self._tf_cache)))
+            hit = (tf, prepared)  # holding tf keeps its id unique
+            self._tf_cache[key] = hit
+        return self._transfer_table(cplx, None, conj, prepared=hit[1])
 
     def force_kspace(self, rhok, scale, grad_tables, want_p=True):
         """fused ``gravity`` k-space pass (fastpm.py:424-431); 3-D only"""

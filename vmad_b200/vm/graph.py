@@ -13,6 +13,7 @@ not the numerics, is the bottleneck.
 """
 import itertools
 import sys
+import weakref
 from collections import OrderedDict
 
 from .errors import (DuplicatedOutput, InferError, ModelError, OverwritePrecaution,
@@ -102,9 +103,19 @@ class Symbol(BaseSymbol):
         assert isinstance(name, str)
         BaseSymbol.__init__(self)
         self._name = name
-        self._model = None
+        # weak reference to a real model (so that dropping a model frees its nodes, symbols and
+        # the tensors its literals pin by reference counting alone -- a vjp model is built, run
+        # once and dropped on every backward pass), strong reference to a transient one
+        self._model_ref = None
         if model is not None:
             model.anchor(self)
+
+    @property
+    def _model(self):
+        r = self._model_ref
+        if r is None or isinstance(r, Model):
+            return r
+        return r()
 
     def __repr__(self):
         return self._name
@@ -388,6 +399,7 @@ class Model(list):
         self._uid = next(_counter)
         self._symbols = []
         self._plans = {}
+        self._weakself = weakref.ref(self)
 
     def __hash__(self):
         return self._uid
@@ -406,7 +418,10 @@ class Model(list):
         old = symbol._model
         if old is not None and old is not self and not isinstance(old, ModelInTransient):
             raise ModelError("cannot change the model after the symbol is no longer in transient.")
-        symbol._model = self
+        if isinstance(self, ModelInTransient):
+            symbol._model_ref = self
+        else:
+            symbol._model_ref = self._weakself
         self._symbols.append(symbol)
 
     def append(self, node):
@@ -417,7 +432,7 @@ class Model(list):
         self._vin.extend(other._vin)
         self._vout.extend(other._vout)
         for s in other._symbols:
-            s._model = None
+            s._model_ref = None
             self.anchor(s)
         list.extend(self, other)
         self._plans.clear()
