@@ -321,7 +321,7 @@ def run_gpu(args):
     field = pm.paint(xs, 1.0)
     kernels = {}
     for name, fn, nbytes in [
-            ('k_paint_rows', lambda: pm.paint(xs, 1.0), 24.0 * Np + 8.0 * Nc),
+            ('k_paint_agg', lambda: pm.paint(xs, 1.0), 24.0 * Np + 8.0 * Nc),
             ('k_readout', lambda: field.readout(xs), 32.0 * Np + 8.0 * Nc),
             ('k_readout_grad', lambda: pm.paint_vjp(field, xs, mass=1.0), 56.0 * Np + 8.0 * Nc),
             ('layout_build', lambda: pm.decompose(x_final), 48.0 * Np),
@@ -329,7 +329,7 @@ def run_gpu(args):
         t = kernel_time(fn)
         kernels[name] = dict(ms=t * 1e3, achieved_gbs=nbytes / t / 1e9, frac=nbytes / t / 1e9 / peak,
                              gparticles_s=Np / t / 1e9)
-    dom = 'k_paint_rows'
+    dom = 'k_paint_agg'
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]['achieved_gbs'],
                 "peak": peak, "unit": "GB/s", "frac": kernels[dom]['frac'],
                 "traffic": recorded_traffic(dom), "peak_source": peak_src,

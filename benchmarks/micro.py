@@ -11,6 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vmad_b200.pm import ParticleMesh, DeviceArray  # noqa: E402
 from vmad_b200 import _capi as C  # noqa: E402
+from vmad_b200 import pm as pmmod  # noqa: E402
 
 
 def timeit(fn, warmup=3, iters=10):
@@ -70,6 +71,11 @@ def main():
         rec('exchange[n,3]', lambda: lay.exchange(x), 52.0 * n)
         rec('gather[n,3]', lambda: lay.gather(xs), 52.0 * n)
         rec('paint_sorted', lambda: pm.paint(xs, 1.0), 24.0 * n + 8.0 * Nc)
+        pmmod.set_paint_algorithm('tile')
+        rec('paint_tile(determ.)', lambda: pm.paint(xs, 1.0), 24.0 * n + 8.0 * Nc)
+        pmmod.set_paint_algorithm('aggregated')
+        rec('paint_agg_unsorted', lambda: pm.paint(x, 1.0, layout=None) if False else pm._paint_any_order(x), 24.0 * n + 8.0 * Nc)
+        rec('paint_rows(ablation)', lambda: pm.paint_rows(xs, 1.0), 24.0 * n + 8.0 * Nc)
         rec('paint_sorted_mass', lambda: pm.paint(xs, ms), 32.0 * n + 8.0 * Nc)
         rec('paint_atomic', lambda: pm.paint_atomic(x, 1.0), 24.0 * n + 8.0 * Nc)
         rec('paint_atomic_sortedx', lambda: pm.paint_atomic(xs, 1.0), 24.0 * n + 8.0 * Nc)

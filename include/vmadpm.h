@@ -85,12 +85,23 @@ int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, in
 
 /* ---- paint  (fastpm.py:224,238,256; pmesh ParticleMesh.paint / paint_jvp and the
  *      mesh half of RealField.readout_vjp) ---------------------------------- */
-/* Particles sorted by cell key (xs = x[perm]); writes EVERY local cell exactly once
- * (no zero-fill needed, no atomics, run-to-run deterministic).
- * mass: per-particle array (sorted like xs) or NULL -> mass0. */
+/* Particles sorted by cell key (xs = x[perm]); fills every local cell (no prior zero fill
+ * needed).  mass: per-particle array (sorted like xs) or NULL -> mass0.
+ * Two algorithms (vpm_paint_set_algorithm): 0 (default) warp-aggregated fp64 reductions --
+ * fastest, summation order not fixed (results agree to rounding); 1 shared-memory tiles --
+ * no atomics, every cell written exactly once, run-to-run bit-identical. */
+int vpm_paint_set_algorithm(int algo);
 int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                      const double* mass, double mass0, int64_t np,
                      const int32_t* cell_start, double* out);
+/* Tuning knob (benchmarks only): output tile extents of the sorted paint kernel in cells;
+ * 0 keeps the default. */
+int vpm_paint_set_tile(int tx, int ty, int tz);
+/* Same contract, earlier "row gather" formulation (one warp per output row, lanes over cells);
+ * kept for ablation against the tile kernel. */
+int vpm_paint_sorted_rows(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
+                          const double* mass, double mass0, int64_t np,
+                          const int32_t* cell_start, double* out);
 /* sum_d mass * vpos[:, d] * dW/dx_d  (+ vmass * W when vmass != NULL) */
 int vpm_paint_jvp_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                          const double* mass, double mass0, const double* vpos,

@@ -58,6 +58,9 @@ SIGNATURES = {
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_paint_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
+    'vpm_paint_set_algorithm': (c_int, [c_int]),
+    'vpm_paint_set_tile': (c_int, [c_int, c_int, c_int]),
+    'vpm_paint_sorted_rows': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
     'vpm_paint_jvp_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, _P, _P,
                                      c_int64, _P, _P]),
     'vpm_paint_atomic': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P]),

@@ -134,19 +134,23 @@ __global__ void k_scatter_ids(const int* __restrict__ keys, const int* __restric
     if (p < np) perm[cell_start[keys[p]] + rank[p]] = (int)p;
 }
 
-// per-cell ascending sort of the ids (restores input order inside a cell)
-constexpr int FIX_SMALL = 32;
+// per-cell ascending sort of the ids (restores input order inside a cell).  Three tiers by
+// occupancy: <= FIX_SMALL ids: insertion sort by one thread; <= FIX_MEDIUM: rank sort by one
+// warp, in place; larger (pathological): rank sort spread over the whole grid via a copy.
+constexpr int FIX_SMALL = 16;
+constexpr int FIX_MEDIUM = 1024;
 __global__ void k_fix_small(const int* __restrict__ cell_start, long long ncell,
-                            int* __restrict__ perm, int* __restrict__ big_list,
-                            int* __restrict__ big_count) {
+                            int* __restrict__ perm, int* __restrict__ lists,
+                            int* __restrict__ counts) {
     long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     int b = cell_start[c], e = cell_start[c + 1];
     int cnt = e - b;
     if (cnt < 2) return;
     if (cnt > FIX_SMALL) {
-        int slot = atomicAdd(big_count, 1);
-        big_list[slot] = (int)c;
+        const int which = cnt > FIX_MEDIUM ? 1 : 0;
+        int slot = atomicAdd(counts + which, 1);
+        lists[which * ncell + slot] = (int)c;
         return;
     }
     for (int i = b + 1; i < e; ++i) {  // insertion sort, segments are tiny
@@ -160,9 +164,46 @@ __global__ void k_fix_small(const int* __restrict__ cell_start, long long ncell,
     }
 }
 
-// crowded cells (more than FIX_SMALL particles): rank sort.  The ids are distinct, so the
-// final slot of an id is the number of ids of the same cell that are smaller.  Every block
-// takes a slice of every crowded cell, so one pathological cell still uses the whole GPU.
+// medium cells: one warp per cell.  The ids are distinct, so the final slot of an id is the
+// number of smaller ids in the cell; ranks are computed first, then written in place.
+__global__ void __launch_bounds__(256)
+k_fix_medium(const int* __restrict__ cell_start, const int* __restrict__ list,
+             const int* __restrict__ count, int* __restrict__ perm) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int n_med = *count;
+    for (int s = warp; s < n_med; s += nwarp) {
+        const int c = list[s];
+        const int b = cell_start[c];
+        const int n = cell_start[c + 1] - b;
+        int* a = perm + b;
+        int v[FIX_MEDIUM / 32], r[FIX_MEDIUM / 32];
+        const int nk = (n + 31) >> 5;  // register slots in use (warp-uniform)
+#pragma unroll
+        for (int k = 0; k < FIX_MEDIUM / 32; ++k) {
+            const int i = lane + 32 * k;
+            v[k] = i < n ? a[i] : 0x7fffffff;
+            r[k] = 0;
+        }
+        for (int t = 0; t < n; ++t) {
+            const int o = a[t];  // warp-uniform broadcast load
+#pragma unroll
+            for (int k = 0; k < FIX_MEDIUM / 32; ++k)
+                if (k < nk) r[k] += (o < v[k]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < FIX_MEDIUM / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i < n) a[r[k]] = v[k];
+        }
+        __syncwarp();
+    }
+}
+
+// huge cells: every block takes a slice of every such cell, so one pathological cell still
+// uses the whole GPU; writes go to perm_out and are copied back afterwards.
 __global__ void k_fix_big_rank(const int* __restrict__ cell_start, const int* __restrict__ big_list,
                                const int* __restrict__ big_count, const int* __restrict__ perm_in,
                                int* __restrict__ perm_out) {
@@ -262,15 +303,15 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
     long long ncell = vpm_layout_ncell(mesh);
     VPM_REQUIRE(cell_start, "cell_start is NULL");
     cudaStream_t st = ctx->stream;
-    // workspace: count[ncell] | rank[np] | scan tmp | big_list[ncell] | big_count | perm2[np]
+    // workspace: count[ncell] | rank[np] | scan tmp | lists[2][ncell] | counts[4] | perm2[np]
     long long ntmp = scan_tmp_ints(ncell);
-    size_t ints = (size_t)ncell + (size_t)np + (size_t)ntmp + (size_t)ncell + 4 + (size_t)np;
+    size_t ints = (size_t)ncell + (size_t)np + (size_t)ntmp + 2 * (size_t)ncell + 4 + (size_t)np;
     int* ws = (int*)ctx->workspace(ints * sizeof(int));
     int* count = ws;
     int* rank = count + ncell;
     int* tmp = rank + np;
-    int* big_list = tmp + ntmp;
-    int* big_count = big_list + ncell;
+    int* big_list = tmp + ntmp;          // [0]: medium cells, [1]: huge cells
+    int* big_count = big_list + 2 * ncell;
     int* perm2 = big_count + 4;
     VPM_CUDA(cudaMemsetAsync(count, 0, (size_t)ncell * sizeof(int), st));
     VPM_CUDA(cudaMemsetAsync(big_count, 0, 4 * sizeof(int), st));
@@ -286,10 +327,13 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
                    (long long)np, perm);
         VPM_LAUNCH(k_fix_small, (unsigned)ceil_div(ncell, 256), 256, 0, st, cell_start, ncell, perm,
                    big_list, big_count);
-        // crowded cells (rare): rank-sort each into perm2, then copy back
         int nblk = 4 * ctx->sm_count;
-        VPM_LAUNCH(k_fix_big_rank, nblk, 256, 0, st, cell_start, big_list, big_count, perm, perm2);
-        VPM_LAUNCH(k_copy_big, nblk, 256, 0, st, cell_start, big_list, big_count, perm2, perm);
+        VPM_LAUNCH(k_fix_medium, nblk, 256, 0, st, cell_start, big_list, big_count, perm);
+        // pathological cells (> FIX_MEDIUM ids): rank-sort each into perm2, then copy back
+        VPM_LAUNCH(k_fix_big_rank, nblk, 256, 0, st, cell_start, big_list + ncell, big_count + 1,
+                   perm, perm2);
+        VPM_LAUNCH(k_copy_big, nblk, 256, 0, st, cell_start, big_list + ncell, big_count + 1, perm2,
+                   perm);
     }
     VPM_API_END
 }

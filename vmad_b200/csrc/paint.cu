@@ -126,6 +126,368 @@ k_paint_rows(Geo g, const double* __restrict__ xs, const double* __restrict__ ma
     if (lane == 0) orow[0] = first_value + carry;  // periodic wrap: cell n2-1 feeds cell 0
 }
 
+// -------------------------------------------------------------------------------------------
+// Tile kernel (the production path).
+//
+// A CTA owns an output tile of TX x TY x TZ cells and accumulates it in shared memory; nothing
+// but this CTA writes those cells, so the mesh needs no zero fill and no atomics, and the
+// result is bit-reproducible.  The particles that touch the tile live in the (TX+1) x (TY+1)
+// source rows (one halo row/plane on the low side) and, because of the cell sort, each row's
+// particles for the tile's z-range are ONE contiguous run of the particle array.  Warps take
+// source rows from a shared counter and walk the run 32 particles at a time with
+// LANES OVER PARTICLES: loads are coalesced and independent of cell_start (no dependent-load
+// chain), every lane does the same amount of fp64 work (no divergence from uneven cell
+// occupancy), and particles of the same cell -- adjacent lanes, thanks to the sort -- are
+// combined with a segmented warp scan whose depth adapts to the longest run in the warp.  The
+// last lane of each run adds the run's eight corner sums into shared memory with plain
+// read-modify-writes: for a fixed corner (a, b) a target row is fed by exactly one source row,
+// i.e. one warp, and within the warp the targets z (phase 1) and z+1 (phase 2) are distinct.
+// Four partial tiles W_ab are kept and summed in a fixed order when the tile is stored.
+// -------------------------------------------------------------------------------------------
+constexpr int TILE_WARPS = 8;
+
+struct TileDims {
+    int TX, TY, TZ;     // tile extents in cells
+    int ntx, nty, ntz;  // number of tiles along each axis
+};
+
+// wrapped cell index along the contiguous axis; the common case (particle inside the box or
+// one box length outside) costs a compare, the general case is the exact 64-bit modulo that
+// the key kernel uses, so the two always agree.
+__device__ __forceinline__ int wrap_cell(double fl, int n) {
+    int i = __double2int_rn(fl);  // exact for |fl| < 2^31, saturates beyond
+    if ((unsigned)i >= (unsigned)n) {
+        if (i < 0 && i >= -n) {
+            i += n;
+        } else if (i >= n && i < 2 * n) {
+            i -= n;
+        } else {
+            long long ll = (fabs(fl) < 9.0e18) ? (long long)fl : 0LL;
+            ll %= (long long)n;
+            if (ll < 0) ll += n;
+            i = (int)ll;
+        }
+    }
+    return i;
+}
+
+// MASSKIND 0: mass == 1 (no multiply); 1: scalar mass0; 2: per-particle array
+template <int MODE, int MASSKIND, bool HAS_VMASS>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 4)
+k_paint_tile(Geo g, TileDims td, const double* __restrict__ xs, const double* __restrict__ mass,
+             double mass0, const double* __restrict__ vpos, const double* __restrict__ vmass,
+             const int* __restrict__ cell_start, double* __restrict__ out) {
+    extern __shared__ __align__(16) double W[];  // [4][TX*TY*TZ]
+    __shared__ int next_item;
+    const int lane = threadIdx.x & 31;
+    const int TY = td.TY, TZ = td.TZ;
+    const int tsize = td.TX * TY * TZ;
+
+    // tile coordinates: y fastest, so that CTAs that share halo rows run close together
+    int t = blockIdx.x;
+    const int ty = t % td.nty; t /= td.nty;
+    const int tz = t % td.ntz; t /= td.ntz;
+    const int ox0 = t * td.TX, oy0 = ty * TY, oz0 = tz * TZ;
+    const int ex = min(td.TX, g.nloc0 - ox0), ey = min(TY, g.n1 - oy0), ez = min(TZ, g.n2 - oz0);
+
+    {
+        double2* W2 = reinterpret_cast<double2*>(W);
+        const double2 z2 = make_double2(0.0, 0.0);
+        for (int i = threadIdx.x; i < 2 * tsize; i += blockDim.x) W2[i] = z2;
+    }
+    if (threadIdx.x == 0) next_item = 0;
+    __syncthreads();
+
+    const int nrows = (ex + 1) * (ey + 1);
+    const int n2 = g.n2;
+    const bool full_row = (ez == n2);
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&next_item, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nrows) break;
+        const int rsx = item / (ey + 1) - 1;  // source row relative to the tile: [-1, ex) x [-1, ey)
+        const int rsy = item - (rsx + 1) * (ey + 1) - 1;
+        int sp = ox0 + rsx;  // local output plane of the source row (may be -1)
+        if (g.ghost) {
+            sp += 1;         // key planes are counted from the lower ghost plane
+        } else if (sp < 0) {
+            sp += g.n0;
+        }
+        int sy = oy0 + rsy;
+        if (sy < 0) sy += g.n1;
+        const int rowbase = (sp * g.n1 + sy) * n2;
+        // which corners (a, b) of this source row land inside the tile (warp-uniform)
+        const bool va0 = rsx >= 0, va1 = rsx + 1 < ex;
+        const bool vb0 = rsy >= 0, vb1 = rsy + 1 < ey;
+        const bool v00 = va0 && vb0, v01 = va0 && vb1, v10 = va1 && vb0, v11 = va1 && vb1;
+        // word offsets of the target rows in the four partial tiles, z origin folded in
+        const int o00 = 0 * tsize + ((rsx + 0) * TY + (rsy + 0)) * TZ - oz0;
+        const int o01 = 1 * tsize + ((rsx + 0) * TY + (rsy + 1)) * TZ - oz0;
+        const int o10 = 2 * tsize + ((rsx + 1) * TY + (rsy + 0)) * TZ - oz0;
+        const int o11 = 3 * tsize + ((rsx + 1) * TY + (rsy + 1)) * TZ - oz0;
+        // particle ranges: source cells [oz0 - 1, oz0 + ez - 1] (periodic), contiguous per range
+        int rb0, re0, rb1 = 0, re1 = 0;
+        if (full_row) {
+            rb0 = __ldg(cell_start + rowbase);
+            re0 = __ldg(cell_start + rowbase + n2);
+        } else {
+            rb0 = __ldg(cell_start + rowbase + max(oz0 - 1, 0));
+            re0 = __ldg(cell_start + rowbase + oz0 + ez);
+            if (oz0 == 0) {
+                rb1 = __ldg(cell_start + rowbase + n2 - 1);
+                re1 = __ldg(cell_start + rowbase + n2);
+            }
+        }
+        for (int r = 0; r < 2; ++r) {
+            const int rb = r ? rb1 : rb0, re = r ? re1 : re0;
+            for (int p0 = rb; p0 < re; p0 += 32) {
+                const int p = p0 + lane;
+                const bool active = p < re;
+                int iz = -1 - lane;  // inactive lanes: unique keys, never merged
+                // S<ab><c>: this particle's contribution to corner (a, b, c)
+                double S000 = 0.0, S001 = 0.0, S010 = 0.0, S011 = 0.0;
+                double S100 = 0.0, S101 = 0.0, S110 = 0.0, S111 = 0.0;
+                if (active) {
+                    const double* xp = xs + 3LL * p;
+                    const double x0 = __ldg(xp + 0), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+                    double u, fl;
+                    u = __dmul_rn(x0, g.s0); fl = floor(u); const double f0 = u - fl;
+                    u = __dmul_rn(x1, g.s1); fl = floor(u); const double f1 = u - fl;
+                    u = __dmul_rn(x2, g.s2); fl = floor(u); const double f2 = u - fl;
+                    iz = wrap_cell(fl, n2);
+                    const double e0 = 1.0 - f0, e1 = 1.0 - f1, e2 = 1.0 - f2;
+                    if (MODE == 0) {
+                        // per-corner weight (w0 * w1) * w2, times the mass
+                        double a0 = e0, a1 = f0;
+                        if (MASSKIND != 0) {
+                            const double m = MASSKIND == 2 ? __ldg(mass + p) : mass0;
+                            a0 *= m;
+                            a1 *= m;
+                        }
+                        if (v00) { const double w = a0 * e1; S000 = w * e2; S001 = w * f2; }
+                        if (v01) { const double w = a0 * f1; S010 = w * e2; S011 = w * f2; }
+                        if (v10) { const double w = a1 * e1; S100 = w * e2; S101 = w * f2; }
+                        if (v11) { const double w = a1 * f1; S110 = w * e2; S111 = w * f2; }
+                    } else {
+                        const double* vp = vpos + 3LL * p;
+                        const double m = MASSKIND == 2 ? __ldg(mass + p) : (MASSKIND == 1 ? mass0 : 1.0);
+                        const double v0 = m * __ldg(vp + 0), v1 = m * __ldg(vp + 1), v2 = m * __ldg(vp + 2);
+                        const double vm = HAS_VMASS ? __ldg(vmass + p) : 0.0;
+                        // corner value: v0 dW/dx0 + v1 dW/dx1 + v2 dW/dx2 (+ vm W)
+                        const double q0 = v0 * g.s0, q1 = v1 * g.s1, q2 = v2 * g.s2;
+#define VPM_TANGENT(W0, D0, W1, D1, SA, SB)                                          \
+    {                                                                                \
+        const double wxy = (W0) * (W1);                                              \
+        const double gxy = (D0) * (W1) + (W0) * (D1);                                \
+        const double base = HAS_VMASS ? vm * wxy : 0.0;                              \
+        SA = gxy * e2 - q2 * wxy + base * e2;                                        \
+        SB = gxy * f2 + q2 * wxy + base * f2;                                        \
+    }
+                        if (v00) VPM_TANGENT(e0, -q0, e1, -q1, S000, S001)
+                        if (v01) VPM_TANGENT(e0, -q0, f1, q1, S010, S011)
+                        if (v10) VPM_TANGENT(f0, q0, e1, -q1, S100, S101)
+                        if (v11) VPM_TANGENT(f0, q0, f1, q1, S110, S111)
+#undef VPM_TANGENT
+                    }
+                }
+                // segmented inclusive scan over runs of equal iz (sorted => runs are contiguous);
+                // the number of rounds adapts to the longest run in this warp
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int izd = __shfl_up_sync(0xffffffffu, iz, d);
+                    const bool same = (lane >= d) && (izd == iz);
+                    if (!__any_sync(0xffffffffu, same)) break;
+#define VPM_SCAN(V)                                                                  \
+    {                                                                                \
+        const double tv = __shfl_up_sync(0xffffffffu, V, d);                         \
+        if (same) V += tv;                                                           \
+    }
+                    if (v00) { VPM_SCAN(S000) VPM_SCAN(S001) }
+                    if (v01) { VPM_SCAN(S010) VPM_SCAN(S011) }
+                    if (v10) { VPM_SCAN(S100) VPM_SCAN(S101) }
+                    if (v11) { VPM_SCAN(S110) VPM_SCAN(S111) }
+#undef VPM_SCAN
+                }
+                const int iznext = __shfl_down_sync(0xffffffffu, iz, 1);
+                const bool tail = active && (lane == 31 || iznext != iz);
+                // phase 1: corner c = 0 -> cell iz; phase 2: c = 1 -> cell iz + 1 (periodic)
+                {
+                    const int zl = iz - oz0;
+                    if (tail && zl >= 0 && zl < ez) {
+                        if (v00) W[o00 + iz] += S000;
+                        if (v01) W[o01 + iz] += S010;
+                        if (v10) W[o10 + iz] += S100;
+                        if (v11) W[o11 + iz] += S110;
+                    }
+                }
+                __syncwarp();
+                {
+                    int zt = iz + 1;
+                    if (zt == n2) zt = 0;
+                    const int zl = zt - oz0;
+                    if (tail && zl >= 0 && zl < ez) {
+                        if (v00) W[o00 + zt] += S001;
+                        if (v01) W[o01 + zt] += S011;
+                        if (v10) W[o10 + zt] += S101;
+                        if (v11) W[o11 + zt] += S111;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    // store the tile: fixed summation order over the four partial tiles; one warp per row
+    const int warp = threadIdx.x >> 5;
+    for (int r = warp; r < ex * ey; r += TILE_WARPS) {
+        const int x = r / ey;
+        const int y = r - x * ey;
+        const double* w = W + (x * TY + y) * TZ;
+        double* o = out + (long long)(ox0 + x) * g.stride0 + (long long)(oy0 + y) * g.stride1 + oz0;
+        for (int z = lane; z < ez; z += 32)
+            o[z] = ((w[z] + w[tsize + z]) + w[2 * tsize + z]) + w[3 * tsize + z];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Warp-aggregated scatter (the fast path).
+//
+// Lanes over cell-sorted particles, no tiles: a warp takes 32 consecutive particles, sums the
+// particles of each cell with the same segmented scan as the tile kernel, folds the c = 1
+// (cell z + 1) sums of a run into the c = 0 sums of the next run when that run is the
+// neighbouring cell of the same row, and the last lane of each run issues at most eight fp64
+// reductions (RED.E.ADD.F64) into the mesh.  Every particle is read exactly once (no halo
+// re-reads) and the instruction count per particle is about a third of the tile kernel's; the
+// price is a zero fill of the mesh beforehand and a summation order that depends on the order
+// in which L2 receives the reductions (results agree to rounding, not bit for bit).
+// -------------------------------------------------------------------------------------------
+template <int MODE, int MASSKIND, bool HAS_VMASS>
+__global__ void __launch_bounds__(256)
+k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, double mass0,
+            const double* __restrict__ vpos, const double* __restrict__ vmass, long long np,
+            double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long nchunk = (np + 31) >> 5;
+    const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long ch = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < nchunk;
+         ch += wstride) {
+        const long long p = (ch << 5) + lane;
+        const bool active = p < np;
+        long long key = -1 - lane;  // inactive lanes: unique keys, never merged
+        int i0 = 0, i1 = 0, iz = 0;
+        double S000 = 0.0, S001 = 0.0, S010 = 0.0, S011 = 0.0;
+        double S100 = 0.0, S101 = 0.0, S110 = 0.0, S111 = 0.0;
+        if (active) {
+            const double* xp = xs + 3 * p;
+            const double x0 = __ldg(xp + 0), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+            double u, fl;
+            u = __dmul_rn(x0, g.s0); fl = floor(u); const double f0 = u - fl; i0 = wrap_cell(fl, g.n0);
+            u = __dmul_rn(x1, g.s1); fl = floor(u); const double f1 = u - fl; i1 = wrap_cell(fl, g.n1);
+            u = __dmul_rn(x2, g.s2); fl = floor(u); const double f2 = u - fl; iz = wrap_cell(fl, g.n2);
+            key = ((long long)i0 * g.n1 + i1) * g.n2 + iz;
+            const double e0 = 1.0 - f0, e1 = 1.0 - f1, e2 = 1.0 - f2;
+            if (MODE == 0) {
+                double a0 = e0, a1 = f0;
+                if (MASSKIND != 0) {
+                    const double m = MASSKIND == 2 ? __ldg(mass + p) : mass0;
+                    a0 *= m;
+                    a1 *= m;
+                }
+                double w;
+                w = a0 * e1; S000 = w * e2; S001 = w * f2;
+                w = a0 * f1; S010 = w * e2; S011 = w * f2;
+                w = a1 * e1; S100 = w * e2; S101 = w * f2;
+                w = a1 * f1; S110 = w * e2; S111 = w * f2;
+            } else {
+                const double* vp = vpos + 3 * p;
+                const double m = MASSKIND == 2 ? __ldg(mass + p) : (MASSKIND == 1 ? mass0 : 1.0);
+                const double q0 = m * __ldg(vp + 0) * g.s0, q1 = m * __ldg(vp + 1) * g.s1,
+                             q2 = m * __ldg(vp + 2) * g.s2;
+                const double vm = HAS_VMASS ? __ldg(vmass + p) : 0.0;
+#define VPM_TANGENT(W0, D0, W1, D1, SA, SB)                                          \
+    {                                                                                \
+        const double wxy = (W0) * (W1);                                              \
+        const double gxy = (D0) * (W1) + (W0) * (D1);                                \
+        const double base = HAS_VMASS ? vm * wxy : 0.0;                              \
+        SA = gxy * e2 - q2 * wxy + base * e2;                                        \
+        SB = gxy * f2 + q2 * wxy + base * f2;                                        \
+    }
+                VPM_TANGENT(e0, -q0, e1, -q1, S000, S001)
+                VPM_TANGENT(e0, -q0, f1, q1, S010, S011)
+                VPM_TANGENT(f0, q0, e1, -q1, S100, S101)
+                VPM_TANGENT(f0, q0, f1, q1, S110, S111)
+#undef VPM_TANGENT
+            }
+        }
+        // segmented inclusive scan over runs of equal cell key
+        const long long kprev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (kprev != key);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (heads != 0xffffffffu) {
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long kd = __shfl_up_sync(0xffffffffu, key, d);
+                const bool same = (lane >= d) && (kd == key);
+                if (!__any_sync(0xffffffffu, same)) break;
+#define VPM_SCAN(V)                                                                  \
+    {                                                                                \
+        const double tv = __shfl_up_sync(0xffffffffu, V, d);                         \
+        if (same) V += tv;                                                           \
+    }
+                VPM_SCAN(S000) VPM_SCAN(S001) VPM_SCAN(S010) VPM_SCAN(S011)
+                VPM_SCAN(S100) VPM_SCAN(S101) VPM_SCAN(S110) VPM_SCAN(S111)
+#undef VPM_SCAN
+            }
+        }
+        const long long knext = __shfl_down_sync(0xffffffffu, key, 1);
+        const bool tail = active && (lane == 31 || knext != key);
+        // z-merge: a run whose successor in this warp is cell z + 1 of the same row hands its
+        // c = 1 sums to that run instead of writing them
+        const bool hand_over = tail && lane < 31 && knext == key + 1 && iz + 1 < g.n2;
+        // the run before mine ends at lane (head of my run) - 1
+        const int myhead = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const int src = myhead - 1;
+        const long long ksrc = __shfl_sync(0xffffffffu, key, src < 0 ? 0 : src);
+        const bool take = tail && src >= 0 && ksrc == key - 1 && iz > 0;
+        {
+            const int sl = src < 0 ? 0 : src;
+            const double t0 = __shfl_sync(0xffffffffu, S001, sl);
+            const double t1 = __shfl_sync(0xffffffffu, S011, sl);
+            const double t2 = __shfl_sync(0xffffffffu, S101, sl);
+            const double t3 = __shfl_sync(0xffffffffu, S111, sl);
+            if (take) {
+                S000 += t0;
+                S010 += t1;
+                S100 += t2;
+                S110 += t3;
+            }
+        }
+        if (tail) {
+            const int j1 = wrap_inc(i1, g.n1), jz = wrap_inc(iz, g.n2);
+            const int la = local_plane(g, i0), lb = local_plane(g, wrap_inc(i0, g.n0));
+            double* r00 = out + (long long)la * g.stride0 + (long long)i1 * g.stride1;
+            double* r01 = out + (long long)la * g.stride0 + (long long)j1 * g.stride1;
+            double* r10 = out + (long long)lb * g.stride0 + (long long)i1 * g.stride1;
+            double* r11 = out + (long long)lb * g.stride0 + (long long)j1 * g.stride1;
+            if (la >= 0) {
+                atomicAdd(r00 + iz, S000);
+                atomicAdd(r01 + iz, S010);
+                if (!hand_over) {
+                    atomicAdd(r00 + jz, S001);
+                    atomicAdd(r01 + jz, S011);
+                }
+            }
+            if (lb >= 0) {
+                atomicAdd(r10 + iz, S100);
+                atomicAdd(r11 + iz, S110);
+                if (!hand_over) {
+                    atomicAdd(r10 + jz, S101);
+                    atomicAdd(r11 + jz, S111);
+                }
+            }
+        }
+    }
+}
+
 // Baseline: thread per particle, 8 fp64 reductions into global memory (RED.E.ADD.F64).
 template <bool HAS_MASS>
 __global__ void k_paint_atomic(Geo g, const double* __restrict__ x, const double* __restrict__ mass,
@@ -193,10 +555,116 @@ static void launch_paint_rows(vpm_ctx* ctx, const Geo& g, const double* xs, cons
     }
 }
 
+template <int MODE, int MK, bool HV>
+static void launch_tile_variant(vpm_ctx* ctx, const Geo& g, const TileDims& td, size_t smem,
+                                const double* xs, const double* mass, double mass0,
+                                const double* vpos, const double* vmass,
+                                const int32_t* cell_start, double* out) {
+    auto kern = k_paint_tile<MODE, MK, HV>;
+    static bool configured = false;  // one attribute call per instantiation
+    if (!configured) {
+        VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    const long long blocks = (long long)td.ntx * td.nty * td.ntz;
+    VPM_REQUIRE(blocks < (1LL << 31), "mesh too large for one launch");
+    VPM_LAUNCH(kern, (unsigned)blocks, TILE_WARPS * 32, smem, ctx->stream, g, td, xs, mass, mass0,
+               vpos, vmass, cell_start, out);
+}
+
+static int g_tile_override[3] = {0, 0, 0};
+static int g_paint_algo = 0;  // 0: warp-aggregated reductions (fast); 1: tile kernel (bit-reproducible)
+
+static void zero_mesh(vpm_ctx* ctx, const Geo& g, double* out) {
+    const long long total = (long long)g.nloc0 * g.n1 * g.n2;
+    if (total == 0) return;
+    if (g.stride1 == g.n2 && g.stride0 == (long long)g.n1 * g.n2) {
+        VPM_CUDA(cudaMemsetAsync(out, 0, (size_t)total * sizeof(double), ctx->stream));
+    } else {
+        unsigned zgrid = (unsigned)std::min<long long>(ceil_div(total, 256), 8LL * ctx->sm_count);
+        VPM_LAUNCH(k_zero_mesh, zgrid, 256, 0, ctx->stream, g, out);
+    }
+}
+
+template <int MODE>
+static void launch_paint_agg(vpm_ctx* ctx, const Geo& g, const double* xs, const double* mass,
+                             double mass0, const double* vpos, const double* vmass, long long np,
+                             double* out) {
+    zero_mesh(ctx, g, out);
+    if (np == 0) return;
+    const long long nchunk = (np + 31) / 32;
+    const unsigned grid = (unsigned)std::min<long long>(ceil_div(nchunk, 8), 64LL * ctx->sm_count);
+    const int mk = mass ? 2 : (mass0 == 1.0 ? 0 : 1);
+    cudaStream_t st = ctx->stream;
+#define VPM_AGG(MODE_, MK_, HV_) VPM_LAUNCH((k_paint_agg<MODE_, MK_, HV_>), grid, 256, 0, st, g, xs, mass, mass0, vpos, vmass, np, out)
+    if (MODE == 0) {
+        if (mk == 2) VPM_AGG(0, 2, false);
+        else if (mk == 1) VPM_AGG(0, 1, false);
+        else VPM_AGG(0, 0, false);
+    } else {
+        if (vmass) {
+            if (mk == 2) VPM_AGG(1, 2, true);
+            else if (mk == 1) VPM_AGG(1, 1, true);
+            else VPM_AGG(1, 0, true);
+        } else {
+            if (mk == 2) VPM_AGG(1, 2, false);
+            else if (mk == 1) VPM_AGG(1, 1, false);
+            else VPM_AGG(1, 0, false);
+        }
+    }
+#undef VPM_AGG
+}
+
+template <int MODE>
+static void launch_paint_tile(vpm_ctx* ctx, const Geo& g, const double* xs, const double* mass,
+                              double mass0, const double* vpos, const double* vmass,
+                              const int32_t* cell_start, double* out) {
+    if (g.nloc0 == 0) return;
+    TileDims td;
+    td.TX = std::min(g_tile_override[0] > 0 ? g_tile_override[0] : 4, g.nloc0);
+    td.TY = std::min(g_tile_override[1] > 0 ? g_tile_override[1] : 8, g.n1);
+    td.TZ = std::min(g_tile_override[2] > 0 ? g_tile_override[2] : 32, g.n2);
+    if ((td.TX * td.TY * td.TZ) & 1) td.TZ += 1;  // the zero fill writes double2
+    td.ntx = (g.nloc0 + td.TX - 1) / td.TX;
+    td.nty = (g.n1 + td.TY - 1) / td.TY;
+    td.ntz = (g.n2 + td.TZ - 1) / td.TZ;
+    const size_t smem = (size_t)4 * td.TX * td.TY * td.TZ * sizeof(double);
+    VPM_REQUIRE(smem <= 160 * 1024, "paint tile does not fit shared memory");
+    const int mk = mass ? 2 : (mass0 == 1.0 ? 0 : 1);
+#define VPM_TILE(MODE_, MK_, HV_) launch_tile_variant<MODE_, MK_, HV_>(ctx, g, td, smem, xs, mass, mass0, vpos, vmass, cell_start, out)
+    if (MODE == 0) {
+        if (mk == 2) VPM_TILE(0, 2, false);
+        else if (mk == 1) VPM_TILE(0, 1, false);
+        else VPM_TILE(0, 0, false);
+    } else {
+        if (vmass) {
+            if (mk == 2) VPM_TILE(1, 2, true);
+            else if (mk == 1) VPM_TILE(1, 1, true);
+            else VPM_TILE(1, 0, true);
+        } else {
+            if (mk == 2) VPM_TILE(1, 2, false);
+            else if (mk == 1) VPM_TILE(1, 1, false);
+            else VPM_TILE(1, 0, false);
+        }
+    }
+#undef VPM_TILE
+}
+
 extern "C" {
 
 int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass,
                      double mass0, int64_t np, const int32_t* cell_start, double* out) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && out && cell_start, "NULL argument");
+    VPM_REQUIRE(np == 0 || xs, "xs is NULL");
+    Geo g = make_geo(mesh);
+    if (g_paint_algo == 0) launch_paint_agg<0>(ctx, g, xs, mass, mass0, nullptr, nullptr, np, out);
+    else launch_paint_tile<0>(ctx, g, xs, mass, mass0, nullptr, nullptr, cell_start, out);
+    VPM_API_END
+}
+
+int vpm_paint_sorted_rows(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass,
+                          double mass0, int64_t np, const int32_t* cell_start, double* out) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx && out && cell_start, "NULL argument");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
@@ -212,8 +680,23 @@ int vpm_paint_jvp_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, c
     VPM_REQUIRE(ctx && out && cell_start, "NULL argument");
     VPM_REQUIRE(np == 0 || (xs && vpos), "xs / vpos is NULL");
     Geo g = make_geo(mesh);
-    launch_paint_rows<1>(ctx, g, xs, mass, mass0, vpos, vmass, cell_start, out);
+    if (g_paint_algo == 0) launch_paint_agg<1>(ctx, g, xs, mass, mass0, vpos, vmass, np, out);
+    else launch_paint_tile<1>(ctx, g, xs, mass, mass0, vpos, vmass, cell_start, out);
     VPM_API_END
+}
+
+int vpm_paint_set_algorithm(int algo) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(algo == 0 || algo == 1, "paint algorithm must be 0 (aggregated) or 1 (tile)");
+    g_paint_algo = algo;
+    VPM_API_END
+}
+
+int vpm_paint_set_tile(int tx, int ty, int tz) {
+    g_tile_override[0] = tx;
+    g_tile_override[1] = ty;
+    g_tile_override[2] = tz;
+    return 0;
 }
 
 int vpm_paint_atomic(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, const double* mass,

@@ -68,6 +68,13 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def set_paint_algorithm(name):
+    """'aggregated' (default): warp-aggregated fp64 reductions, fastest; 'tile': shared-memory
+    tiles, no atomics, run-to-run bit-identical meshes."""
+    algo = {'aggregated': 0, 'tile': 1}[name]
+    C.check(C.lib.vpm_paint_set_algorithm(algo))
+
+
 def _is_zero_literal(x):
     # vmad's ZeroGradient is an int subclass equal to 0; the literal 0 marks "no gradient"
     return isinstance(x, numbers.Number) and not isinstance(x, bool) and x == 0
@@ -898,6 +905,35 @@ class ParticleMesh(object):
         C.check(C.lib.vpm_paint_jvp_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr),
                                            m0, _ptr(vp3), _ptr(vm), x3.shape[0],
                                            _ptr(lay.cell_start), _ptr(o)))
+        return RealField(self, o)
+
+    def _paint_any_order(self, pos, mass=1.0):
+        """The aggregated-reduction kernel on particles in ANY order (it merges whatever equal
+        or z-adjacent cells happen to sit in neighbouring lanes); benchmark helper."""
+        rt = self.rt
+        _, x3 = self._pos3(pos)
+        rt.sync_stream()
+        C.check(C.lib.vpm_paint_set_algorithm(0))
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_paint_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), None, float(mass),
+                                       x3.shape[0], _ptr(self._dummy_cs()), _ptr(o)))
+        return RealField(self, o)
+
+    def _dummy_cs(self):
+        if 'dummy_cs' not in self._tables:
+            self._tables['dummy_cs'] = torch.zeros((4,), dtype=torch.int32, device=self.rt.device)
+        return self._tables['dummy_cs']
+
+    def paint_rows(self, pos, mass=1.0, layout=None):
+        """Ablation: the earlier row-gather formulation of the sorted paint."""
+        rt = self.rt
+        lay, x3, (mass,), _ = self._sorted(pos, layout, (mass,))
+        rt.sync_stream()
+        marr = mass.t if isinstance(mass, DeviceArray) else None
+        m0 = 1.0 if marr is not None else float(mass)
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_paint_sorted_rows(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr),
+                                            m0, x3.shape[0], _ptr(lay.cell_start), _ptr(o)))
         return RealField(self, o)
 
     def paint_atomic(self, pos, mass=1.0):
