@@ -94,6 +94,12 @@ int vpm_paint_set_algorithm(int algo);
 int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                      const double* mass, double mass0, int64_t np,
                      const int32_t* cell_start, double* out);
+/* mass = column `col` of an interleaved [np, ncomp] array (no gather of the column needed);
+ * used by the reverse sweep of the fused force operator (three paints of the columns of the
+ * force cotangent).  Always the aggregated-reduction algorithm. */
+int vpm_paint_sorted_col(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
+                         const double* mass2d, int ncomp, int col, int64_t np,
+                         const int32_t* cell_start, double* out);
 /* Tuning knob (benchmarks only): output tile extents of the sorted paint kernel in cells;
  * 0 keeps the default. */
 int vpm_paint_set_tile(int tx, int ty, int tz);
@@ -125,6 +131,12 @@ int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const dou
 int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
                      const double* x, const double* weight, double weight0, int64_t np,
                      double* value, double* grad);
+/* grad[p, :] = sum_d w3[p, d] * gradreadout(f_d, x_p) + gradreadout(r, x_p): the particle half
+ * of the reverse sweep of the fused force operator (readout.vjp x3 + paint.vjp, fastpm.py:229,
+ * 256) in one pass over the particles. */
+int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                      const double* f2, const double* r, const double* x, const double* w3,
+                      int64_t np, double* grad);
 /* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);
  * either term may be absent (NULL). */
 int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
@@ -164,6 +176,13 @@ int vpm_force_kspace(vpm_ctx* ctx, const int64_t nc[3], const double* rhok, doub
                      const double* kk0, const double* kk1, const double* kk2,
                      const double* a0, const double* a1, const double* a2,
                      double* p_out, double* g0, double* g1, double* g2);
+
+/* adjoint of vpm_force_kspace: rhok_bar = scale * L * (sum_d conj(a_d) g_d_bar + p_bar);
+ * p_bar may be NULL. */
+int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, const double* g1,
+                         const double* g2, const double* p_bar, double scale, const double* kk0,
+                         const double* kk1, const double* kk2, const double* a0, const double* a1,
+                         const double* a2, double* rhok_bar);
 
 /* ---- elementwise and reductions on flat fp64 arrays (the stdlib arithmetic that
  *      vmad applies to fields / particle arrays: vmad/core/stdlib/operators.py:14-152;

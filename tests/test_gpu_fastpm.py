@@ -15,8 +15,16 @@ def put(x):
     return DeviceArray.from_host(x)
 
 
+@pytest.fixture(params=[True, False], ids=['fused', 'unfused'])
+def fused(request):
+    from vmad_b200.lib import fastpm
+    fastpm.set_fused(request.param)
+    yield request.param
+    fastpm.set_fused(True)
+
+
 @pytest.mark.parametrize("name", ["nbody_8_2step", "nbody_16_3step"])
-def test_golden_on_device(device_pm, name):
+def test_golden_on_device(device_pm, fused, name):
     g = load_golden(name)
     pm = device_pm([int(g['N'])] * 3, g['BoxSize'])
     errs = run_golden_case(pm, g, tol=1e-10, put=put)
@@ -24,7 +32,7 @@ def test_golden_on_device(device_pm, name):
 
 
 @pytest.mark.parametrize("N,nsteps", [(32, 5), (64, 3)])
-def test_nbody_vs_oracle(oracle_pm, device_pm, N, nsteps):
+def test_nbody_vs_oracle(oracle_pm, device_pm, fused, N, nsteps):
     """config-1/2 style: white noise -> induce_correlation -> nbody, forward + vjp + jvp"""
     L = 100.0 * N / 32
     opm = oracle_pm([N] * 3, L)
@@ -50,3 +58,28 @@ def test_nbody_vs_oracle(oracle_pm, device_pm, N, nsteps):
     # displacements must be non-trivial (about a cell at a = 1) for the test to mean something
     assert numpy.std(res["oracle"][0]) > 0.5 * L / N
     assert all(e < 1e-10 for e in errs.values()), errs
+
+
+def test_force_operator_matches_gravity(device_pm):
+    """the fused force operator against the node-by-node gravity graph: f, potk, vjp, jvp"""
+    from vmad_b200 import Builder
+    from vmad_b200.lib import fastpm
+    N = 32
+    pm = device_pm([N] * 3, 100.0)
+    rng = numpy.random.default_rng(5)
+    q = pm.generate_uniform_particle_grid(shift=0.0)
+    dx = put(rng.standard_normal((N ** 3, 3)) * 2.5)
+    cf = put(rng.standard_normal((N ** 3, 3)))
+    cp = pm.create('complex', value=rng.standard_normal(pm.cshape) + 1j * rng.standard_normal(pm.cshape))
+    tan = put(rng.standard_normal((N ** 3, 3)))
+    out = {}
+    for name, op in [('gravity', fastpm.gravity), ('force', fastpm.force)]:
+        with Builder() as m:
+            x = m.input('x')
+            f, potk = op(x, q, pm)
+            m.output(f=f, potk=potk)
+        (f, potk), (g,) = m.compute_with_vjp(init=dict(x=dx), v=dict(_f=cf, _potk=cp))
+        _, (f_, potk_) = m.compute_with_jvp(['f', 'potk'], init=dict(x=dx), v=dict(x_=tan))
+        out[name] = [host(a) for a in (f, potk, g, f_, potk_)]
+    for a, b, what in zip(out['force'], out['gravity'], ['f', 'potk', 'vjp', 'jvp_f', 'jvp_potk']):
+        assert rel_l2(a, b) < 1e-12, (what, rel_l2(a, b))

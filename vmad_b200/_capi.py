@@ -58,6 +58,7 @@ SIGNATURES = {
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_paint_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
+    'vpm_paint_sorted_col': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int, c_int, c_int64, _P, _P]),
     'vpm_paint_set_algorithm': (c_int, [c_int]),
     'vpm_paint_set_tile': (c_int, [c_int, c_int, c_int]),
     'vpm_paint_sorted_rows': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     'vpm_readout3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_readout_grad': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, c_double, c_int64,
                                  _P, _P]),
+    'vpm_readout_grad4': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P]),
     'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
@@ -77,6 +79,8 @@ SIGNATURES = {
                                    c_int, c_int]),
     'vpm_force_kspace': (c_int, [c_void_p, POINTER(c_int64), _P, c_double, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P]),
+    'vpm_force_kspace_vjp': (c_int, [c_void_p, POINTER(c_int64), _P, _P, _P, _P, c_double, _P, _P, _P,
+                                     _P, _P, _P, _P]),
     'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),
     'vpm_mul': (c_int, [c_void_p, c_int64, _P, _P, _P]),
     'vpm_div': (c_int, [c_void_p, c_int64, _P, _P, _P]),

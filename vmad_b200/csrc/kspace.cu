@@ -113,6 +113,34 @@ k_force_kspace(CShape s, const double2* __restrict__ rhok, double scale,
     g2[e] = cmul(v, load_tab(a2, k, false));
 }
 
+// adjoint of k_force_kspace: rhok_bar = scale * L * (sum_d conj(a_d) g_d_bar + p_bar)
+__global__ void __launch_bounds__(KS_THREADS)
+k_force_kspace_vjp(CShape s, const double2* __restrict__ g0, const double2* __restrict__ g1,
+                   const double2* __restrict__ g2, const double2* __restrict__ p_bar, double scale,
+                   const double* __restrict__ kk0, const double* __restrict__ kk1,
+                   const double* __restrict__ kk2, const double* __restrict__ a0,
+                   const double* __restrict__ a1, const double* __restrict__ a2,
+                   double2* __restrict__ rhok_bar) {
+    long long e = blockIdx.x * (long long)KS_THREADS + threadIdx.x;
+    if (e >= s.total) return;
+    int i, j, k;
+    decompose(s, e, i, j, k);
+    double2 acc = cmul(g0[e], load_tab(a0, i, true));
+    double2 t = cmul(g1[e], load_tab(a1, j, true));
+    acc.x += t.x;
+    acc.y += t.y;
+    t = cmul(g2[e], load_tab(a2, k, true));
+    acc.x += t.x;
+    acc.y += t.y;
+    if (p_bar) {
+        const double2 pb = p_bar[e];
+        acc.x += pb.x;
+        acc.y += pb.y;
+    }
+    const double L = green(kk0, kk1, kk2, i, j, k) * scale;
+    rhok_bar[e] = make_double2(acc.x * L, acc.y * L);
+}
+
 // ---- Hermitian-weighted reduction sum_k w_k x conj(y) -----------------------------------
 constexpr int RED_THREADS = 256;
 
@@ -231,6 +259,21 @@ int vpm_force_kspace(vpm_ctx* ctx, const int64_t nc[3], const double* rhok, doub
                reinterpret_cast<const double2*>(rhok), scale, kk0, kk1, kk2, a0, a1, a2,
                reinterpret_cast<double2*>(p_out), reinterpret_cast<double2*>(g0),
                reinterpret_cast<double2*>(g1), reinterpret_cast<double2*>(g2));
+    VPM_API_END
+}
+
+int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, const double* g1,
+                         const double* g2, const double* p_bar, double scale, const double* kk0,
+                         const double* kk1, const double* kk2, const double* a0, const double* a1,
+                         const double* a2, double* rhok_bar) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && g0 && g1 && g2 && kk0 && kk1 && kk2 && a0 && a1 && a2 && rhok_bar, "NULL argument");
+    CShape s = make_cshape(nc);
+    unsigned grid = (unsigned)ceil_div(s.total, KS_THREADS);
+    VPM_LAUNCH(k_force_kspace_vjp, grid, KS_THREADS, 0, ctx->stream, s,
+               reinterpret_cast<const double2*>(g0), reinterpret_cast<const double2*>(g1),
+               reinterpret_cast<const double2*>(g2), reinterpret_cast<const double2*>(p_bar), scale,
+               kk0, kk1, kk2, a0, a1, a2, reinterpret_cast<double2*>(rhok_bar));
     VPM_API_END
 }
 

@@ -364,8 +364,8 @@ k_paint_tile(Geo g, TileDims td, const double* __restrict__ xs, const double* __
 template <int MODE, int MASSKIND, bool HAS_VMASS>
 __global__ void __launch_bounds__(256)
 k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, double mass0,
-            const double* __restrict__ vpos, const double* __restrict__ vmass, long long np,
-            double* __restrict__ out) {
+            int mstride, const double* __restrict__ vpos, const double* __restrict__ vmass,
+            long long np, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long long nchunk = (np + 31) >> 5;
     const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -389,7 +389,7 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
             if (MODE == 0) {
                 double a0 = e0, a1 = f0;
                 if (MASSKIND != 0) {
-                    const double m = MASSKIND == 2 ? __ldg(mass + p) : mass0;
+                    const double m = MASSKIND == 2 ? __ldg(mass + p * mstride) : mass0;
                     a0 *= m;
                     a1 *= m;
                 }
@@ -400,7 +400,7 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
                 w = a1 * f1; S110 = w * e2; S111 = w * f2;
             } else {
                 const double* vp = vpos + 3 * p;
-                const double m = MASSKIND == 2 ? __ldg(mass + p) : (MASSKIND == 1 ? mass0 : 1.0);
+                const double m = MASSKIND == 2 ? __ldg(mass + p * mstride) : (MASSKIND == 1 ? mass0 : 1.0);
                 const double q0 = m * __ldg(vp + 0) * g.s0, q1 = m * __ldg(vp + 1) * g.s1,
                              q2 = m * __ldg(vp + 2) * g.s2;
                 const double vm = HAS_VMASS ? __ldg(vmass + p) : 0.0;
@@ -589,14 +589,14 @@ static void zero_mesh(vpm_ctx* ctx, const Geo& g, double* out) {
 template <int MODE>
 static void launch_paint_agg(vpm_ctx* ctx, const Geo& g, const double* xs, const double* mass,
                              double mass0, const double* vpos, const double* vmass, long long np,
-                             double* out) {
+                             double* out, int mstride = 1) {
     zero_mesh(ctx, g, out);
     if (np == 0) return;
     const long long nchunk = (np + 31) / 32;
     const unsigned grid = (unsigned)std::min<long long>(ceil_div(nchunk, 8), 64LL * ctx->sm_count);
     const int mk = mass ? 2 : (mass0 == 1.0 ? 0 : 1);
     cudaStream_t st = ctx->stream;
-#define VPM_AGG(MODE_, MK_, HV_) VPM_LAUNCH((k_paint_agg<MODE_, MK_, HV_>), grid, 256, 0, st, g, xs, mass, mass0, vpos, vmass, np, out)
+#define VPM_AGG(MODE_, MK_, HV_) VPM_LAUNCH((k_paint_agg<MODE_, MK_, HV_>), grid, 256, 0, st, g, xs, mass, mass0, mstride, vpos, vmass, np, out)
     if (MODE == 0) {
         if (mk == 2) VPM_AGG(0, 2, false);
         else if (mk == 1) VPM_AGG(0, 1, false);
@@ -682,6 +682,17 @@ int vpm_paint_jvp_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, c
     Geo g = make_geo(mesh);
     if (g_paint_algo == 0) launch_paint_agg<1>(ctx, g, xs, mass, mass0, vpos, vmass, np, out);
     else launch_paint_tile<1>(ctx, g, xs, mass, mass0, vpos, vmass, cell_start, out);
+    VPM_API_END
+}
+
+int vpm_paint_sorted_col(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass2d,
+                         int ncomp, int col, int64_t np, const int32_t* cell_start, double* out) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && out && mass2d, "NULL argument");
+    VPM_REQUIRE(ncomp >= 1 && col >= 0 && col < ncomp, "bad column");
+    VPM_REQUIRE(np == 0 || xs, "xs is NULL");
+    Geo g = make_geo(mesh);
+    launch_paint_agg<0>(ctx, g, xs, mass2d + col, 1.0, nullptr, nullptr, np, out, ncomp);
     VPM_API_END
 }
 

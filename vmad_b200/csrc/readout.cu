@@ -137,6 +137,52 @@ k_readout_grad(Geo g, const double* __restrict__ field, const double* __restrict
     grad[3 * p + 2] = g2 * w;
 }
 
+// grad[p, :] = sum_d w[p, d] * grad_readout(F_d, x_p) + grad_readout(R, x_p): the particle half
+// of the reverse sweep of a fused force evaluation, one pass over the particles for the four
+// meshes (F_0, F_1, F_2: the force components; R: the density cotangent)
+__global__ void __launch_bounds__(256)
+k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__ F1,
+                const double* __restrict__ F2, const double* __restrict__ R,
+                const double* __restrict__ x, const double* __restrict__ w3, long long np,
+                double* __restrict__ grad) {
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    Stencil s = make_stencil(g, x, p);
+    const double wa = __ldg(w3 + 3 * p + 0), wb = __ldg(w3 + 3 * p + 1), wc = __ldg(w3 + 3 * p + 2);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const double w2a = 1.0 - s.f2, w2b = s.f2;
+#pragma unroll
+    for (int ab = 0; ab < 4; ++ab) {
+        if (s.off[ab] < 0) continue;
+        const int a = ab >> 1, b = ab & 1;
+        const double w0 = a ? s.f0 : 1.0 - s.f0;
+        const double w1 = b ? s.f1 : 1.0 - s.f1;
+        const double d0 = a ? g.s0 : -g.s0;
+        const double d1 = b ? g.s1 : -g.s1;
+        double u0, u1, t0, t1;
+        // combined mesh value seen by this particle: m = wa F0 + wb F1 + wc F2 + R
+        load_pair(F0, s.off[ab], s.i2, s.j2, t0, t1);
+        u0 = wa * t0;
+        u1 = wa * t1;
+        load_pair(F1, s.off[ab], s.i2, s.j2, t0, t1);
+        u0 += wb * t0;
+        u1 += wb * t1;
+        load_pair(F2, s.off[ab], s.i2, s.j2, t0, t1);
+        u0 += wc * t0;
+        u1 += wc * t1;
+        load_pair(R, s.off[ab], s.i2, s.j2, t0, t1);
+        u0 += t0;
+        u1 += t1;
+        const double wxy = w0 * w1;
+        a0 += u0 * ((d0 * w1) * w2a) + u1 * ((d0 * w1) * w2b);
+        a1 += u0 * ((w0 * d1) * w2a) + u1 * ((w0 * d1) * w2b);
+        a2 += (u1 - u0) * (wxy * g.s2);
+    }
+    grad[3 * p + 0] = a0;
+    grad[3 * p + 1] = a1;
+    grad[3 * p + 2] = a2;
+}
+
 template <bool HAS_FDOT, bool HAS_XDOT>
 __global__ void __launch_bounds__(256)
 k_readout_jvp(Geo g, const double* __restrict__ field, const double* __restrict__ field_dot,
@@ -202,6 +248,20 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, co
         else if (weight) VPM_LAUNCH((k_readout_grad<true, false>), grid, 256, 0, st, g, field, x, weight, weight0, (long long)np, value, grad);
         else if (value) VPM_LAUNCH((k_readout_grad<false, true>), grid, 256, 0, st, g, field, x, weight, weight0, (long long)np, value, grad);
         else VPM_LAUNCH((k_readout_grad<false, false>), grid, 256, 0, st, g, field, x, weight, weight0, (long long)np, value, grad);
+    }
+    VPM_API_END
+}
+
+int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                      const double* f2, const double* r, const double* x, const double* w3,
+                      int64_t np, double* grad) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx, "ctx is NULL");
+    Geo g = make_geo(mesh);
+    if (np > 0) {
+        VPM_REQUIRE(f0 && f1 && f2 && r && x && w3 && grad, "NULL array");
+        VPM_LAUNCH(k_readout_grad4, (unsigned)ceil_div(np, 256), 256, 0, ctx->stream, g, f0, f1, f2, r,
+                   x, w3, (long long)np, grad);
     }
     VPM_API_END
 }

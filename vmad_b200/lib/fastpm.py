@@ -406,16 +406,23 @@ def DriftFactor(pt, ai, ac, af):
     return 1 / (ac ** 3 * pt.E(ac)) * (pt.Gp(af) - pt.Gp(ai)) / pt.gp(ac)
 
 
-def _leapfrog_body(dx, p, stages, pt, force_fn):
-    """kick-drift-kick stepping of fastpm.py:455-473 around a force callback"""
+def _leapfrog_body(dx, p, stages, pt, force_fn, fused=False):
+    """kick-drift-kick stepping of fastpm.py:455-473 around a force callback; ``fused`` swaps
+    the stdlib mul + add pairs for the single-pass kick / drift operators (same values)"""
     Om0 = pt.Om0
+    if fused:
+        do_kick = lambda p, f, c: kick(p, f, c)
+        do_drift = lambda dx, p, c: drift(dx, p, c)
+    else:
+        do_kick = lambda p, f, c: p + f * c
+        do_drift = lambda dx, p, c: dx + p * c
     f, potk = force_fn(dx)
     for ai, af in zip(stages[:-1], stages[1:]):
         ac = (ai * af) ** 0.5
-        p = p + f * (KickFactor(pt, ai, ai, ac) * 1.5 * Om0)       # kick
-        dx = dx + p * DriftFactor(pt, ai, ac, af)                  # drift
-        f, potk = force_fn(dx)                                     # force
-        p = p + f * (KickFactor(pt, ac, af, af) * 1.5 * Om0)       # kick
+        p = do_kick(p, f, KickFactor(pt, ai, ai, ac) * 1.5 * Om0)
+        dx = do_drift(dx, p, DriftFactor(pt, ai, ac, af))
+        f, potk = force_fn(dx)
+        p = do_kick(p, f, KickFactor(pt, ac, af, af) * 1.5 * Om0)
     f = f * (1.5 * Om0)
     return dict(dx=dx, p=p, f=f)
 
@@ -424,6 +431,8 @@ def _leapfrog_body(dx, p, stages, pt, force_fn):
 def leapfrog(dx_i, p_i, q, stages, pt, pm):
     """fastpm.py:446-474"""
     q = _localize(q, pm)
+    if _fusable(pm):
+        return _leapfrog_body(dx_i, p_i, stages, pt, lambda dx: force(dx, q, pm), fused=True)
     return _leapfrog_body(dx_i, p_i, stages, pt, lambda dx: gravity(dx, q, pm))
 
 
@@ -509,4 +518,98 @@ class FastPMSimulation(object):
     @autooperator('rhok->dx,p,f')
     def run(self, rhok):
         dx, p = self.firststep(rhok)
+        if _fusable(self.fpm):
+            return _leapfrog_body(dx, p, self.stages, self.pt,
+                                  lambda dx: force(dx, self.q, self.fpm), fused=True)
         return _leapfrog_body(dx, p, self.stages, self.pt, lambda dx: self.gravity(dx))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused operators named by the north star: force, kick, drift (not in the reference, where
+# they are sub-graphs of stdlib mul / add nodes and the `gravity` autooperator, fastpm.py:409-474)
+# ---------------------------------------------------------------------------------------------
+USE_FUSED = True   # leapfrog / nbody / FastPMSimulation use force / kick / drift on the device
+
+
+def set_fused(flag):
+    """switch the leapfrog between the fused operators and the reference's node-by-node graph;
+    drops the memoised models so that the next build sees the new setting"""
+    global USE_FUSED
+    USE_FUSED = bool(flag)
+    for op in (leapfrog, nbody, FastPMSimulation.run):
+        op._model_cache.clear()
+
+
+def _fusable(pm):
+    return USE_FUSED and hasattr(pm, 'rt') and pm.ndim == 3
+
+
+@operator
+class force:
+    """``f, potk = gravity(dx, q, pm)`` (fastpm.py:409-438) as ONE operator with hand-written
+    vjp and jvp: decompose + exchange + paint + FFT + fused Green/gradient pass + 3 inverse FFTs
+    + fused 3-mesh readout + gather.  Device backend only; ``gravity`` is the portable graph."""
+    ain = {'dx': 'ndarray'}
+    aout = [('f', 'ndarray'), ('potk', 'ComplexField')]
+
+    def apl(node, dx, q, pm):
+        from .. import pm as dev
+        f, potk, state = dev.force_apl(pm, dx, q)
+        return dict(f=f, potk=potk, state=state)
+
+    def vjp(node, _f, _potk, state, pm):
+        from .. import pm as dev
+        return dict(_dx=dev.force_vjp(pm, state, _f, _potk))
+
+    def jvp(node, dx_, state, pm):
+        from .. import pm as dev
+        f_, potk_ = dev.force_jvp(pm, state, dx_)
+        return dict(f_=f_, potk_=potk_)
+
+
+def _axpy(y, x, fac):
+    """y + x * fac in one pass on the device"""
+    ax = getattr(y, '_axpby', None)
+    if ax is not None and hasattr(x, 't') and x.t.shape == y.t.shape:
+        return ax(1.0, float(fac), x.t)
+    return y + x * fac
+
+
+@operator
+class kick:
+    """``p + f * fac`` (fastpm.py:459-460,470-471)"""
+    ain = 'p', 'f'
+    aout = 'y'
+
+    def apl(node, p, f, fac):
+        return dict(y=_axpy(p, f, fac))
+
+    def vjp(node, _y, fac):
+        return dict(_p=_y, _f=_y * fac)
+
+    def jvp(node, p_, f_, fac):
+        if _is_zero(f_):
+            return dict(y_=p_)
+        if _is_zero(p_):
+            return dict(y_=f_ * fac)
+        return dict(y_=_axpy(p_, f_, fac))
+
+
+@operator
+class drift:
+    """``dx + p * fac`` (fastpm.py:463-464)"""
+    ain = 'dx', 'p'
+    aout = 'y'
+
+    def apl(node, dx, p, fac):
+        return dict(y=_axpy(dx, p, fac))
+
+    def vjp(node, _y, fac):
+        return dict(_dx=_y, _p=_y * fac)
+
+    def jvp(node, dx_, p_, fac):
+        if _is_zero(p_):
+            return dict(y_=dx_)
+        if _is_zero(dx_):
+            return dict(y_=p_ * fac)
+        return dict(y_=_axpy(dx_, p_, fac))

@@ -1115,3 +1115,107 @@ class ParticleMesh(object):
                                        _ptr(grad_tables[1]), _ptr(grad_tables[2]), _ptr(p),
                                        _ptr(g[0]), _ptr(g[1]), _ptr(g[2])))
         return (ComplexField(self, p) if want_p else None), [ComplexField(self, t) for t in g]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused force evaluation (the `gravity` graph of fastpm.py:409-438 as three calls)
+# ---------------------------------------------------------------------------------------------
+class ForceState(object):
+    """what one fused force evaluation leaves on the tape for its vjp / jvp"""
+    __slots__ = ('xl', 'layout', 'F', 'scale', 'grad_tables')
+
+    def __init__(self, xl, layout, F, scale, grad_tables):
+        self.xl = xl
+        self.layout = layout
+        self.F = F
+        self.scale = scale
+        self.grad_tables = grad_tables
+
+
+def _force_tables(pm, order=1):
+    """per-axis finite-difference gradient tables -i (8 sin w - sin 2w) / (6 h) (fastpm.py:316-323),
+    evaluated once on the host with numpy -- the numbers the oracle uses"""
+    key = ('force_tables', order)
+    if key not in pm._tables:
+        tabs = []
+        for d in range(3):
+            h = pm.BoxSize[d] / pm.Nmesh[d]
+            w = pm.freq_index(d) * (2 * numpy.pi / pm.BoxSize[d]) * h
+            a = 1 / (6.0 * h) * (8 * numpy.sin(w) - numpy.sin(2 * w))
+            tabs.append(_upload(-1j * a))
+        pm._tables[key] = tabs
+    return pm._tables[key]
+
+
+def force_apl(pm, dx, q):
+    """f = -grad laplace^-1 (rho Nc / Np) read out at x = q + dx; returns (f, potk, state)"""
+    if pm.ndim != 3:
+        raise ValueError("the fused force operator is 3-D only")
+    rt = pm.rt
+    q = asdevice(q)
+    dx = asdevice(dx)
+    x = q + dx
+    layout = pm.decompose(x)
+    xl = layout.exchange(x)
+    rho = pm.paint(xl, 1.0)
+    rhok = pm._r2c(rho, 1.0)                                   # un-normalised cuFFT output
+    npart = pm.comm.allreduce(len(q))
+    scale = 1.0 / npart                                        # (Nc / Np) * (1 / Nc)
+    tabs = _force_tables(pm)
+    potk, g = pm.force_kspace(rhok, scale, tabs, want_p=True)
+    F = [pm._c2r(gd, 1.0) for gd in g]
+    fl = pm.readout3(F[0], F[1], F[2], xl)
+    f = layout.gather(fl)
+    return f, potk, ForceState(xl, layout, F, scale, tabs)
+
+
+def force_vjp(pm, st, _f, _potk):
+    """reverse sweep of force_apl: cotangents of (f, potk) -> cotangent of dx"""
+    rt = pm.rt
+    lay, xl = st.layout, st.xl
+    f_zero = _is_zero_literal(_f)
+    n = xl.t.shape[0]
+    if f_zero:
+        _fl = DeviceArray(torch.zeros((n, 3), dtype=_F8, device=rt.device))
+    else:
+        _fl = lay.exchange(asdevice(_f))
+    # readout.vjp (mesh half) x3 -> c2r.vjp x3: three paints of the columns, three forward FFTs
+    gbar = []
+    rt.sync_stream()
+    for d in range(3):
+        m = rt.empty(pm.rshape)
+        C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(pm._mesh), _ptr(xl.t), _ptr(_fl.t),
+                                           3, d, n, _ptr(lay.cell_start), _ptr(m)))
+        gbar.append(pm._r2c(RealField(pm, m), 1.0))
+    pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
+    rhok_bar = rt.empty(pm.cshape, _C16)
+    C.check(C.lib.vpm_force_kspace_vjp(
+        rt.ctx, C.i3(pm._cshape3), _ptr(gbar[0].t), _ptr(gbar[1].t), _ptr(gbar[2].t),
+        _ptr(pbar.t) if pbar is not None else None, float(st.scale), _ptr(pm._k_table(0)),
+        _ptr(pm._k_table(1)), _ptr(pm._k_table(2)), _ptr(st.grad_tables[0]),
+        _ptr(st.grad_tables[1]), _ptr(st.grad_tables[2]), _ptr(rhok_bar)))
+    # r2c.vjp of the un-normalised transform is the un-normalised inverse
+    rho_bar = pm._c2r(ComplexField(pm, rhok_bar), 1.0)
+    # particle half: readout.vjp x3 and paint.vjp in one pass
+    g = rt.empty((n, 3))
+    C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(st.F[0].t), _ptr(st.F[1].t),
+                                    _ptr(st.F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
+                                    _ptr(g)))
+    return lay.gather(DeviceArray(g))
+
+
+def force_jvp(pm, st, dx_):
+    """forward-mode sweep of force_apl: tangent of dx -> tangents of (f, potk)"""
+    rt = pm.rt
+    lay, xl = st.layout, st.xl
+    if _is_zero_literal(dx_):
+        return 0, 0
+    xl_ = lay.exchange(asdevice(dx_))
+    rho_ = pm.paint_jvp(xl, mass=1.0, v_pos=xl_)
+    rhok_ = pm._r2c(rho_, 1.0)
+    potk_, g_ = pm.force_kspace(rhok_, st.scale, st.grad_tables, want_p=True)
+    cols = []
+    for d in range(3):
+        Fd_ = pm._c2r(g_[d], 1.0)
+        cols.append(pm._readout_jvp(st.F[d], xl, Fd_, xl_, None))
+    return lay.gather(stack(cols, axis=-1)), potk_
