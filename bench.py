@@ -231,6 +231,7 @@ def run_gpu(args):
 
     N = args.nmesh
     pm = ParticleMesh([N] * 3, 100.0 * N / 32)
+    pm.force_recompute = N >= 512  # keep potk instead of 3 force meshes per step on the tape
     wn_h, cot_h = make_inputs(N)
     q = pm.generate_uniform_particle_grid(shift=0.0)
     stages = numpy.linspace(0.1, 1.0, args.nsteps + 1)

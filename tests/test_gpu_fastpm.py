@@ -73,7 +73,8 @@ def test_force_operator_matches_gravity(device_pm):
     cp = pm.create('complex', value=rng.standard_normal(pm.cshape) + 1j * rng.standard_normal(pm.cshape))
     tan = put(rng.standard_normal((N ** 3, 3)))
     out = {}
-    for name, op in [('gravity', fastpm.gravity), ('force', fastpm.force)]:
+    for name, op in [('gravity', fastpm.gravity), ('force', fastpm.force), ('force_rc', fastpm.force)]:
+        pm.force_recompute = (name == 'force_rc')
         with Builder() as m:
             x = m.input('x')
             f, potk = op(x, q, pm)
@@ -81,5 +82,6 @@ def test_force_operator_matches_gravity(device_pm):
         (f, potk), (g,) = m.compute_with_vjp(init=dict(x=dx), v=dict(_f=cf, _potk=cp))
         _, (f_, potk_) = m.compute_with_jvp(['f', 'potk'], init=dict(x=dx), v=dict(x_=tan))
         out[name] = [host(a) for a in (f, potk, g, f_, potk_)]
-    for a, b, what in zip(out['force'], out['gravity'], ['f', 'potk', 'vjp', 'jvp_f', 'jvp_potk']):
-        assert rel_l2(a, b) < 1e-12, (what, rel_l2(a, b))
+    for variant in ('force', 'force_rc'):
+        for a, b, what in zip(out[variant], out['gravity'], ['f', 'potk', 'vjp', 'jvp_f', 'jvp_potk']):
+            assert rel_l2(a, b) < 1e-12, (variant, what, rel_l2(a, b))

@@ -46,7 +46,7 @@ def test_keys_and_layout_bit_exact(oracle_pm, device_pm, Nmesh, BoxSize, n):
     dkeys = dpm.cell_keys(x).cpu().numpy()
     assert numpy.array_equal(okeys, dkeys)
     olay = opm.decompose(x)
-    dlay = dpm.decompose(x)
+    dlay = dpm.decompose(x, keep_index=True)
     assert numpy.array_equal(dlay.keys.cpu().numpy(), okeys)
     assert numpy.array_equal(dlay.indices.cpu().numpy(), olay.indices)
     cs = dlay.cell_start.cpu().numpy()

@@ -68,11 +68,17 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_KEEP_CELL_INDEX = False
+
+
 def set_paint_algorithm(name):
     """'aggregated' (default): warp-aggregated fp64 reductions, fastest; 'tile': shared-memory
-    tiles, no atomics, run-to-run bit-identical meshes."""
+    tiles, no atomics, run-to-run bit-identical meshes (needs the per-cell offsets, so layouts
+    keep them while it is selected)."""
+    global _KEEP_CELL_INDEX
     algo = {'aggregated': 0, 'tile': 1}[name]
     C.check(C.lib.vpm_paint_set_algorithm(algo))
+    _KEEP_CELL_INDEX = (algo == 1)
 
 
 def _is_zero_literal(x):
@@ -608,9 +614,9 @@ class Layout(object):
 
     def __init__(self, pm, keys, perm, cell_start, oldlength):
         self.pm = pm
-        self.keys = keys            # int32 [np]   cell key of every input particle
+        self.keys = keys            # int32 [np]   cell key of every input particle (or None)
         self.indices = perm         # int32 [np]   slot -> input particle (stable)
-        self.cell_start = cell_start  # int32 [ncell + 1]
+        self.cell_start = cell_start  # int32 [ncell + 1] (or None: only the tile paint needs it)
         self.oldlength = oldlength
         self.newlength = int(perm.shape[0])
 
@@ -812,7 +818,10 @@ class ParticleMesh(object):
         C.check(C.lib.vpm_cell_keys(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), n, _ptr(keys)))
         return keys
 
-    def decompose(self, pos, smoothing=None):
+    def decompose(self, pos, smoothing=None, keep_index=None):
+        """``keep_index``: also keep the cell keys and cell offsets on the layout (the sorted
+        permutation alone is what exchange / gather and the default paint need; the layout sits
+        on the tape of every force evaluation, so the extra 8 B/particle + 4 B/cell matter)"""
         rt = self.rt
         rt.sync_stream()
         _, x3 = self._pos3(pos)
@@ -822,6 +831,10 @@ class ParticleMesh(object):
         cell_start = rt.empty((self._ncell + 1,), torch.int32)
         C.check(C.lib.vpm_layout_build(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), n, _ptr(keys),
                                        _ptr(perm), _ptr(cell_start)))
+        if keep_index is None:
+            keep_index = _KEEP_CELL_INDEX
+        if not keep_index:
+            keys = cell_start = None
         return Layout(self, keys, perm, cell_start, n)
 
     def _sorted(self, pos, layout, extras=()):
@@ -854,8 +867,20 @@ class ParticleMesh(object):
         m0 = 1.0 if marr is not None else float(mass)
         o = rt.empty(self.rshape)
         C.check(C.lib.vpm_paint_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr), m0,
-                                       x3.shape[0], _ptr(lay.cell_start), _ptr(o)))
+                                       x3.shape[0], _ptr(self._cell_start_of(lay, x3)), _ptr(o)))
         return RealField(self, o)
+
+    def _cell_start_of(self, lay, x3):
+        """cell offsets for the kernels that need them (tile / row paint); rebuilt from the
+        sorted positions when the layout did not keep them"""
+        if lay.cell_start is not None:
+            return lay.cell_start
+        if not _KEEP_CELL_INDEX:
+            return self._dummy_cs()  # the aggregated paint ignores it
+        lay2 = self.decompose(DeviceArray(x3 if self.ndim == 3 else x3[:, 1:].contiguous()),
+                              keep_index=True)
+        lay.cell_start = lay2.cell_start
+        return lay.cell_start
 
     def paint_vjp(self, v, pos, layout=None, mass=1.0, resampler=None):
         """returns ``(_pos, _mass)`` (fastpm.py:229)."""
@@ -904,7 +929,7 @@ class ParticleMesh(object):
         o = rt.empty(self.rshape)
         C.check(C.lib.vpm_paint_jvp_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr),
                                            m0, _ptr(vp3), _ptr(vm), x3.shape[0],
-                                           _ptr(lay.cell_start), _ptr(o)))
+                                           _ptr(self._cell_start_of(lay, x3)), _ptr(o)))
         return RealField(self, o)
 
     def _paint_any_order(self, pos, mass=1.0):
@@ -932,6 +957,8 @@ class ParticleMesh(object):
         marr = mass.t if isinstance(mass, DeviceArray) else None
         m0 = 1.0 if marr is not None else float(mass)
         o = rt.empty(self.rshape)
+        if lay.cell_start is None:
+            lay = self.decompose(DeviceArray(x3), keep_index=True)
         C.check(C.lib.vpm_paint_sorted_rows(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr),
                                             m0, x3.shape[0], _ptr(lay.cell_start), _ptr(o)))
         return RealField(self, o)
@@ -1122,14 +1149,27 @@ class ParticleMesh(object):
 # ---------------------------------------------------------------------------------------------
 class ForceState(object):
     """what one fused force evaluation leaves on the tape for its vjp / jvp"""
-    __slots__ = ('xl', 'layout', 'F', 'scale', 'grad_tables')
+    __slots__ = ('xl', 'layout', 'F', 'potk', 'scale', 'grad_tables')
 
-    def __init__(self, xl, layout, F, scale, grad_tables):
+    def __init__(self, xl, layout, F, potk, scale, grad_tables):
         self.xl = xl
         self.layout = layout
-        self.F = F
+        self.F = F            # the three real force meshes, or None when they are recomputed
+        self.potk = potk      # kept only when F is not (1 complex mesh instead of 3 real ones)
         self.scale = scale
         self.grad_tables = grad_tables
+
+    def meshes(self, pm):
+        if self.F is not None:
+            return self.F
+        return [pm._c2r(pm._transfer(self.potk, tables=_only(d, self.grad_tables[d])), 1.0)
+                for d in range(3)]
+
+
+def _only(d, table):
+    t = [None, None, None]
+    t[d] = table
+    return t
 
 
 def _force_tables(pm, order=1):
@@ -1166,7 +1206,10 @@ def force_apl(pm, dx, q):
     F = [pm._c2r(gd, 1.0) for gd in g]
     fl = pm.readout3(F[0], F[1], F[2], xl)
     f = layout.gather(fl)
-    return f, potk, ForceState(xl, layout, F, scale, tabs)
+    if getattr(pm, 'force_recompute', False):
+        # trade 3 inverse FFTs in the reverse sweep for 2/3 of the mesh memory on the tape
+        return f, potk, ForceState(xl, layout, None, potk, scale, tabs)
+    return f, potk, ForceState(xl, layout, F, None, scale, tabs)
 
 
 def force_vjp(pm, st, _f, _potk):
@@ -1185,7 +1228,7 @@ def force_vjp(pm, st, _f, _potk):
     for d in range(3):
         m = rt.empty(pm.rshape)
         C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(pm._mesh), _ptr(xl.t), _ptr(_fl.t),
-                                           3, d, n, _ptr(lay.cell_start), _ptr(m)))
+                                           3, d, n, _ptr(pm._dummy_cs()), _ptr(m)))
         gbar.append(pm._r2c(RealField(pm, m), 1.0))
     pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
     rhok_bar = rt.empty(pm.cshape, _C16)
@@ -1197,9 +1240,11 @@ def force_vjp(pm, st, _f, _potk):
     # r2c.vjp of the un-normalised transform is the un-normalised inverse
     rho_bar = pm._c2r(ComplexField(pm, rhok_bar), 1.0)
     # particle half: readout.vjp x3 and paint.vjp in one pass
+    F = st.meshes(pm)
+    rt.sync_stream()
     g = rt.empty((n, 3))
-    C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(st.F[0].t), _ptr(st.F[1].t),
-                                    _ptr(st.F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
+    C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
+                                    _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
                                     _ptr(g)))
     return lay.gather(DeviceArray(g))
 
@@ -1215,7 +1260,8 @@ def force_jvp(pm, st, dx_):
     rhok_ = pm._r2c(rho_, 1.0)
     potk_, g_ = pm.force_kspace(rhok_, st.scale, st.grad_tables, want_p=True)
     cols = []
+    F = st.meshes(pm)
     for d in range(3):
         Fd_ = pm._c2r(g_[d], 1.0)
-        cols.append(pm._readout_jvp(st.F[d], xl, Fd_, xl_, None))
+        cols.append(pm._readout_jvp(F[d], xl, Fd_, xl_, None))
     return lay.gather(stack(cols, axis=-1)), potk_
