@@ -912,6 +912,10 @@ class ParticleMesh(object):
     def paint_jvp(self, pos, v_mass=None, mass=1.0, v_pos=None, layout=None, resampler=None):
         """fastpm.py:238."""
         rt = self.rt
+        if _is_zero_literal(v_pos):
+            v_pos = None
+        if _is_zero_literal(v_mass):
+            v_mass = None
         if v_pos is None and v_mass is None:
             return self.create('real')
         if v_pos is None:
@@ -1029,6 +1033,10 @@ class ParticleMesh(object):
     def _readout_jvp(self, field, pos, v_self, v_pos, layout):
         rt = self.rt
         pos = asdevice(pos)
+        if _is_zero_literal(v_self):
+            v_self = None
+        if _is_zero_literal(v_pos):
+            v_pos = None
         if v_self is None and v_pos is None:
             return 0
         if layout is not None:
