@@ -83,6 +83,15 @@ int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64
 int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n,
                          int ncomp, double* dst);
 
+/* Routing for the slab decomposition over `nranks` ranks (rank r owns planes
+ * [r n0/nranks, (r+1) n0/nranks)): a particle is sent to the owner of its floor plane and, when
+ * different, to the owner of the next plane.  send_idx[send_start[d] .. send_start[d+1]) are the
+ * particle indices bound for rank d, in original order (stable).  send_start_host[nranks + 1]
+ * is delivered to the host (this call synchronises: the counts size the all-to-all, as the
+ * MPI_Alltoall of counts does inside pmesh's decompose).  send_capacity >= 2 np is always safe. */
+int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double* x, int64_t np,
+                    int32_t* send_idx, int64_t send_capacity, int32_t* send_start_host);
+
 /* ---- paint  (fastpm.py:224,238,256; pmesh ParticleMesh.paint / paint_jvp and the
  *      mesh half of RealField.readout_vjp) ---------------------------------- */
 /* Particles sorted by cell key (xs = x[perm]); fills every local cell (no prior zero fill
@@ -151,6 +160,25 @@ int vpm_r2c(vpm_ctx* ctx, const int64_t n[3], const double* real_in, double* cpl
 /* preserves cplx_in (copies into the context workspace first) */
 int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
             double scale);
+
+/* Pieces of the slab-decomposed transform (the local transforms are cuFFT; the transpose
+ * between them is an all-to-all done by the caller):
+ *   r2c: vpm_fft_r2c_planes -> vpm_swap_leading_axes (pack) -> all-to-all -> vpm_fft_c2c_axis0
+ *   c2r: vpm_fft_c2c_axis0 (inverse) -> all-to-all -> vpm_swap_leading_axes (unpack)
+ *        -> vpm_fft_c2r_planes
+ * Local real slab [nplanes, n1, n2]; local complex slab [n0, n1 / P, n2/2 + 1] ("transposed
+ * out": the complex mesh is sharded along axis 1). */
+int vpm_fft_r2c_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, const double* real_in,
+                       double* cplx_out);
+/* destroys cplx_in */
+int vpm_fft_c2r_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, double* cplx_in,
+                       double* real_out, double scale);
+/* in place, `inner` transforms of length n0 with stride `inner` */
+int vpm_fft_c2c_axis0(vpm_ctx* ctx, int64_t n0, int64_t inner, double* data, int inverse,
+                      double scale);
+/* dst[b][a][:] = src[a][b][:] for [a, b, c] complex128 */
+int vpm_swap_leading_axes(vpm_ctx* ctx, int64_t a, int64_t b, int64_t c, const double* src,
+                          double* dst);
 
 /* ---- k-space  (fastpm.py:79,83,87 apply_transfer; :310-334 filters; pmesh
  *      ComplexField.apply) ---------------------------------------------------- */

@@ -54,6 +54,8 @@ SIGNATURES = {
     'vpm_cell_keys': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P]),
     'vpm_layout_ncell': (c_int64, [POINTER(vpm_mesh)]),
     'vpm_layout_build': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P, _P, _P]),
+    'vpm_route_build': (c_int, [c_void_p, POINTER(vpm_mesh), c_int, _P, c_int64, _P, c_int64,
+                                POINTER(c_int32)]),
     'vpm_take_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
@@ -73,6 +75,10 @@ SIGNATURES = {
     'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
+    'vpm_fft_r2c_planes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P]),
+    'vpm_fft_c2r_planes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P, c_double]),
+    'vpm_fft_c2c_axis0': (c_int, [c_void_p, c_int64, c_int64, _P, c_int, c_double]),
+    'vpm_swap_leading_axes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P]),
     'vpm_transfer': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double, c_int, _P, _P, _P,
                              _P, _P, _P, c_int]),
     'vpm_transfer_table': (c_int, [c_void_p, POINTER(c_int64), _P, _P, _P, POINTER(c_int64),

@@ -41,9 +41,48 @@ k_scale_inplace(long long n, double a, double* __restrict__ x) {
     }
 }
 
+// dst[b][a][:] = src[a][b][:] for an [A, B, C] array of complex128 (C contiguous):
+// pack / unpack around the all-to-all transpose of the slab FFT
+__global__ void __launch_bounds__(256)
+k_swap_leading_axes(long long A, long long B, long long Cn, const double2* __restrict__ src,
+                    double2* __restrict__ dst) {
+    const long long total = A * B * Cn;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long c = e % Cn;
+        const long long r = e / Cn;   // output row index = b * A + a
+        const long long a = r % A;
+        const long long b = r / A;
+        dst[e] = src[(a * B + b) * Cn + c];
+    }
+}
+
 }  // namespace vpm
 
 using namespace vpm;
+
+// batched plans for the slab-decomposed transform; kind 10: 2-D D2Z over planes, 11: 2-D Z2D
+// over planes, 12: 1-D Z2Z along the leading (strided) axis
+static cufftHandle slab_plan(vpm_ctx* ctx, int kind, int64_t a, int64_t b, int64_t c) {
+    auto key = std::make_tuple(a, b, c, kind);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) return it->second;
+    cufftHandle h;
+    if (kind == 10 || kind == 11) {
+        // a planes of a (b, c) real mesh
+        int n[2] = {(int)b, (int)c};
+        VPM_CUFFT(cufftPlanMany(&h, 2, n, nullptr, 1, 0, nullptr, 1, 0,
+                                kind == 10 ? CUFFT_D2Z : CUFFT_Z2D, (int)a));
+    } else {
+        // length-a transforms with stride b (= number of transforms), one element apart
+        int n[1] = {(int)a};
+        int embed[1] = {(int)a};
+        VPM_CUFFT(cufftPlanMany(&h, 1, n, embed, (int)b, 1, embed, (int)b, 1, CUFFT_Z2Z, (int)b));
+    }
+    VPM_CUFFT(cufftSetStream(h, ctx->stream));
+    ctx->plans[key] = h;
+    return h;
+}
 
 cufftHandle vpm_ctx::plan(const int64_t n[3], int dir) {
     auto key = std::make_tuple(n[0], n[1], n[2], dir);
@@ -95,6 +134,63 @@ int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* rea
         long long nd = (long long)n[0] * n[1] * n[2];
         VPM_LAUNCH(k_scale_inplace, (unsigned)ceil_div(nd, EW_THREADS * EW_UNROLL), EW_THREADS, 0,
                    ctx->stream, nd, scale, real_out);
+    }
+    VPM_API_END
+}
+
+int vpm_fft_r2c_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, const double* real_in,
+                       double* cplx_out) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && real_in && cplx_out && nplanes >= 1, "bad argument");
+    cufftHandle h = slab_plan(ctx, 10, nplanes, n1, n2);
+    VPM_CUFFT(cufftExecD2Z(h, const_cast<double*>(real_in),
+                           reinterpret_cast<cufftDoubleComplex*>(cplx_out)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    VPM_API_END
+}
+
+int vpm_fft_c2r_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, double* cplx_in,
+                       double* real_out, double scale) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && real_out && cplx_in && nplanes >= 1, "bad argument");
+    cufftHandle h = slab_plan(ctx, 11, nplanes, n1, n2);
+    VPM_CUFFT(cufftExecZ2D(h, reinterpret_cast<cufftDoubleComplex*>(cplx_in), real_out));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (scale != 1.0) {
+        long long nd = (long long)nplanes * n1 * n2;
+        VPM_LAUNCH(k_scale_inplace, (unsigned)ceil_div(nd, EW_THREADS * EW_UNROLL), EW_THREADS, 0,
+                   ctx->stream, nd, scale, real_out);
+    }
+    VPM_API_END
+}
+
+int vpm_fft_c2c_axis0(vpm_ctx* ctx, int64_t n0, int64_t inner, double* data, int inverse,
+                      double scale) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && data && n0 >= 1 && inner >= 1, "bad argument");
+    VPM_REQUIRE(inner < (1LL << 31), "too many transforms for one plan");
+    cufftHandle h = slab_plan(ctx, 12, n0, inner, 0);
+    cufftDoubleComplex* d = reinterpret_cast<cufftDoubleComplex*>(data);
+    VPM_CUFFT(cufftExecZ2Z(h, d, d, inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (scale != 1.0) {
+        long long nd = 2LL * n0 * inner;
+        VPM_LAUNCH(k_scale_inplace, (unsigned)ceil_div(nd, EW_THREADS * EW_UNROLL), EW_THREADS, 0,
+                   ctx->stream, nd, scale, data);
+    }
+    VPM_API_END
+}
+
+int vpm_swap_leading_axes(vpm_ctx* ctx, int64_t a, int64_t b, int64_t c, const double* src,
+                          double* dst) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && src && dst && src != dst, "bad argument");
+    long long total = (long long)a * b * c;
+    if (total > 0) {
+        unsigned grid = (unsigned)std::min<long long>(ceil_div(total, 256), 32LL * ctx->sm_count);
+        VPM_LAUNCH(k_swap_leading_axes, grid, 256, 0, ctx->stream, (long long)a, (long long)b,
+                   (long long)c, reinterpret_cast<const double2*>(src),
+                   reinterpret_cast<double2*>(dst));
     }
     VPM_API_END
 }

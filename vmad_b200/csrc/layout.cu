@@ -271,11 +271,119 @@ __global__ void k_scatter_rows(const double* __restrict__ src, const int* __rest
     else *d = v;
 }
 
+// ---- routing of particles to slab owners (stable multisplit) -----------------------------
+// A particle goes to the rank that owns its floor plane i0 and, when different, to the rank
+// that owns plane i0 + 1 (the two planes a CIC particle touches).  Within a destination the
+// original particle order is kept (stable), so the routing is deterministic.
+constexpr int ROUTE_THREADS = 256;
+constexpr int ROUTE_MAXP = 64;
+
+__device__ __forceinline__ void route_of(const Geo& g, int planes_per_rank, const double* x,
+                                         long long p, int& r0, int& r1) {
+    int i0;
+    double f;
+    cell_axis(x[3 * p], g.s0, g.n0, i0, f);
+    r0 = i0 / planes_per_rank;
+    r1 = wrap_inc(i0, g.n0) / planes_per_rank;
+    if (r1 == r0) r1 = -1;
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS)
+k_route_count(Geo g, int planes_per_rank, int P, const double* __restrict__ x, long long np,
+              long long nblocks, int* __restrict__ counts /* [P][nblocks] */) {
+    __shared__ int c[ROUTE_MAXP];
+    for (int d = threadIdx.x; d < P; d += blockDim.x) c[d] = 0;
+    __syncthreads();
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p < np) {
+        int r0, r1;
+        route_of(g, planes_per_rank, x, p, r0, r1);
+        atomicAdd(&c[r0], 1);
+        if (r1 >= 0) atomicAdd(&c[r1], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < P; d += blockDim.x) counts[d * nblocks + blockIdx.x] = c[d];
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS)
+k_route_scatter(Geo g, int planes_per_rank, int P, const double* __restrict__ x, long long np,
+                long long nblocks, const int* __restrict__ offsets /* [P][nblocks] */,
+                int* __restrict__ send_idx) {
+    __shared__ int warp_cnt[ROUTE_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int r0 = -1, r1 = -1;
+    if (p < np) route_of(g, planes_per_rank, x, p, r0, r1);
+    for (int d = 0; d < P; ++d) {
+        const bool mine = (r0 == d) || (r1 == d);
+        const unsigned b = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) warp_cnt[w] = __popc(b);
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < w; ++k) base += warp_cnt[k];
+        if (mine) {
+            const int rank = base + __popc(b & ((1u << lane) - 1));
+            send_idx[offsets[d * nblocks + blockIdx.x] + rank] = (int)p;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_route_totals(int P, long long nblocks, long long nsend_total_index,
+                               const int* __restrict__ offsets, const int* __restrict__ counts,
+                               int* __restrict__ totals /* [P + 1] */) {
+    int d = threadIdx.x;
+    if (d < P) totals[d] = offsets[d * nblocks];
+    if (d == P) {
+        long long last = (long long)P * nblocks - 1;
+        totals[P] = offsets[last] + counts[last];
+    }
+}
+
 }  // namespace vpm
 
 using namespace vpm;
 
 extern "C" {
+
+int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double* x, int64_t np,
+                    int32_t* send_idx, int64_t send_capacity, int32_t* send_start_host) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && mesh && send_start_host, "NULL argument");
+    VPM_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXP, "unsupported number of ranks");
+    VPM_REQUIRE(mesh->n[0] % nranks == 0, "mesh planes must divide evenly over the ranks");
+    VPM_REQUIRE(np >= 0 && 2 * np < (1LL << 31) - 1, "particle count must fit int32");
+    vpm_mesh m = *mesh;  // routing only needs the global geometry
+    m.start0 = 0;
+    m.nloc0 = m.n[0];
+    m.ghost = 0;
+    Geo g = make_geo(&m);
+    const int ppr = (int)(mesh->n[0] / nranks);
+    cudaStream_t st = ctx->stream;
+    const long long nblocks = std::max<long long>(1, ceil_div(np, ROUTE_THREADS));
+    const long long ncount = (long long)nranks * nblocks;
+    const long long ntmp = scan_tmp_ints(ncount);
+    int* ws = (int*)ctx->workspace((size_t)(2 * ncount + ntmp + nranks + 8) * sizeof(int));
+    int* counts = ws;
+    int* offsets = counts + ncount;
+    int* tmp = offsets + ncount;
+    int* totals = tmp + ntmp;
+    VPM_LAUNCH(k_route_count, (unsigned)nblocks, ROUTE_THREADS, 0, st, g, ppr, nranks, x,
+               (long long)np, nblocks, counts);
+    exclusive_scan(st, counts, ncount, offsets, tmp);
+    VPM_LAUNCH(k_route_totals, 1, ROUTE_MAXP + 1, 0, st, nranks, nblocks, 0LL, offsets, counts, totals);
+    // the send counts are needed on the host to size the exchange: the one sync of decompose
+    VPM_CUDA(cudaMemcpyAsync(send_start_host, totals, (nranks + 1) * sizeof(int),
+                             cudaMemcpyDeviceToHost, st));
+    VPM_CUDA(cudaStreamSynchronize(st));
+    VPM_REQUIRE(send_start_host[nranks] <= send_capacity, "send index buffer too small");
+    if (np > 0) {
+        VPM_REQUIRE(x && send_idx, "NULL array");
+        VPM_LAUNCH(k_route_scatter, (unsigned)nblocks, ROUTE_THREADS, 0, st, g, ppr, nranks, x,
+                   (long long)np, nblocks, offsets, send_idx);
+    }
+    VPM_API_END
+}
 
 int64_t vpm_layout_ncell(const vpm_mesh* m) {
     if (!m) return -1;

@@ -498,8 +498,10 @@ class RealField(Field):
         xs = []
         for d in range(pm.ndim):
             shape = [1] * pm.ndim
-            shape[d] = int(pm.Nmesh[d])
+            shape[d] = pm.rshape[d]
             i = numpy.arange(pm.Nmesh[d])
+            if pm.P > 1 and d == 0:
+                i = i[pm.rstart0:pm.rstart0 + pm.rshape[0]]
             x = i if kind == 'index' else i * (pm.BoxSize[d] / pm.Nmesh[d])
             xs.append(x.reshape(shape))
         return KList(xs)
@@ -650,6 +652,77 @@ class Layout(object):
         return DeviceArray(out)
 
 
+class DistLayout(object):
+    """``pm.decompose`` over several ranks (slab decomposition along mesh axis 0).
+
+    Routing (done by ``vpm_route_build``, stable, deterministic): a particle goes to the rank
+    owning its floor plane and, when different, to the rank owning the next plane -- the two
+    planes a CIC particle touches; each rank paints / reads only its own planes and ``gather``
+    sums the partial results of the copies, so ``exchange`` and ``gather`` stay mutual adjoints
+    (fastpm.py:281-308) and P-rank results equal 1-rank results to rounding.  What arrives is
+    cell-sorted locally (keys counted from the lower ghost plane).
+    """
+
+    def __init__(self, pm, pos, keep_index=None):
+        rt = pm.rt
+        rt.sync_stream()
+        self.pm = pm
+        comm = pm.comm
+        P = pm.P
+        _, x3 = pm._pos3(pos)
+        n = x3.shape[0]
+        self.oldlength = n
+        send_idx = rt.empty((max(2 * n, 1),), torch.int32)
+        start = (ctypes.c_int32 * (P + 1))()
+        C.check(C.lib.vpm_route_build(rt.ctx, ctypes.byref(pm._mesh), P, _ptr(x3), n,
+                                      _ptr(send_idx), send_idx.shape[0], start))
+        self.send_counts = [start[d + 1] - start[d] for d in range(P)]
+        self.nsend = int(start[P])
+        self.send_idx = send_idx[:self.nsend].clone()  # drop the over-allocation
+        self.recv_counts = comm.alltoall_counts(self.send_counts)
+        self.nrecv = int(sum(self.recv_counts))
+        # positions travel once here; the local cell sort is built on what arrived
+        xr = self._forward(x3)
+        local = pm._decompose_local(DeviceArray(xr), keep_index)
+        self.indices = local.indices
+        self.cell_start = local.cell_start
+        self.keys = local.keys
+        self.newlength = self.nrecv
+
+    def _forward(self, t):
+        """rows of a local [oldlength, ...] tensor -> rows received here, ordered by source"""
+        rt = self.pm.rt
+        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        send = rt.empty((self.nsend,) + tuple(t.shape[1:]))
+        C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.send_idx), self.nsend, ncomp, _ptr(send)))
+        return self.pm.comm.alltoallv_rows(send, self.send_counts, self.recv_counts)
+
+    def exchange(self, data):
+        """fastpm.py:289,301,308"""
+        data = asdevice(data)
+        rt = self.pm.rt
+        rt.sync_stream()
+        recv = self._forward(data.t)
+        ncomp = recv.numel() // max(recv.shape[0], 1) if recv.dim() > 1 else 1
+        out = rt.empty(tuple(recv.shape))
+        C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(recv), _ptr(self.indices), self.nrecv, ncomp, _ptr(out)))
+        return DeviceArray(out, cellindex=self)
+
+    def gather(self, data, mode='sum'):
+        """fastpm.py:286,293,304: back to the home rank and order, copies summed"""
+        data = asdevice(data)
+        rt = self.pm.rt
+        rt.sync_stream()
+        t = data.t
+        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        unsorted = rt.empty(tuple(t.shape))
+        C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), self.nrecv, ncomp, _ptr(unsorted)))
+        back = self.pm.comm.alltoallv_rows(unsorted, self.recv_counts, self.send_counts)
+        out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
+        C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(back), _ptr(self.send_idx), self.nsend, ncomp, _ptr(out)))
+        return DeviceArray(out)
+
+
 # ---------------------------------------------------------------------------------------------
 # particle mesh
 # ---------------------------------------------------------------------------------------------
@@ -674,8 +747,26 @@ class ParticleMesh(object):
         self.comm = comm if comm is not None else SelfComm()
         self.dtype = numpy.dtype(dtype)
         self.resampler = resampler
-        self.rshape = tuple(int(n) for n in Nmesh)
-        self.cshape = tuple(int(n) for n in Nmesh[:-1]) + (int(Nmesh[-1]) // 2 + 1,)
+        self.P = int(getattr(self.comm, 'size', 1))
+        self.rank = int(getattr(self.comm, 'rank', 0))
+        # global shapes
+        self.grshape = tuple(int(n) for n in Nmesh)
+        self.gcshape = tuple(int(n) for n in Nmesh[:-1]) + (int(Nmesh[-1]) // 2 + 1,)
+        # local shapes: real mesh sharded in slabs along axis 0, complex mesh along axis 1
+        # ("transposed out", so that r2c and c2r need one all-to-all each)
+        if self.P > 1:
+            if ndim != 3:
+                raise ValueError("multi-rank meshes must be 3-D")
+            if Nmesh[0] % self.P or Nmesh[1] % self.P:
+                raise ValueError("Nmesh[0] and Nmesh[1] must be divisible by the number of ranks")
+            n0l, n1l = int(Nmesh[0]) // self.P, int(Nmesh[1]) // self.P
+            self.rstart0, self.cstart1 = self.rank * n0l, self.rank * n1l
+            self.rshape = (n0l,) + self.grshape[1:]
+            self.cshape = (self.gcshape[0], n1l, self.gcshape[2])
+        else:
+            self.rstart0 = self.cstart1 = 0
+            self.rshape = self.grshape
+            self.cshape = self.gcshape
         self.Ntot = int(Nmesh.prod())
         self.scale = self.Nmesh / self.BoxSize  # the one rounded fp64 scale (as in the oracle)
 
@@ -683,16 +774,16 @@ class ParticleMesh(object):
         n3 = [1] * (3 - ndim) + [int(n) for n in Nmesh]
         s3 = [1.0] * (3 - ndim) + [float(s) for s in self.scale]
         self._n3 = n3
-        self._cshape3 = [n3[0], n3[1], n3[2] // 2 + 1]
+        self._cshape3 = [1] * (3 - ndim) + list(self.cshape)
         m = C.vpm_mesh()
         for d in range(3):
             m.n[d] = n3[d]
             m.scale[d] = s3[d]
-        m.start0 = 0
-        m.nloc0 = n3[0]
+        m.start0 = self.rstart0
+        m.nloc0 = self.rshape[0] if ndim == 3 else 1
         m.stride1 = n3[2]
         m.stride0 = n3[1] * n3[2]
-        m.ghost = 0
+        m.ghost = 1 if self.P > 1 else 0
         self._mesh = m
         self._ncell = int(C.lib.vpm_layout_ncell(ctypes.byref(m)))
         self._tables = {}
@@ -700,9 +791,12 @@ class ParticleMesh(object):
 
     # -- host-side tables ---------------------------------------------------------------
     def freq_index(self, d):
+        """integer frequencies of the LOCAL part of complex axis d"""
         N = int(self.Nmesh[d])
-        j = numpy.arange(self.cshape[d], dtype='i8')
+        j = numpy.arange(self.gcshape[d], dtype='i8')
         j[j >= N // 2] -= N
+        if self.P > 1 and d == 1:
+            j = j[self.cstart1:self.cstart1 + self.cshape[1]]
         return j
 
     def _k_table(self, d3):
@@ -713,7 +807,7 @@ class ParticleMesh(object):
             if d < 0:
                 k = numpy.zeros(1)
             else:
-                k = self.freq_index(d) * (2 * numpy.pi / self.BoxSize[d])
+                k = self.freq_index(d) * (2 * numpy.pi / self.BoxSize[d])  # local part
             self._tables[key] = _upload(k)
         return self._tables[key]
 
@@ -736,7 +830,13 @@ class ParticleMesh(object):
             return t
         if isinstance(value, numbers.Number):
             return torch.full(shape, value, dtype=dtype, device=self.rt.device)
-        a = numpy.broadcast_to(numpy.asarray(value), shape)
+        a = numpy.asarray(value)
+        gshape = self.gcshape if is_complex else self.grshape
+        if self.P > 1 and a.shape == gshape:
+            # a global host array: keep the local slab
+            a = a[:, self.cstart1:self.cstart1 + shape[1]] if is_complex \
+                else a[self.rstart0:self.rstart0 + shape[0]]
+        a = numpy.broadcast_to(a, shape)
         return _upload(a, numpy.complex128 if is_complex else numpy.float64)
 
     def _as_field(self, value, is_complex):
@@ -761,7 +861,9 @@ class ParticleMesh(object):
     def generate_uniform_particle_grid(self, shift=0.5, dtype='f8', return_host=False):
         """``(i + shift) * BoxSize / Nmesh``, C order, ``[Np, ndim]`` (fastpm.py:532)."""
         cell = self.BoxSize / self.Nmesh
-        axes = [(numpy.arange(n) + shift) * cell[d] for d, n in enumerate(self.rshape)]
+        axes = [(numpy.arange(n) + shift) * cell[d] for d, n in enumerate(self.grshape)]
+        if self.P > 1:
+            axes[0] = axes[0][self.rstart0:self.rstart0 + self.rshape[0]]
         grid = numpy.meshgrid(*axes, indexing='ij')
         q = numpy.stack([g.ravel() for g in grid], axis=-1).astype('f8')
         return q if return_host else DeviceArray.from_host(q)
@@ -772,7 +874,7 @@ class ParticleMesh(object):
         own generator is not reproducible here).  Generated on the host."""
         type = mode if mode is not None else type
         rng = numpy.random.default_rng(seed)
-        g = rng.standard_normal(self.rshape)
+        g = rng.standard_normal(self.grshape)
         c = numpy.fft.rfftn(g) / self.Ntot ** 0.5
         if unitary:
             a = numpy.abs(c)
@@ -780,7 +882,7 @@ class ParticleMesh(object):
             c = c / a
         c[(0,) * self.ndim] = mean
         if type == 'real':
-            r = numpy.fft.irfftn(c, s=self.rshape) * self.Ntot
+            r = numpy.fft.irfftn(c, s=self.grshape) * self.Ntot
             return r if return_host else self.create('real', value=r)
         return c if return_host else self.create('complex', value=c)
 
@@ -819,6 +921,13 @@ class ParticleMesh(object):
         return keys
 
     def decompose(self, pos, smoothing=None, keep_index=None):
+        """fastpm.py:272.  One rank: the stable cell sort.  Several ranks: route every particle
+        to the slab(s) that own the two planes it touches, then cell-sort what arrived."""
+        if self.P > 1:
+            return DistLayout(self, pos, keep_index)
+        return self._decompose_local(pos, keep_index)
+
+    def _decompose_local(self, pos, keep_index=None):
         """``keep_index``: also keep the cell keys and cell offsets on the layout (the sorted
         permutation alone is what exchange / gather and the default paint need; the layout sits
         on the tape of every force evaluation, so the extra 8 B/particle + 4 B/cell matter)"""
@@ -849,7 +958,9 @@ class ParticleMesh(object):
             _, x3 = self._pos3(pos)
             return lay, x3, [asdevice(e) for e in extras], False
         if layout is None:
-            layout = self.decompose(pos)
+            # no layout: the positions are taken as local (pmesh semantics); sorting them
+            # locally is an optimisation, not an exchange
+            layout = self._decompose_local(pos)
         xs = layout.exchange(pos)
         _, x3 = self._pos3(xs)
         ex = []
@@ -877,8 +988,8 @@ class ParticleMesh(object):
             return lay.cell_start
         if not _KEEP_CELL_INDEX:
             return self._dummy_cs()  # the aggregated paint ignores it
-        lay2 = self.decompose(DeviceArray(x3 if self.ndim == 3 else x3[:, 1:].contiguous()),
-                              keep_index=True)
+        lay2 = self._decompose_local(DeviceArray(x3 if self.ndim == 3 else x3[:, 1:].contiguous()),
+                                     keep_index=True)
         lay.cell_start = lay2.cell_start
         return lay.cell_start
 
@@ -962,7 +1073,7 @@ class ParticleMesh(object):
         m0 = 1.0 if marr is not None else float(mass)
         o = rt.empty(self.rshape)
         if lay.cell_start is None:
-            lay = self.decompose(DeviceArray(x3), keep_index=True)
+            lay = self._decompose_local(DeviceArray(x3), keep_index=True)
         C.check(C.lib.vpm_paint_sorted_rows(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr),
                                             m0, x3.shape[0], _ptr(lay.cell_start), _ptr(o)))
         return RealField(self, o)
@@ -1061,6 +1172,8 @@ class ParticleMesh(object):
     def _r2c(self, real, scale):
         rt = self.rt
         rt.sync_stream()
+        if self.P > 1:
+            return self._r2c_slab(real, scale)
         o = rt.empty(self.cshape, _C16)
         C.check(C.lib.vpm_r2c(rt.ctx, C.i3(self._n3), _ptr(real.t), _ptr(o), float(scale)))
         return ComplexField(self, o)
@@ -1068,8 +1181,41 @@ class ParticleMesh(object):
     def _c2r(self, cplx, scale):
         rt = self.rt
         rt.sync_stream()
+        if self.P > 1:
+            return self._c2r_slab(cplx, scale)
         o = rt.empty(self.rshape)
         C.check(C.lib.vpm_c2r(rt.ctx, C.i3(self._n3), _ptr(cplx.t), _ptr(o), float(scale)))
+        return RealField(self, o)
+
+    # slab-decomposed transforms: local cuFFT, one all-to-all transpose each -------------------
+    def _r2c_slab(self, real, scale):
+        """[n0l, N1, N2] real -> [N0, n1l, Nh] complex: 2-D D2Z over the local planes, pack,
+        all-to-all (the distributed-FFT transpose), 1-D Z2Z along axis 0"""
+        rt = self.rt
+        P = self.P
+        n0l, N1, N2 = self.rshape
+        N0, n1l, Nh = self.cshape
+        a = rt.empty((n0l, N1, Nh), _C16)
+        C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
+        # [n0l, P, n1l*Nh] -> [P, n0l, n1l*Nh]: block d goes to rank d
+        send = rt.empty((P, n0l, n1l, Nh), _C16)
+        C.check(C.lib.vpm_swap_leading_axes(rt.ctx, n0l, P, n1l * Nh, _ptr(a), _ptr(send)))
+        recv = self.comm.alltoall_blocks(send)          # [P (source slab), n0l, n1l, Nh] = [N0, n1l, Nh]
+        C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(recv), 0, float(scale)))
+        return ComplexField(self, recv.view(N0, n1l, Nh))
+
+    def _c2r_slab(self, cplx, scale):
+        rt = self.rt
+        P = self.P
+        n0l, N1, N2 = self.rshape
+        N0, n1l, Nh = self.cshape
+        work = cplx.t.clone()                           # operators must not mutate their inputs
+        C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(work), 1, 1.0))
+        recv = self.comm.alltoall_blocks(work.view(P, n0l, n1l, Nh))   # [P (column block), n0l, n1l, Nh]
+        a = rt.empty((n0l, N1, Nh), _C16)
+        C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, n1l * Nh, _ptr(recv), _ptr(a)))
+        o = rt.empty(self.rshape)
+        C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
         return RealField(self, o)
 
     # -- k-space (fastpm.py:79,83,87) ---------------------------------------------------------------
