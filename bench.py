@@ -13,8 +13,13 @@ inside the timed region, the gradient copied back device->host).
 
 Timing: W untimed warm-up steps, then K steps each bracketed by CUDA events on the stream the
 kernels are launched on, an L2 flush (256 MiB write) between steps outside the events, a
-barrier + synchronize on both sides, max over ranks.  N > 1 (torchrun): every rank runs the
-same problem on its own GPU ("replicas only" this round) -- weak scaling.
+barrier + synchronize on both sides, max over ranks.
+
+N > 1 (torchrun, one rank per GPU): ONE problem, slab-decomposed over the N GPUs (mesh planes
+and the particles on them per rank, NCCL all-to-all for the particle exchange and the FFT
+transposes; vmad_b200/dist.py).  Weak scaling: the global mesh grows with N so that every GPU
+keeps nmesh^3 cells and particles ([nmesh*a, nmesh*b, nmesh*c] with a*b*c = N, cell size
+fixed); ``value`` = N * nsteps / seconds, i.e. steps/s in units of the N = 1 problem.
 """
 import argparse
 import json
@@ -49,12 +54,26 @@ def power(k):
     return 1.5e6 * k / (1.0 + (k / 0.05) ** 2) ** 2
 
 
-def make_inputs(nmesh, seed=None):
-    """synthetic Gaussian initial conditions (host arrays)"""
-    N = nmesh
-    rng = numpy.random.default_rng(300 + N if seed is None else seed)
-    wn = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5
-    cot = rng.standard_normal((N ** 3, 3))
+def global_shape(nmesh, world):
+    """weak scaling: distribute the factors of ``world`` (a power of two) over the axes"""
+    dims = [nmesh, nmesh, nmesh]
+    w, d = world, 0
+    while w > 1:
+        if w % 2:
+            raise SystemExit("bench.py: --gpus must be a power of two")
+        dims[d % 3] *= 2
+        w //= 2
+        d += 1
+    return dims
+
+
+def make_inputs(nmesh, seed=None, dims=None):
+    """synthetic Gaussian initial conditions (host arrays, global)"""
+    dims = [nmesh] * 3 if dims is None else list(dims)
+    ntot = dims[0] * dims[1] * dims[2]
+    rng = numpy.random.default_rng(300 + nmesh if seed is None else seed)
+    wn = numpy.fft.rfftn(rng.standard_normal(tuple(dims))) / ntot ** 0.5
+    cot = rng.standard_normal((ntot, 3))
     return wn, cot
 
 
@@ -230,10 +249,20 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     N = args.nmesh
-    pm = ParticleMesh([N] * 3, 100.0 * N / 32)
+    dims = global_shape(N, world)
+    comm = None
+    if world > 1:
+        from vmad_b200.dist import TorchComm
+        comm = TorchComm()
+    pm = ParticleMesh(dims, [100.0 * n / 32 for n in dims], comm=comm)
     pm.force_recompute = N >= 512  # keep potk instead of 3 force meshes per step on the tape
-    wn_h, cot_h = make_inputs(N)
+    wn_g, cot_g = make_inputs(N, dims=dims)
     q = pm.generate_uniform_particle_grid(shift=0.0)
+    npl = len(q)
+    # this rank's share: complex slab along axis 1, particles of its planes (lattice order)
+    wn_h = numpy.ascontiguousarray(wn_g[:, pm.cstart1:pm.cstart1 + pm.cshape[1]]) if world > 1 else wn_g
+    cot_h = numpy.ascontiguousarray(cot_g[rank * npl:(rank + 1) * npl])
+    del wn_g, cot_g
     stages = numpy.linspace(0.1, 1.0, args.nsteps + 1)
     model = build_model(pm, q, stages)
 
@@ -300,7 +329,7 @@ def run_gpu(args):
     x_final = q + dx
     lay = pm.decompose(x_final)
     xs = lay.exchange(x_final)
-    Np, Nc = N ** 3, N ** 3
+    Np, Nc = len(xs), int(numpy.prod(pm.rshape))
     peak, peak_src = measured_peak()
 
     def kernel_time(fn, iters=20):
@@ -325,8 +354,8 @@ def run_gpu(args):
             ('k_paint_agg', lambda: pm.paint(xs, 1.0), 24.0 * Np + 8.0 * Nc),
             ('k_readout', lambda: field.readout(xs), 32.0 * Np + 8.0 * Nc),
             ('k_readout_grad', lambda: pm.paint_vjp(field, xs, mass=1.0), 56.0 * Np + 8.0 * Nc),
-            ('layout_build', lambda: pm.decompose(x_final), 48.0 * Np),
-            ('cufft_r2c', lambda: field.r2c(), 16.06 * Nc)]:
+            ('layout_build', lambda: pm._decompose_local(xs), 48.0 * Np),
+            ('r2c', lambda: field.r2c(), 16.06 * Nc)]:
         t = kernel_time(fn)
         kernels[name] = dict(ms=t * 1e3, achieved_gbs=nbytes / t / 1e9, frac=nbytes / t / 1e9 / peak,
                              gparticles_s=Np / t / 1e9)
@@ -359,8 +388,11 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N, args.nsteps), "nmesh": N, "nsteps": args.nsteps,
-                   "np": N ** 3, "boxsize": 100.0 * N / 32,
-                   "parallelism": "replicas x%d" % world if world > 1 else "1 gpu",
+                   "global_mesh": dims, "np": int(numpy.prod(dims)),
+                   "boxsize": [100.0 * n / 32 for n in dims],
+                   "parallelism": ("slab decomposition over %d GPUs (mesh axis 0; NCCL all-to-all "
+                                   "for particle exchange and FFT transposes), %d^3 cells per GPU"
+                                   % (world, N)) if world > 1 else "1 gpu",
                    "l2": "256 MiB flush write between timed steps",
                    "step": "one Model.compute_with_vjp = %d FastPM steps forward + reverse" % args.nsteps},
         "clocks": clocks,
