@@ -361,35 +361,65 @@ k_paint_tile(Geo g, TileDims td, const double* __restrict__ xs, const double* __
 // price is a zero fill of the mesh beforehand and a summation order that depends on the order
 // in which L2 receives the reductions (results agree to rounding, not bit for bit).
 // -------------------------------------------------------------------------------------------
+// wrapped cell index, branch-free in the common case (inside the box or one box length out)
+__device__ __forceinline__ int wrap_fast(double fl, int n) {
+    int i = __double2int_rn(fl);  // exact for |fl| < 2^31, saturates beyond
+    i += (i < 0) ? n : 0;
+    i -= (i >= n) ? n : 0;
+    if (__builtin_expect((unsigned)i >= (unsigned)n, 0)) i = wrap_cell(fl, n);
+    return i;
+}
+
+// V += tv on the lanes where pred != 0 (one predicated DADD, no select)
+#define VPM_ADD_IF(V, TV, PRED)                                                      \
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.f64 %0, %0, %1;\n\t}"   \
+        : "+d"(V) : "d"(TV), "r"(PRED))
+
 template <int MODE, int MASSKIND, bool HAS_VMASS>
 __global__ void __launch_bounds__(256)
 k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, double mass0,
             int mstride, const double* __restrict__ vpos, const double* __restrict__ vmass,
-            long long np, double* __restrict__ out) {
+            int np, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const long long nchunk = (np + 31) >> 5;
-    const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long ch = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < nchunk;
-         ch += wstride) {
-        const long long p = (ch << 5) + lane;
+    const int nchunk = (np + 31) >> 5;
+    const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
+    const int st0 = (int)g.stride0, st1 = (int)g.stride1;  // local slab < 2^31 elements (checked)
+    // software pipeline: the positions of the warp's next chunk are requested before the
+    // current chunk is processed (the loads are the longest-latency step of the loop)
+    int ch = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    double nx0 = 0.0, nx1 = 0.0, nx2 = 0.0;
+    if (ch < nchunk && (ch << 5) + lane < np) {
+        const double* xp = xs + 3LL * ((ch << 5) + lane);
+        nx0 = __ldg(xp + 0); nx1 = __ldg(xp + 1); nx2 = __ldg(xp + 2);
+    }
+    for (; ch < nchunk; ch += wstride) {
+        const int p = (ch << 5) + lane;
         const bool active = p < np;
-        long long key = -1 - lane;  // inactive lanes: unique keys, never merged
+        const double x0 = nx0, x1 = nx1, x2 = nx2;
+        {
+            if (ch + wstride < nchunk) {
+                const int pn = ((ch + wstride) << 5) + lane;
+                if (pn < np) {
+                    const double* xp = xs + 3LL * pn;
+                    nx0 = __ldg(xp + 0); nx1 = __ldg(xp + 1); nx2 = __ldg(xp + 2);
+                }
+            }
+        }
+        int key = -1 - lane;  // inactive lanes: unique keys, never merged
         int i0 = 0, i1 = 0, iz = 0;
         double S000 = 0.0, S001 = 0.0, S010 = 0.0, S011 = 0.0;
         double S100 = 0.0, S101 = 0.0, S110 = 0.0, S111 = 0.0;
         if (active) {
-            const double* xp = xs + 3 * p;
-            const double x0 = __ldg(xp + 0), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
             double u, fl;
-            u = __dmul_rn(x0, g.s0); fl = floor(u); const double f0 = u - fl; i0 = wrap_cell(fl, g.n0);
-            u = __dmul_rn(x1, g.s1); fl = floor(u); const double f1 = u - fl; i1 = wrap_cell(fl, g.n1);
-            u = __dmul_rn(x2, g.s2); fl = floor(u); const double f2 = u - fl; iz = wrap_cell(fl, g.n2);
-            key = ((long long)i0 * g.n1 + i1) * g.n2 + iz;
+            u = __dmul_rn(x0, g.s0); fl = floor(u); const double f0 = u - fl; i0 = wrap_fast(fl, g.n0);
+            u = __dmul_rn(x1, g.s1); fl = floor(u); const double f1 = u - fl; i1 = wrap_fast(fl, g.n1);
+            u = __dmul_rn(x2, g.s2); fl = floor(u); const double f2 = u - fl; iz = wrap_fast(fl, g.n2);
+            key = (i0 * g.n1 + i1) * g.n2 + iz;
             const double e0 = 1.0 - f0, e1 = 1.0 - f1, e2 = 1.0 - f2;
             if (MODE == 0) {
                 double a0 = e0, a1 = f0;
                 if (MASSKIND != 0) {
-                    const double m = MASSKIND == 2 ? __ldg(mass + p * mstride) : mass0;
+                    const double m = MASSKIND == 2 ? __ldg(mass + (long long)p * mstride) : mass0;
                     a0 *= m;
                     a1 *= m;
                 }
@@ -399,8 +429,9 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
                 w = a1 * e1; S100 = w * e2; S101 = w * f2;
                 w = a1 * f1; S110 = w * e2; S111 = w * f2;
             } else {
-                const double* vp = vpos + 3 * p;
-                const double m = MASSKIND == 2 ? __ldg(mass + p * mstride) : (MASSKIND == 1 ? mass0 : 1.0);
+                const double* vp = vpos + 3LL * p;
+                const double m = MASSKIND == 2 ? __ldg(mass + (long long)p * mstride)
+                                               : (MASSKIND == 1 ? mass0 : 1.0);
                 const double q0 = m * __ldg(vp + 0) * g.s0, q1 = m * __ldg(vp + 1) * g.s1,
                              q2 = m * __ldg(vp + 2) * g.s2;
                 const double vm = HAS_VMASS ? __ldg(vmass + p) : 0.0;
@@ -419,69 +450,64 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
 #undef VPM_TANGENT
             }
         }
-        // segmented inclusive scan over runs of equal cell key
-        const long long kprev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = (lane == 0) || (kprev != key);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        // segmented inclusive scan over runs of equal cell key (adjacent lanes, thanks to the
+        // sort); skipped when every lane starts its own run, rounds adapt to the longest run
+        const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (kprev != key));
         if (heads != 0xffffffffu) {
             for (int d = 1; d < 32; d <<= 1) {
-                const long long kd = __shfl_up_sync(0xffffffffu, key, d);
-                const bool same = (lane >= d) && (kd == key);
+                const int kd = __shfl_up_sync(0xffffffffu, key, d);
+                const int same = (lane >= d) && (kd == key);
                 if (!__any_sync(0xffffffffu, same)) break;
 #define VPM_SCAN(V)                                                                  \
     {                                                                                \
         const double tv = __shfl_up_sync(0xffffffffu, V, d);                         \
-        if (same) V += tv;                                                           \
+        VPM_ADD_IF(V, tv, same);                                                     \
     }
                 VPM_SCAN(S000) VPM_SCAN(S001) VPM_SCAN(S010) VPM_SCAN(S011)
                 VPM_SCAN(S100) VPM_SCAN(S101) VPM_SCAN(S110) VPM_SCAN(S111)
 #undef VPM_SCAN
             }
         }
-        const long long knext = __shfl_down_sync(0xffffffffu, key, 1);
+        const int knext = __shfl_down_sync(0xffffffffu, key, 1);
         const bool tail = active && (lane == 31 || knext != key);
         // z-merge: a run whose successor in this warp is cell z + 1 of the same row hands its
-        // c = 1 sums to that run instead of writing them
+        // c = 1 sums to that run instead of writing them.  The run before mine ends at lane
+        // (head of my run) - 1.
         const bool hand_over = tail && lane < 31 && knext == key + 1 && iz + 1 < g.n2;
-        // the run before mine ends at lane (head of my run) - 1
         const int myhead = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-        const int src = myhead - 1;
-        const long long ksrc = __shfl_sync(0xffffffffu, key, src < 0 ? 0 : src);
-        const bool take = tail && src >= 0 && ksrc == key - 1 && iz > 0;
+        const int sl = max(myhead - 1, 0);
+        const int ksrc = __shfl_sync(0xffffffffu, key, sl);
+        const int take = tail && myhead > 0 && ksrc == key - 1 && iz > 0;
         {
-            const int sl = src < 0 ? 0 : src;
             const double t0 = __shfl_sync(0xffffffffu, S001, sl);
             const double t1 = __shfl_sync(0xffffffffu, S011, sl);
             const double t2 = __shfl_sync(0xffffffffu, S101, sl);
             const double t3 = __shfl_sync(0xffffffffu, S111, sl);
-            if (take) {
-                S000 += t0;
-                S010 += t1;
-                S100 += t2;
-                S110 += t3;
-            }
+            VPM_ADD_IF(S000, t0, take);
+            VPM_ADD_IF(S010, t1, take);
+            VPM_ADD_IF(S100, t2, take);
+            VPM_ADD_IF(S110, t3, take);
         }
         if (tail) {
             const int j1 = wrap_inc(i1, g.n1), jz = wrap_inc(iz, g.n2);
             const int la = local_plane(g, i0), lb = local_plane(g, wrap_inc(i0, g.n0));
-            double* r00 = out + (long long)la * g.stride0 + (long long)i1 * g.stride1;
-            double* r01 = out + (long long)la * g.stride0 + (long long)j1 * g.stride1;
-            double* r10 = out + (long long)lb * g.stride0 + (long long)i1 * g.stride1;
-            double* r11 = out + (long long)lb * g.stride0 + (long long)j1 * g.stride1;
+            const int ra = la * st0, rb = lb * st0;
+            const int c0 = i1 * st1, c1 = j1 * st1;
             if (la >= 0) {
-                atomicAdd(r00 + iz, S000);
-                atomicAdd(r01 + iz, S010);
+                atomicAdd(out + (ra + c0 + iz), S000);
+                atomicAdd(out + (ra + c1 + iz), S010);
                 if (!hand_over) {
-                    atomicAdd(r00 + jz, S001);
-                    atomicAdd(r01 + jz, S011);
+                    atomicAdd(out + (ra + c0 + jz), S001);
+                    atomicAdd(out + (ra + c1 + jz), S011);
                 }
             }
             if (lb >= 0) {
-                atomicAdd(r10 + iz, S100);
-                atomicAdd(r11 + iz, S110);
+                atomicAdd(out + (rb + c0 + iz), S100);
+                atomicAdd(out + (rb + c1 + iz), S110);
                 if (!hand_over) {
-                    atomicAdd(r10 + jz, S101);
-                    atomicAdd(r11 + jz, S111);
+                    atomicAdd(out + (rb + c0 + jz), S101);
+                    atomicAdd(out + (rb + c1 + jz), S111);
                 }
             }
         }
@@ -592,11 +618,13 @@ static void launch_paint_agg(vpm_ctx* ctx, const Geo& g, const double* xs, const
                              double* out, int mstride = 1) {
     zero_mesh(ctx, g, out);
     if (np == 0) return;
+    VPM_REQUIRE(np < (1LL << 31) - 64, "particle count must fit int32");
+    VPM_REQUIRE((long long)g.nloc0 * g.stride0 < (1LL << 31), "local mesh slab must have < 2^31 elements");
     const long long nchunk = (np + 31) / 32;
     const unsigned grid = (unsigned)std::min<long long>(ceil_div(nchunk, 8), 64LL * ctx->sm_count);
     const int mk = mass ? 2 : (mass0 == 1.0 ? 0 : 1);
     cudaStream_t st = ctx->stream;
-#define VPM_AGG(MODE_, MK_, HV_) VPM_LAUNCH((k_paint_agg<MODE_, MK_, HV_>), grid, 256, 0, st, g, xs, mass, mass0, mstride, vpos, vmass, np, out)
+#define VPM_AGG(MODE_, MK_, HV_) VPM_LAUNCH((k_paint_agg<MODE_, MK_, HV_>), grid, 256, 0, st, g, xs, mass, mass0, mstride, vpos, vmass, (int)np, out)
     if (MODE == 0) {
         if (mk == 2) VPM_AGG(0, 2, false);
         else if (mk == 1) VPM_AGG(0, 1, false);
