@@ -85,3 +85,68 @@ def test_force_operator_matches_gravity(device_pm):
     for variant in ('force', 'force_rc'):
         for a, b, what in zip(out[variant], out['gravity'], ['f', 'potk', 'vjp', 'jvp_f', 'jvp_potk']):
             assert rel_l2(a, b) < 1e-12, (variant, what, rel_l2(a, b))
+
+
+def test_chisquare_gauss_newton_vs_oracle(oracle_pm, device_pm):
+    """config-4 shape (contrib Chi-square: objective, gradient, Gauss-Newton J^T J v) on the
+    device against the same problem on the oracle backend"""
+    from vmad_b200 import autooperator
+    from vmad_b200.contrib.chisquare import MPIChiSquareProblem
+    from vmad_b200.lib import fastpm, linalg
+    N = 16
+    L = 50.0
+    rng = numpy.random.default_rng(3)
+    data_h = 1.0 + 0.3 * rng.standard_normal((N, N, N))
+    wn = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5
+    vh = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5
+    stages = numpy.linspace(0.1, 1.0, 6)
+    out = {}
+    for name, PM in [('oracle', oracle_pm), ('device', device_pm)]:
+        pm = PM([N] * 3, L)
+        q = pm.generate_uniform_particle_grid(shift=0.0)
+        data = pm.create('real', value=data_h)
+
+        @autooperator('x->model')
+        def forward(x):
+            rhok = fastpm.induce_correlation(x, power, pm)
+            dx, p, f = fastpm.nbody(rhok, q, stages, Cosmology, pm)
+            xf = linalg.add(dx, q)
+            layout = fastpm.decompose(xf, pm)
+            return dict(model=fastpm.paint(xf, 1.0, layout, pm))
+
+        @autooperator('model->r')
+        def residual(model):
+            return dict(r=(model - data) * 0.5)
+
+        problem = MPIChiSquareProblem(pm.comm, forward, [residual])
+        s = pm.create('complex', value=wn)
+        v = pm.create('complex', value=vh)
+        out[name] = [float(problem.objective(s)), host(problem.gradient(s)),
+                     host(problem.hessian_vector_product(s, v))]
+    assert abs(out['device'][0] - out['oracle'][0]) < 1e-11 * abs(out['oracle'][0])
+    assert rel_l2(out['device'][1], out['oracle'][1]) < 1e-10
+    assert rel_l2(out['device'][2], out['oracle'][2]) < 1e-10
+
+
+def test_apply_digitized_vs_oracle(oracle_pm, device_pm):
+    from vmad_b200 import Builder
+    from vmad_b200.lib import fastpm
+    N = 8
+    kedges = numpy.linspace(0, 2 * numpy.pi / 4.0 * 3, 8)
+    digitizer = fastpm.apply_digitized.isotropic_wavenumber(kedges)
+    rng = numpy.random.default_rng(9)
+    xh = rng.standard_normal((N, N, N))
+    out = {}
+    for mode in ('amplitude', 'phase'):
+        tf0 = numpy.linspace(-1, 2, len(kedges) - 1) if mode == 'phase' else numpy.arange(len(kedges) - 1) + 1.0
+        for name, PM in [('oracle', oracle_pm), ('device', device_pm)]:
+            pm = PM([N] * 3, 4.0)
+            c0 = pm.create('real', value=xh).r2c()
+            with Builder() as m:
+                t = m.input('x')
+                c = fastpm.apply_digitized(c0, tf=t, digitizer=digitizer, kind='wavenumber', mode=mode)
+                m.output(y=fastpm.to_scalar(fastpm.c2r(c)))
+            (y,), (g,) = m.compute_with_vjp(init=dict(x=tf0), v=dict(_y=1.0))
+            out[name] = (float(y), numpy.asarray(g))
+        assert abs(out['device'][0] - out['oracle'][0]) < 1e-12 * abs(out['oracle'][0])
+        assert numpy.allclose(out['device'][1], out['oracle'][1], rtol=1e-10, atol=1e-12)

@@ -205,6 +205,96 @@ class apply_transfer:
         return dict(y_=_apply_tf(x_, tf, kind, False))
 
 
+def _take_default(array, ind, conj, default):
+    """``array[ind]`` with out-of-range bins replaced by ``default`` and conjugation where
+    flagged (fastpm.py:89-95)"""
+    array = numpy.asarray(array)
+    ind1 = ind.clip(0, len(array) - 1)
+    r = array[ind1]
+    if conj.any():
+        r = numpy.where(conj, numpy.conj(r), r)
+    return numpy.where(ind != ind1, default, r)
+
+
+def _times_table(x, table):
+    """field times a host multiplier table of the field's (local) shape"""
+    f = getattr(x.pm, '_transfer_table', None)
+    if f is not None:
+        return f(x, numpy.ascontiguousarray(table))
+    return x * table
+
+
+@operator
+class apply_digitized:
+    """fastpm.py:97-213 -- transfer function given per bin: ``y = x * tf[bin(k)]`` (mode
+    'amplitude') or ``y = x * exp(i tf[bin(k)])`` (mode 'phase'); modes whose bin falls outside
+    ``tf`` are left alone.  ``digitizer(k) -> (ind, conj)``.  The binned reductions of the vjp
+    run on the host (this operator is used by no autooperator of the library)."""
+    ain = 'x', 'tf'
+    aout = 'y'
+
+    @staticmethod
+    def isotropic_wavenumber(kedges):
+        def digitizer(k):
+            k2 = k.normp(2)
+            ind = numpy.digitize(k2 ** 0.5, kedges) - 1
+            return ind, numpy.zeros_like(ind, dtype='?')
+        return digitizer
+
+    def apl(node, x, tf, digitizer, kind='wavenumber', mode='amplitude'):
+        assert mode in ('amplitude', 'phase')
+        shape = tuple(x.shape)
+        ind, conj = digitizer(x._coords(kind))
+        ind = numpy.broadcast_to(numpy.asarray(ind, dtype='intp'), shape)
+        conj = numpy.broadcast_to(numpy.asarray(conj, dtype='?'), shape)
+        tf = numpy.asarray(tf)
+        if mode == 'amplitude':
+            eit = None
+            y = _times_table(x, _take_default(tf, ind, conj, 1))
+        else:
+            eit = numpy.exp(1j * tf)
+            y = _times_table(x, _take_default(eit, ind, conj, 1))
+        return dict(y=y, ind=ind, conj=conj, eit=eit)
+
+    def vjp(node, _y, x, tf, ind, conj, eit, mode):
+        tf = numpy.asarray(tf)
+        ind1 = ind.clip(0, len(tf) - 1)
+        mask = ind1 != ind
+        pm = x.pm
+        _y = pm.create(type='complex', value=_y)
+        # every stored mode stands for 1 or 2 modes of the full spectrum (fastpm.py:174,188)
+        i_last = x._coords('index')[-1]
+        mult = 1 + ((i_last != 0) & (numpy.abs(i_last) != int(pm.Nmesh[-1]) // 2))
+        xh = numpy.asarray(x)
+        yh = numpy.asarray(_y)
+        if mode == 'amplitude':
+            weights = yh * numpy.conj(xh) * mult
+            _x = _times_table(_y, _take_default(tf, ind, conj, 1))
+        else:
+            y = xh * _take_default(eit, ind, conj, 0)
+            weights = yh * numpy.conj(1j * y) * mult
+            _x = _times_table(_y, _take_default(eit.conj(), ind, conj, 1))
+        weights = numpy.where(mask, 0, weights)
+        _tf = numpy.bincount(ind1.ravel(), weights=weights.real.ravel(), minlength=len(tf))
+        _tf = pm.comm.allreduce(_tf)
+        return dict(_tf=_tf, _x=_x)
+
+    def jvp(node, tf_, x_, x, tf, ind, conj, eit, mode):
+        y_ = 0
+        tf = numpy.asarray(tf)
+        if mode == 'amplitude':
+            if not _is_zero(tf_):
+                y_ = y_ + _times_table(x, _take_default(numpy.asarray(tf_), ind, conj, 0))
+            if not _is_zero(x_):
+                y_ = y_ + _times_table(x.pm.create(type='complex', value=x_), _take_default(tf, ind, conj, 1))
+        else:
+            if not _is_zero(tf_):
+                y_ = y_ + _times_table(x, _take_default(eit * 1j * numpy.asarray(tf_), ind, conj, 0))
+            if not _is_zero(x_):
+                y_ = y_ + _times_table(x.pm.create(type='complex', value=x_), _take_default(eit, ind, conj, 1))
+        return dict(y_=y_)
+
+
 # ---------------------------------------------------------------------------------------------
 # particles <-> mesh
 # ---------------------------------------------------------------------------------------------
