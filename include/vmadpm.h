@@ -161,6 +161,11 @@ int vpm_r2c(vpm_ctx* ctx, const int64_t n[3], const double* real_in, double* cpl
 int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
             double scale);
 
+/* same transform, but the complex input is a scratch buffer the caller gives up (cuFFT may
+ * overwrite it): saves the staging copy for temporaries such as the force gradient fields */
+int vpm_c2r_inplace(vpm_ctx* ctx, const int64_t n[3], double* cplx_scratch, double* real_out,
+                    double scale);
+
 /* Pieces of the slab-decomposed transform (the local transforms are cuFFT; the transpose
  * between them is an all-to-all done by the caller):
  *   r2c: vpm_fft_r2c_planes -> vpm_swap_leading_axes (pack) -> all-to-all -> vpm_fft_c2c_axis0

@@ -75,6 +75,7 @@ SIGNATURES = {
     'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
+    'vpm_c2r_inplace': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_fft_r2c_planes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P]),
     'vpm_fft_c2r_planes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P, c_double]),
     'vpm_fft_c2c_axis0': (c_int, [c_void_p, c_int64, c_int64, _P, c_int, c_double]),

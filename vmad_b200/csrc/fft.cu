@@ -119,15 +119,18 @@ int vpm_r2c(vpm_ctx* ctx, const int64_t n[3], const double* real_in, double* cpl
     VPM_API_END
 }
 
-int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
-            double scale) {
+static int c2r_impl(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
+                    double scale, bool preserve_input) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx && n && cplx_in && real_out, "NULL argument");
     cufftHandle h = ctx->plan(n, 1);
     // multi-dimensional Z2D may overwrite its input; operators must not mutate theirs
-    size_t bytes = (size_t)16 * n[0] * n[1] * (n[2] / 2 + 1);
-    void* stage = ctx->workspace(bytes);
-    VPM_CUDA(cudaMemcpyAsync(stage, cplx_in, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    void* stage = const_cast<double*>(cplx_in);
+    if (preserve_input) {
+        size_t bytes = (size_t)16 * n[0] * n[1] * (n[2] / 2 + 1);
+        stage = ctx->workspace(bytes);
+        VPM_CUDA(cudaMemcpyAsync(stage, cplx_in, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     VPM_CUFFT(cufftExecZ2D(h, reinterpret_cast<cufftDoubleComplex*>(stage), real_out));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (scale != 1.0) {
@@ -136,6 +139,16 @@ int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* rea
                    ctx->stream, nd, scale, real_out);
     }
     VPM_API_END
+}
+
+int vpm_c2r(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
+            double scale) {
+    return c2r_impl(ctx, n, cplx_in, real_out, scale, true);
+}
+
+int vpm_c2r_inplace(vpm_ctx* ctx, const int64_t n[3], double* cplx_scratch, double* real_out,
+                    double scale) {
+    return c2r_impl(ctx, n, cplx_scratch, real_out, scale, false);
 }
 
 int vpm_fft_r2c_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, const double* real_in,

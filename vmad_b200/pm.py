@@ -95,6 +95,8 @@ def _upload(a, dtype=None):
     if dtype is None:
         dtype = numpy.complex128 if numpy.iscomplexobj(a) else numpy.float64
     a = numpy.ascontiguousarray(a, dtype=dtype)
+    if not a.flags.writeable:
+        a = a.copy()
     return torch.from_numpy(a).to(rt.device)
 
 
@@ -1178,13 +1180,15 @@ class ParticleMesh(object):
         C.check(C.lib.vpm_r2c(rt.ctx, C.i3(self._n3), _ptr(real.t), _ptr(o), float(scale)))
         return ComplexField(self, o)
 
-    def _c2r(self, cplx, scale):
+    def _c2r(self, cplx, scale, consume=False):
+        """``consume``: the caller owns ``cplx`` and gives it up (no input-preserving copy)"""
         rt = self.rt
         rt.sync_stream()
         if self.P > 1:
-            return self._c2r_slab(cplx, scale)
+            return self._c2r_slab(cplx, scale, consume)
         o = rt.empty(self.rshape)
-        C.check(C.lib.vpm_c2r(rt.ctx, C.i3(self._n3), _ptr(cplx.t), _ptr(o), float(scale)))
+        fn = C.lib.vpm_c2r_inplace if consume else C.lib.vpm_c2r
+        C.check(fn(rt.ctx, C.i3(self._n3), _ptr(cplx.t), _ptr(o), float(scale)))
         return RealField(self, o)
 
     # slab-decomposed transforms: local cuFFT, one all-to-all transpose each -------------------
@@ -1204,12 +1208,12 @@ class ParticleMesh(object):
         C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(recv), 0, float(scale)))
         return ComplexField(self, recv.view(N0, n1l, Nh))
 
-    def _c2r_slab(self, cplx, scale):
+    def _c2r_slab(self, cplx, scale, consume=False):
         rt = self.rt
         P = self.P
         n0l, N1, N2 = self.rshape
         N0, n1l, Nh = self.cshape
-        work = cplx.t.clone()                           # operators must not mutate their inputs
+        work = cplx.t if consume else cplx.t.clone()    # operators must not mutate their inputs
         C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(work), 1, 1.0))
         recv = self.comm.alltoall_blocks(work.view(P, n0l, n1l, Nh))   # [P (column block), n0l, n1l, Nh]
         a = rt.empty((n0l, N1, Nh), _C16)
@@ -1316,7 +1320,7 @@ class ForceState(object):
     def meshes(self, pm):
         if self.F is not None:
             return self.F
-        return [pm._c2r(pm._transfer(self.potk, tables=_only(d, self.grad_tables[d])), 1.0)
+        return [pm._c2r(pm._transfer(self.potk, tables=_only(d, self.grad_tables[d])), 1.0, consume=True)
                 for d in range(3)]
 
 
@@ -1357,7 +1361,7 @@ def force_apl(pm, dx, q):
     scale = 1.0 / npart                                        # (Nc / Np) * (1 / Nc)
     tabs = _force_tables(pm)
     potk, g = pm.force_kspace(rhok, scale, tabs, want_p=True)
-    F = [pm._c2r(gd, 1.0) for gd in g]
+    F = [pm._c2r(gd, 1.0, consume=True) for gd in g]   # g are temporaries of this call
     fl = pm.readout3(F[0], F[1], F[2], xl)
     f = layout.gather(fl)
     if getattr(pm, 'force_recompute', False):
@@ -1392,7 +1396,7 @@ def force_vjp(pm, st, _f, _potk):
         _ptr(pm._k_table(1)), _ptr(pm._k_table(2)), _ptr(st.grad_tables[0]),
         _ptr(st.grad_tables[1]), _ptr(st.grad_tables[2]), _ptr(rhok_bar)))
     # r2c.vjp of the un-normalised transform is the un-normalised inverse
-    rho_bar = pm._c2r(ComplexField(pm, rhok_bar), 1.0)
+    rho_bar = pm._c2r(ComplexField(pm, rhok_bar), 1.0, consume=True)
     # particle half: readout.vjp x3 and paint.vjp in one pass
     F = st.meshes(pm)
     rt.sync_stream()
@@ -1416,6 +1420,6 @@ def force_jvp(pm, st, dx_):
     cols = []
     F = st.meshes(pm)
     for d in range(3):
-        Fd_ = pm._c2r(g_[d], 1.0)
+        Fd_ = pm._c2r(g_[d], 1.0, consume=True)
         cols.append(pm._readout_jvp(F[d], xl, Fd_, xl_, None))
     return lay.gather(stack(cols, axis=-1)), potk_
