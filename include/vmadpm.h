@@ -217,6 +217,17 @@ int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, co
                          const double* kk1, const double* kk2, const double* a0, const double* a1,
                          const double* a2, double* rhok_bar);
 
+/* Real-space form of fourier_space_neg_gradient(order=1) (fastpm.py:316-323): its multiplier is
+ * the Fourier symbol of minus the 4-point central difference, so the three force meshes of
+ * `gravity` are f_d = -D_d phi, phi = c2r(p): one inverse FFT + this stencil instead of three
+ * inverse FFTs.  n: real mesh shape (single slab), h: cell sizes BoxSize / Nmesh. */
+int vpm_fd4_neg_gradient(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* phi,
+                         double* f0, double* f1, double* f2);
+/* adjoint: phibar = sum_d D_d fbar_d */
+int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3],
+                                 const double* f0, const double* f1, const double* f2,
+                                 double* phibar);
+
 /* ---- elementwise and reductions on flat fp64 arrays (the stdlib arithmetic that
  *      vmad applies to fields / particle arrays: vmad/core/stdlib/operators.py:14-152;
  *      kick / drift of fastpm.py:459-471) ------------------------------------- */

@@ -73,8 +73,13 @@ def test_force_operator_matches_gravity(device_pm):
     cp = pm.create('complex', value=rng.standard_normal(pm.cshape) + 1j * rng.standard_normal(pm.cshape))
     tan = put(rng.standard_normal((N ** 3, 3)))
     out = {}
-    for name, op in [('gravity', fastpm.gravity), ('force', fastpm.force), ('force_rc', fastpm.force)]:
-        pm.force_recompute = (name == 'force_rc')
+    variants = {'gravity': (fastpm.gravity, True, False),
+                'force_stencil': (fastpm.force, True, False),      # real-space gradients (default)
+                'force_kspace': (fastpm.force, False, False),      # k-space gradients, meshes kept
+                'force_kspace_rc': (fastpm.force, False, True)}    # ... meshes recomputed
+    for name, (op, stencil, recompute) in variants.items():
+        pm.force_stencil = stencil
+        pm.force_recompute = recompute
         with Builder() as m:
             x = m.input('x')
             f, potk = op(x, q, pm)
@@ -82,8 +87,9 @@ def test_force_operator_matches_gravity(device_pm):
         (f, potk), (g,) = m.compute_with_vjp(init=dict(x=dx), v=dict(_f=cf, _potk=cp))
         _, (f_, potk_) = m.compute_with_jvp(['f', 'potk'], init=dict(x=dx), v=dict(x_=tan))
         out[name] = [host(a) for a in (f, potk, g, f_, potk_)]
-    for variant in ('force', 'force_rc'):
+    for variant in ('force_stencil', 'force_kspace', 'force_kspace_rc'):
         for a, b, what in zip(out[variant], out['gravity'], ['f', 'potk', 'vjp', 'jvp_f', 'jvp_potk']):
+            print(variant, what, rel_l2(a, b))
             assert rel_l2(a, b) < 1e-12, (variant, what, rel_l2(a, b))
 
 

@@ -88,6 +88,8 @@ SIGNATURES = {
                                  _P, _P, _P, _P, _P]),
     'vpm_force_kspace_vjp': (c_int, [c_void_p, POINTER(c_int64), _P, _P, _P, _P, c_double, _P, _P, _P,
                                      _P, _P, _P, _P]),
+    'vpm_fd4_neg_gradient': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
+    'vpm_fd4_neg_gradient_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
     'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),
     'vpm_mul': (c_int, [c_void_p, c_int64, _P, _P, _P]),
     'vpm_div': (c_int, [c_void_p, c_int64, _P, _P, _P]),

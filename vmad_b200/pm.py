@@ -1307,19 +1307,22 @@ class ParticleMesh(object):
 # ---------------------------------------------------------------------------------------------
 class ForceState(object):
     """what one fused force evaluation leaves on the tape for its vjp / jvp"""
-    __slots__ = ('xl', 'layout', 'F', 'potk', 'scale', 'grad_tables')
+    __slots__ = ('xl', 'layout', 'F', 'potk', 'phi', 'scale', 'grad_tables')
 
-    def __init__(self, xl, layout, F, potk, scale, grad_tables):
+    def __init__(self, xl, layout, F, potk, phi, scale, grad_tables):
         self.xl = xl
         self.layout = layout
         self.F = F            # the three real force meshes, or None when they are recomputed
-        self.potk = potk      # kept only when F is not (1 complex mesh instead of 3 real ones)
+        self.potk = potk      # slab path with recompute: 1 complex mesh instead of 3 real ones
+        self.phi = phi        # single-GPU path: the real potential; F_d = -D_d phi by stencil
         self.scale = scale
         self.grad_tables = grad_tables
 
     def meshes(self, pm):
         if self.F is not None:
             return self.F
+        if self.phi is not None:
+            return _fd4(pm, self.phi)
         return [pm._c2r(pm._transfer(self.potk, tables=_only(d, self.grad_tables[d])), 1.0, consume=True)
                 for d in range(3)]
 
@@ -1328,6 +1331,20 @@ def _only(d, table):
     t = [None, None, None]
     t[d] = table
     return t
+
+
+def _h3(pm):
+    return (ctypes.c_double * 3)(*[float(pm.BoxSize[d] / pm.Nmesh[d]) for d in range(3)])
+
+
+def _fd4(pm, phi):
+    """F_d = -D_d phi: the three force meshes from the real potential (4-point stencil)"""
+    rt = pm.rt
+    rt.sync_stream()
+    F = [rt.empty(pm.rshape) for _ in range(3)]
+    C.check(C.lib.vpm_fd4_neg_gradient(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(phi.t), _ptr(F[0]),
+                                       _ptr(F[1]), _ptr(F[2])))
+    return [RealField(pm, t) for t in F]
 
 
 def _force_tables(pm, order=1):
@@ -1345,6 +1362,12 @@ def _force_tables(pm, order=1):
     return pm._tables[key]
 
 
+def _use_stencil(pm):
+    """the real-space gradient needs +-2 planes of neighbours: single slab only (a slab
+    decomposition would need a halo exchange; it keeps the k-space gradients)"""
+    return pm.P == 1 and getattr(pm, 'force_stencil', True) and min(pm.rshape) >= 1
+
+
 def force_apl(pm, dx, q):
     """f = -grad laplace^-1 (rho Nc / Np) read out at x = q + dx; returns (f, potk, state)"""
     if pm.ndim != 3:
@@ -1360,14 +1383,21 @@ def force_apl(pm, dx, q):
     npart = pm.comm.allreduce(len(q))
     scale = 1.0 / npart                                        # (Nc / Np) * (1 / Nc)
     tabs = _force_tables(pm)
+    if _use_stencil(pm):
+        # one inverse FFT (of the potential) + a streaming 4-point stencil for the 3 gradients
+        potk = pm._transfer(rhok, scale=scale, laplace=True)
+        phi = pm._c2r(potk, 1.0)                               # potk is an output: preserved
+        F = _fd4(pm, phi)
+        fl = pm.readout3(F[0], F[1], F[2], xl)
+        return layout.gather(fl), potk, ForceState(xl, layout, None, None, phi, scale, tabs)
     potk, g = pm.force_kspace(rhok, scale, tabs, want_p=True)
     F = [pm._c2r(gd, 1.0, consume=True) for gd in g]   # g are temporaries of this call
     fl = pm.readout3(F[0], F[1], F[2], xl)
     f = layout.gather(fl)
     if getattr(pm, 'force_recompute', False):
         # trade 3 inverse FFTs in the reverse sweep for 2/3 of the mesh memory on the tape
-        return f, potk, ForceState(xl, layout, None, potk, scale, tabs)
-    return f, potk, ForceState(xl, layout, F, None, scale, tabs)
+        return f, potk, ForceState(xl, layout, None, potk, None, scale, tabs)
+    return f, potk, ForceState(xl, layout, F, None, None, scale, tabs)
 
 
 def force_vjp(pm, st, _f, _potk):
@@ -1380,23 +1410,37 @@ def force_vjp(pm, st, _f, _potk):
         _fl = DeviceArray(torch.zeros((n, 3), dtype=_F8, device=rt.device))
     else:
         _fl = lay.exchange(asdevice(_f))
-    # readout.vjp (mesh half) x3 -> c2r.vjp x3: three paints of the columns, three forward FFTs
-    gbar = []
+    # readout.vjp (mesh half) x3: three paints of the columns of the force cotangent
+    Fbar = []
     rt.sync_stream()
     for d in range(3):
         m = rt.empty(pm.rshape)
         C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(pm._mesh), _ptr(xl.t), _ptr(_fl.t),
                                            3, d, n, _ptr(pm._dummy_cs()), _ptr(m)))
-        gbar.append(pm._r2c(RealField(pm, m), 1.0))
+        Fbar.append(RealField(pm, m))
     pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
-    rhok_bar = rt.empty(pm.cshape, _C16)
-    C.check(C.lib.vpm_force_kspace_vjp(
-        rt.ctx, C.i3(pm._cshape3), _ptr(gbar[0].t), _ptr(gbar[1].t), _ptr(gbar[2].t),
-        _ptr(pbar.t) if pbar is not None else None, float(st.scale), _ptr(pm._k_table(0)),
-        _ptr(pm._k_table(1)), _ptr(pm._k_table(2)), _ptr(st.grad_tables[0]),
-        _ptr(st.grad_tables[1]), _ptr(st.grad_tables[2]), _ptr(rhok_bar)))
+    if st.phi is not None:
+        # adjoint of the stencil, then ONE forward FFT (c2r.vjp of the un-normalised inverse)
+        phibar = rt.empty(pm.rshape)
+        C.check(C.lib.vpm_fd4_neg_gradient_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(Fbar[0].t),
+                                                   _ptr(Fbar[1].t), _ptr(Fbar[2].t), _ptr(phibar)))
+        del Fbar
+        potk_bar = pm._r2c(RealField(pm, phibar), 1.0)
+        if pbar is not None:
+            potk_bar = potk_bar + pbar
+        rhok_bar = pm._transfer(potk_bar, scale=st.scale, laplace=True)
+    else:
+        gbar = [pm._r2c(Fd, 1.0) for Fd in Fbar]
+        del Fbar
+        out = rt.empty(pm.cshape, _C16)
+        C.check(C.lib.vpm_force_kspace_vjp(
+            rt.ctx, C.i3(pm._cshape3), _ptr(gbar[0].t), _ptr(gbar[1].t), _ptr(gbar[2].t),
+            _ptr(pbar.t) if pbar is not None else None, float(st.scale), _ptr(pm._k_table(0)),
+            _ptr(pm._k_table(1)), _ptr(pm._k_table(2)), _ptr(st.grad_tables[0]),
+            _ptr(st.grad_tables[1]), _ptr(st.grad_tables[2]), _ptr(out)))
+        rhok_bar = ComplexField(pm, out)
     # r2c.vjp of the un-normalised transform is the un-normalised inverse
-    rho_bar = pm._c2r(ComplexField(pm, rhok_bar), 1.0, consume=True)
+    rho_bar = pm._c2r(rhok_bar, 1.0, consume=True)
     # particle half: readout.vjp x3 and paint.vjp in one pass
     F = st.meshes(pm)
     rt.sync_stream()
@@ -1416,10 +1460,12 @@ def force_jvp(pm, st, dx_):
     xl_ = lay.exchange(asdevice(dx_))
     rho_ = pm.paint_jvp(xl, mass=1.0, v_pos=xl_)
     rhok_ = pm._r2c(rho_, 1.0)
-    potk_, g_ = pm.force_kspace(rhok_, st.scale, st.grad_tables, want_p=True)
-    cols = []
+    if st.phi is not None:
+        potk_ = pm._transfer(rhok_, scale=st.scale, laplace=True)
+        F_ = _fd4(pm, pm._c2r(potk_, 1.0))
+    else:
+        potk_, g_ = pm.force_kspace(rhok_, st.scale, st.grad_tables, want_p=True)
+        F_ = [pm._c2r(g_[d], 1.0, consume=True) for d in range(3)]
     F = st.meshes(pm)
-    for d in range(3):
-        Fd_ = pm._c2r(g_[d], 1.0, consume=True)
-        cols.append(pm._readout_jvp(F[d], xl, Fd_, xl_, None))
+    cols = [pm._readout_jvp(F[d], xl, F_[d], xl_, None) for d in range(3)]
     return lay.gather(stack(cols, axis=-1)), potk_
