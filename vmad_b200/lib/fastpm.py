@@ -497,24 +497,34 @@ def DriftFactor(pt, ai, ac, af):
 
 
 def _leapfrog_body(dx, p, stages, pt, force_fn, fused=False):
-    """kick-drift-kick stepping of fastpm.py:455-473 around a force callback; ``fused`` swaps
-    the stdlib mul + add pairs for the single-pass kick / drift operators (same values)"""
+    """kick-drift-kick stepping of fastpm.py:455-473 around a force callback.
+
+    ``fused`` (device backend) uses the single-pass kick / drift operators and merges the
+    closing half-kick of a step with the opening half-kick of the next one -- both add the SAME
+    force to ``p`` with nothing in between, so ``p + f c1 + f c2 = p + f (c1 + c2)`` (one pass
+    over the particles instead of two; equal to rounding)."""
     Om0 = pt.Om0
-    if fused:
-        do_kick = lambda p, f, c: kick(p, f, c)
-        do_drift = lambda dx, p, c: drift(dx, p, c)
-    else:
-        do_kick = lambda p, f, c: p + f * c
-        do_drift = lambda dx, p, c: dx + p * c
+    pairs = list(zip(stages[:-1], stages[1:]))
     f, potk = force_fn(dx)
-    for ai, af in zip(stages[:-1], stages[1:]):
+    if not fused:
+        for ai, af in pairs:
+            ac = (ai * af) ** 0.5
+            p = p + f * (KickFactor(pt, ai, ai, ac) * 1.5 * Om0)       # kick
+            dx = dx + p * DriftFactor(pt, ai, ac, af)                  # drift
+            f, potk = force_fn(dx)                                     # force
+            p = p + f * (KickFactor(pt, ac, af, af) * 1.5 * Om0)       # kick
+        return dict(dx=dx, p=p, f=f * (1.5 * Om0))
+    opening = [KickFactor(pt, ai, ai, (ai * af) ** 0.5) * 1.5 * Om0 for ai, af in pairs]
+    closing = [KickFactor(pt, (ai * af) ** 0.5, af, af) * 1.5 * Om0 for ai, af in pairs]
+    if pairs:
+        p = kick(p, f, opening[0])
+    for i, (ai, af) in enumerate(pairs):
         ac = (ai * af) ** 0.5
-        p = do_kick(p, f, KickFactor(pt, ai, ai, ac) * 1.5 * Om0)
-        dx = do_drift(dx, p, DriftFactor(pt, ai, ac, af))
+        dx = drift(dx, p, DriftFactor(pt, ai, ac, af))
         f, potk = force_fn(dx)
-        p = do_kick(p, f, KickFactor(pt, ac, af, af) * 1.5 * Om0)
-    f = f * (1.5 * Om0)
-    return dict(dx=dx, p=p, f=f)
+        c = closing[i] + (opening[i + 1] if i + 1 < len(pairs) else 0.0)
+        p = kick(p, f, c)
+    return dict(dx=dx, p=p, f=f * (1.5 * Om0))
 
 
 @autooperator('dx_i,p_i->dx,p,f')

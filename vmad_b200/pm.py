@@ -1097,6 +1097,10 @@ class ParticleMesh(object):
     def _readout(self, field, pos, layout):
         rt = self.rt
         pos = asdevice(pos)
+        if layout is not None and self.P == 1:
+            # one rank: the layout only re-orders.  A gather needs no sorted input (a scatter
+            # does), and exchange + gather would cost four more passes over the particles
+            layout = None
         xs = layout.exchange(pos) if layout is not None else pos
         _, x3 = self._pos3(xs)
         rt.sync_stream()
