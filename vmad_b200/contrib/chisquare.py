@@ -5,7 +5,9 @@ FastPM simulation), R_i residual operators -- into objective / gradient / Gauss-
 Hessian-vector product callables (chisquare.py:34-99).  The reference derives from
 ``abopt.abopt2.Problem`` / ``VectorSpace`` (an optimiser package that is not part of vmad and
 is absent here); when abopt is importable those bases are used, otherwise two minimal
-stand-ins with the same constructor arguments.  The optimisers themselves are out of scope.
+stand-ins with the same constructor arguments.  The optimisers themselves and the multi-epoch
+driver scaffolding around them (``EpochScheduler``, ``MAPInversion``: chisquare.py:101-246,
+pure bookkeeping over an abopt optimiser object) are out of scope.
 """
 from ..vm import Builder, autooperator
 from ..lib import linalg, mpi
@@ -112,91 +114,3 @@ class MPIChiSquareProblem(BaseProblem):
 
         BaseProblem.__init__(self, vs=vectorspace, objective=objective, gradient=gradient,
                              hessian_vector_product=hessian_vector_product)
-
-
-class EpochScheduler(dict):
-    """chisquare.py:101-151 -- per-epoch hyper-parameter schedule"""
-
-    def __call__(self, argname, values):
-        self.schedule(argname, values)
-
-    @property
-    def min_nepochs(self):
-        return max(list(self.keys()) + [0]) + 1
-
-    def schedule(self, argname, values):
-        if isinstance(values, (list, tuple)):
-            items = enumerate(values)
-        elif isinstance(values, dict):
-            items = values.items()
-        else:
-            items = enumerate([values])
-        for epoch, value in items:
-            args = self.get(epoch, {})
-            args[argname] = value
-            self[epoch] = args
-
-    def get_args(self, epoch):
-        args = {}
-        for e in sorted(self.keys()):
-            if e <= epoch:
-                args.update(self[e])
-        return args
-
-
-class Epoch(object):
-    def __init__(self, epoch, nepochs):
-        self.epoch = epoch
-        self.nepochs = nepochs
-
-    def __repr__(self):
-        return "Epoch %d / %d" % (self.epoch, self.nepochs)
-
-
-class MAPInversion(object):
-    """chisquare.py:160-246 -- multi-epoch MAP reconstruction driver around an optimiser object
-    that offers ``minimize(problem, x0, monitor=)`` (abopt's; not provided here)"""
-
-    def __init__(self, optimizer, ForwardOperator):
-        self.optimizer = optimizer
-        self.ForwardOperator = ForwardOperator
-        self.schedule_optimizer = EpochScheduler()
-        self.schedule_problem = EpochScheduler()
-
-    @classmethod
-    def create_like(kls, other, epochs=None):
-        self = object.__new__(kls)
-        self.__dict__.update(other.__dict__)
-        self.schedule_optimizer = EpochScheduler()
-        self.schedule_problem = EpochScheduler()
-        if epochs is None:
-            self.schedule_optimizer.update(other.schedule_optimizer)
-            self.schedule_problem.update(other.schedule_problem)
-        else:
-            for i, epoch in enumerate(epochs):
-                self.schedule_optimizer[i] = other.schedule_optimizer.get_args(epoch)
-                self.schedule_problem[i] = other.schedule_problem.get_args(epoch)
-        return self
-
-    def apply(self, d, s0, epochs=None, monitor_epoch=None, monitor_progress=None):
-        if epochs is None:
-            epochs = range(self.nepochs)
-        s1 = s0
-        for epoch in epochs:
-            if monitor_epoch:
-                monitor_epoch(Epoch(epoch, max(epochs) + 1))
-            problem = self.get_problem(d, epoch)
-            self.optimizer.__dict__.update(self.schedule_optimizer.get_args(epoch))
-            state = self.optimizer.minimize(problem, s1, monitor=monitor_progress)
-            s1 = state['x']
-        return s1
-
-    @property
-    def nepochs(self):
-        return max(self.schedule_optimizer.min_nepochs, self.schedule_problem.min_nepochs)
-
-    def get_problem(self, d, epoch=0):
-        return self.problem_factory(d=d, **self.schedule_problem.get_args(epoch))
-
-    def problem_factory(self, d, **args):
-        raise NotImplementedError

@@ -1,56 +1,37 @@
-"""Error types of the tape VM (same names and hierarchy as vmad/core/error.py:1-21)."""
+"""Error types of the tape VM.
+
+The names are API (user code and the reference's tests catch them): the same hierarchy as
+vmad/core/error.py:1-21 -- everything derives from ``ModelError``; ``ExecutionError`` wraps an
+exception raised inside a node together with the node that raised it.
+"""
 
 
 class ModelError(Exception):
-    pass
+    """base of every error raised while building or running a model"""
 
 
-class BadArgument(ModelError):
-    pass
+def _declare(*names):
+    for name in names:
+        globals()[name] = type(name, (ModelError,), {'__module__': __name__})
 
 
-class UnpackError(ModelError):
-    pass
-
-
-class DuplicatedOutput(ModelError):
-    pass
-
-
-class MissingArgument(ModelError):
-    pass
-
-
-class OverwritePrecaution(ModelError):
-    pass
-
-
-class UnexpectedOutput(ModelError):
-    pass
-
-
-class ResolveError(ModelError):
-    pass
-
-
-class InferError(ModelError):
-    pass
-
-
-class BrokenPrimitive(ModelError):
-    pass
+# argument parsing / graph construction / execution problems
+_declare('BadArgument', 'UnpackError', 'DuplicatedOutput', 'MissingArgument',
+         'OverwritePrecaution', 'UnexpectedOutput', 'ResolveError', 'InferError',
+         'BrokenPrimitive')
 
 
 class ExecutionError(ModelError):
     def __init__(self, msg, reason):
-        self.reason = reason
         ModelError.__init__(self, msg)
+        self.reason = reason
 
 
 def makeExecutionError(msg, reason):
-    """An error that is both an ExecutionError and an instance of the original error type."""
+    """an error that is an ExecutionError AND an instance of the original exception's type, so
+    that ``except TypeError`` style handlers keep working when errors are wrapped"""
     try:
-        kls = type("ExecutionError(%s)" % type(reason).__name__, (type(reason), ExecutionError), {})
-        return kls(msg, reason)
-    except TypeError:
+        both = type("ExecutionError(%s)" % type(reason).__name__, (type(reason), ExecutionError), {})
+        return both(msg, reason)
+    except TypeError:  # exception types with incompatible layouts
         return ExecutionError(msg, reason)

@@ -22,34 +22,38 @@ class terminal:
         return dict(y_=x_)
 
 
-@operator
-class neg:
-    ain = 'x'
-    aout = 'y'
-
+def _linear_unary(name, f):
+    """y = f(x) with f linear: the vjp and jvp are f itself"""
     def apl(node, x):
-        return dict(y=-x)
+        return dict(y=f(x))
 
     def vjp(node, _y):
-        return dict(_x=-_y)
+        return dict(_x=f(_y))
 
     def jvp(node, x_):
-        return dict(y_=-x_)
+        return dict(y_=f(x_))
+
+    return operator(type(name, (), dict(ain='x', aout='y', apl=apl, vjp=vjp, jvp=jvp)))
 
 
-@operator
-class pos:
-    ain = 'x'
-    aout = 'y'
-
-    def apl(node, x):
-        return dict(y=+x)
+def _linear_binary(name, f, sign2):
+    """y = f(x1, x2) = x1 + sign2 * x2"""
+    def apl(node, x1, x2):
+        return dict(y=f(x1, x2))
 
     def vjp(node, _y):
-        return dict(_x=+_y)
+        return dict(_x1=_y, _x2=_y if sign2 > 0 else -_y)
 
-    def jvp(node, x_):
-        return dict(y_=+x_)
+    def jvp(node, x1_, x2_):
+        return dict(y_=f(x1_, x2_))
+
+    return operator(type(name, (), dict(ain=('x1', 'x2'), aout='y', apl=apl, vjp=vjp, jvp=jvp)))
+
+
+neg = _linear_unary('neg', lambda x: -x)
+pos = _linear_unary('pos', lambda x: +x)
+add = _linear_binary('add', lambda a, b: a + b, +1)
+sub = _linear_binary('sub', lambda a, b: a - b, -1)
 
 
 @operator
@@ -65,36 +69,6 @@ class abs:
 
     def jvp(node, x_, x):
         return dict(y_=x_ * (x > 0) + -x_ * (x < 0))
-
-
-@operator
-class add:
-    ain = 'x1', 'x2'
-    aout = 'y'
-
-    def apl(node, x1, x2):
-        return dict(y=x1 + x2)
-
-    def vjp(node, _y):
-        return dict(_x1=_y, _x2=_y)
-
-    def jvp(node, x1_, x2_):
-        return dict(y_=x1_ + x2_)
-
-
-@operator
-class sub:
-    ain = 'x1', 'x2'
-    aout = 'y'
-
-    def apl(node, x1, x2):
-        return dict(y=x1 - x2)
-
-    def vjp(node, _y):
-        return dict(_x1=_y, _x2=-_y)
-
-    def jvp(node, x1_, x2_):
-        return dict(y_=x1_ - x2_)
 
 
 @operator
