@@ -457,7 +457,7 @@ class ParticleMesh(object):
         """Integer frequency along axis ``d`` of the stored complex array."""
         N = int(self.Nmesh[d])
         j = numpy.arange(self.cshape[d], dtype='i8')
-        j[j >= N // 2] -= N
+        j[j >= (N + 1) // 2] -= N  # even N: Nyquist stored as -N/2; odd N: no Nyquist
         return j
 
     def hermitian_weights(self):

@@ -289,3 +289,42 @@ def test_paint_readout_adjoint_large(device_pm):
     assert abs(lhs - rhs) < 1e-11 * abs(lhs)
     total = dpm.paint(x, m).sum()
     assert abs(total - m.sum()) < 1e-11 * total
+
+
+def test_edge_cases_empty_single_and_odd_meshes(oracle_pm, device_pm, paint_algorithm):
+    """empty and one-particle inputs, odd mesh sizes (no Nyquist mode), a mesh axis of length 1"""
+    rng = numpy.random.default_rng(8)
+    for Nmesh, Box in [([5, 7, 9], [5.0, 3.5, 18.0]), ([1, 6, 4], 6.0), ([3, 1, 5], 2.0), ([9, 9], 4.5)]:
+        opm = oracle_pm(Nmesh, Box)
+        dpm = device_pm(Nmesh, Box)
+        nd = len(Nmesh)
+        L = numpy.empty(nd)
+        L[...] = Box
+        # empty particle set: a zero mesh, empty readouts, an empty layout
+        empty = numpy.zeros((0, nd))
+        assert numpy.array_equal(dpm.paint(empty, 1.0).numpy(), numpy.zeros(Nmesh))
+        f = rng.standard_normal(Nmesh)
+        df, of = dpm.create('real', value=f), opm.create('real', value=f)
+        assert df.readout(empty).numpy().shape == (0,)
+        lay = dpm.decompose(empty)
+        assert lay.exchange(empty).numpy().shape == (0, nd)
+        assert lay.gather(numpy.zeros((0,))).numpy().shape == (0,)
+        # one particle, and a handful, on this odd / degenerate mesh
+        for n in (1, 37):
+            x = rng.uniform(-1, 2, size=(n, nd)) * L
+            m = rng.uniform(0.5, 1.5, size=n)
+            assert rel_l2(dpm.paint(x, m).numpy(), opm.paint(x, m).value) < TOL
+            assert rel_l2(df.readout(x).numpy(), of.readout(x)) < TOL
+            dmesh, dpos = df.readout_vjp(x, m)
+            omesh, opos = of.readout_vjp(x, m)
+            assert rel_l2(dmesh.numpy(), omesh.value) < TOL
+            assert rel_l2(dpos.numpy(), opos) < TOL
+            assert numpy.array_equal(dpm.decompose(x).indices.cpu().numpy(), opm.decompose(x).indices)
+        # transforms and a k-space filter on odd sizes
+        c = rng.standard_normal(opm.cshape) + 1j * rng.standard_normal(opm.cshape)
+        dc, oc = dpm.create('complex', value=c), opm.create('complex', value=c)
+        assert rel_l2(df.r2c().numpy(), of.r2c().value) < TOL
+        assert rel_l2(dc.c2r().numpy(), oc.c2r().value) < TOL
+        assert abs(dc.cnorm() - oc.cnorm()) < 1e-12 * abs(oc.cnorm())
+        tf = lambda k: 1.0 / (1.0 + sum(ki ** 2 for ki in k)) + 0.5j * k[-1]
+        assert rel_l2(dc.apply(lambda k, v: v * tf(k)).numpy(), oc.apply(lambda k, v: v * tf(k)).value) < TOL

@@ -70,6 +70,31 @@ def _ptr(t):
 
 _KEEP_CELL_INDEX = False
 
+# bench.py sets this to a list to time every paint launch of a step in place (CUDA events on
+# the launching stream); entries are (start_event, end_event, algorithmic_bytes)
+PAINT_EVENTS = None
+
+
+class _timed_paint(object):
+    """context manager around one paint launch; a no-op unless PAINT_EVENTS is a list"""
+    __slots__ = ('nbytes', 'e0')
+
+    def __init__(self, nbytes):
+        self.nbytes = nbytes
+        self.e0 = None
+
+    def __enter__(self):
+        if PAINT_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PAINT_EVENTS.append((self.e0, e1, self.nbytes))
+        return False
+
 
 def set_paint_algorithm(name):
     """'aggregated' (default): warp-aggregated fp64 reductions, fastest; 'tile': shared-memory
@@ -79,6 +104,14 @@ def set_paint_algorithm(name):
     algo = {'aggregated': 0, 'tile': 1}[name]
     C.check(C.lib.vpm_paint_set_algorithm(algo))
     _KEEP_CELL_INDEX = (algo == 1)
+
+
+def _ncomp(t):
+    """values per row of a [n, ...] tensor (also right for n = 0)"""
+    c = 1
+    for d in t.shape[1:]:
+        c *= int(d)
+    return c
 
 
 def _is_zero_literal(x):
@@ -199,7 +232,7 @@ class DeviceArray(object):
         rt.sync_stream()
         out = torch.empty_like(self.t)
         n = self.t.shape[0]
-        C.check(C.lib.vpm_mul_rows(rt.ctx, n, self.t.numel() // n, _ptr(self.t), _ptr(w), _ptr(out)))
+        C.check(C.lib.vpm_mul_rows(rt.ctx, n, _ncomp(self.t), _ptr(self.t), _ptr(w), _ptr(out)))
         return self._like(out)
 
     @staticmethod
@@ -633,7 +666,7 @@ class Layout(object):
         rt.sync_stream()
         t = data.t
         n = self.newlength
-        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        ncomp = _ncomp(t)
         out = rt.empty((n,) + tuple(t.shape[1:]))
         C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, _ptr(out)))
         return DeviceArray(out, cellindex=self)
@@ -647,7 +680,7 @@ class Layout(object):
         rt.sync_stream()
         t = data.t
         n = self.newlength
-        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        ncomp = _ncomp(t)
         # single rank: the permutation is a bijection, every output row is written once
         out = rt.empty((self.oldlength,) + tuple(t.shape[1:]))
         C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, _ptr(out)))
@@ -694,7 +727,7 @@ class DistLayout(object):
     def _forward(self, t):
         """rows of a local [oldlength, ...] tensor -> rows received here, ordered by source"""
         rt = self.pm.rt
-        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        ncomp = _ncomp(t)
         send = rt.empty((self.nsend,) + tuple(t.shape[1:]))
         C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.send_idx), self.nsend, ncomp, _ptr(send)))
         return self.pm.comm.alltoallv_rows(send, self.send_counts, self.recv_counts)
@@ -705,7 +738,7 @@ class DistLayout(object):
         rt = self.pm.rt
         rt.sync_stream()
         recv = self._forward(data.t)
-        ncomp = recv.numel() // max(recv.shape[0], 1) if recv.dim() > 1 else 1
+        ncomp = _ncomp(recv)
         out = rt.empty(tuple(recv.shape))
         C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(recv), _ptr(self.indices), self.nrecv, ncomp, _ptr(out)))
         return DeviceArray(out, cellindex=self)
@@ -716,7 +749,7 @@ class DistLayout(object):
         rt = self.pm.rt
         rt.sync_stream()
         t = data.t
-        ncomp = t.numel() // max(t.shape[0], 1) if t.dim() > 1 else 1
+        ncomp = _ncomp(t)
         unsorted = rt.empty(tuple(t.shape))
         C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), self.nrecv, ncomp, _ptr(unsorted)))
         back = self.pm.comm.alltoallv_rows(unsorted, self.recv_counts, self.send_counts)
@@ -796,7 +829,7 @@ class ParticleMesh(object):
         """integer frequencies of the LOCAL part of complex axis d"""
         N = int(self.Nmesh[d])
         j = numpy.arange(self.gcshape[d], dtype='i8')
-        j[j >= N // 2] -= N
+        j[j >= (N + 1) // 2] -= N  # even N: Nyquist stored as -N/2; odd N: no Nyquist
         if self.P > 1 and d == 1:
             j = j[self.cstart1:self.cstart1 + self.cshape[1]]
         return j
@@ -979,8 +1012,10 @@ class ParticleMesh(object):
         marr = mass.t if isinstance(mass, DeviceArray) else None
         m0 = 1.0 if marr is not None else float(mass)
         o = rt.empty(self.rshape)
-        C.check(C.lib.vpm_paint_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr), m0,
-                                       x3.shape[0], _ptr(self._cell_start_of(lay, x3)), _ptr(o)))
+        cs = self._cell_start_of(lay, x3)
+        with _timed_paint((24.0 + (8.0 if marr is not None else 0.0)) * x3.shape[0] + 8.0 * o.numel()):
+            C.check(C.lib.vpm_paint_sorted(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(marr), m0,
+                                           x3.shape[0], _ptr(cs), _ptr(o)))
         return RealField(self, o)
 
     def _cell_start_of(self, lay, x3):
@@ -1419,8 +1454,9 @@ def force_vjp(pm, st, _f, _potk):
     rt.sync_stream()
     for d in range(3):
         m = rt.empty(pm.rshape)
-        C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(pm._mesh), _ptr(xl.t), _ptr(_fl.t),
-                                           3, d, n, _ptr(pm._dummy_cs()), _ptr(m)))
+        with _timed_paint(32.0 * n + 8.0 * m.numel()):
+            C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(pm._mesh), _ptr(xl.t), _ptr(_fl.t),
+                                               3, d, n, _ptr(pm._dummy_cs()), _ptr(m)))
         Fbar.append(RealField(pm, m))
     pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
     if st.phi is not None:
