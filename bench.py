@@ -241,6 +241,8 @@ def run_gpu(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout must carry the one JSON line only: NCCL's version / debug lines go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():
