@@ -204,7 +204,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -241,8 +241,6 @@ def run_gpu(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout must carry the one JSON line only: NCCL's version / debug lines go to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():
@@ -423,12 +421,32 @@ def run_gpu(args):
         "cpu_baseline": cpu_baseline,
         "host_wall_s_timed_region": wall,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry the one JSON line and nothing else: point fd 1 at stderr for the rest
+    of the process (NCCL, cuFFT and friends print their banners from C), keep the real one"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
