@@ -36,6 +36,14 @@ class TorchComm(object):
             device = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' \
                 else torch.device('cpu')
         self.device = device
+        # small host-side exchanges (the per-peer particle counts of a decompose) go through a
+        # CPU group when the main group is NCCL: no device tensor, no stream synchronisation
+        self._cpu_group = None
+        if self.device.type == 'cuda' and self.size > 1:
+            try:
+                self._cpu_group = dist.new_group(backend='gloo')
+            except Exception:
+                self._cpu_group = None
 
     # -- what vmad asks of a communicator ---------------------------------------------------
     def allreduce(self, x, op=None):
@@ -61,6 +69,11 @@ class TorchComm(object):
 
     # -- exchanges --------------------------------------------------------------------------
     def alltoall_counts(self, send_counts):
+        if self._cpu_group is not None:
+            s = torch.tensor([int(c) for c in send_counts], dtype=torch.int64)
+            r = torch.empty_like(s)
+            dist.all_to_all_single(r, s, group=self._cpu_group)
+            return [int(v) for v in r.tolist()]
         s = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=self.device)
         r = torch.empty_like(s)
         dist.all_to_all_single(r, s, group=self.group)

@@ -1247,6 +1247,50 @@ class ParticleMesh(object):
         C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(recv), 0, float(scale)))
         return ComplexField(self, recv.view(N0, n1l, Nh))
 
+    def _r2c_slab_many(self, reals, scale):
+        """several real fields at once: one all-to-all for all of them"""
+        rt = self.rt
+        rt.sync_stream()
+        P, K = self.P, len(reals)
+        n0l, N1, N2 = self.rshape
+        N0, n1l, Nh = self.cshape
+        send = rt.empty((P, K, n0l, n1l, Nh), _C16)
+        a = rt.empty((n0l, N1, Nh), _C16)
+        tmp = rt.empty((P, n0l, n1l, Nh), _C16)
+        for k, real in enumerate(reals):
+            C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
+            C.check(C.lib.vpm_swap_leading_axes(rt.ctx, n0l, P, n1l * Nh, _ptr(a), _ptr(tmp)))
+            send[:, k].copy_(tmp)
+        recv = self.comm.alltoall_blocks(send)            # [P, K, n0l, n1l, Nh]
+        out = []
+        for k in range(K):
+            o = recv[:, k].contiguous().view(N0, n1l, Nh)
+            C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(o), 0, float(scale)))
+            out.append(ComplexField(self, o))
+        return out
+
+    def _c2r_slab_many(self, cplxs, scale):
+        """several complex fields (given up by the caller) at once: one all-to-all"""
+        rt = self.rt
+        rt.sync_stream()
+        P, K = self.P, len(cplxs)
+        n0l, N1, N2 = self.rshape
+        N0, n1l, Nh = self.cshape
+        send = rt.empty((P, K, n0l, n1l, Nh), _C16)
+        for k, c in enumerate(cplxs):
+            C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(c.t), 1, 1.0))
+            send[:, k].copy_(c.t.view(P, n0l, n1l, Nh))
+        recv = self.comm.alltoall_blocks(send)            # [P (column block), K, n0l, n1l, Nh]
+        out = []
+        a = rt.empty((n0l, N1, Nh), _C16)
+        for k in range(K):
+            blk = recv[:, k].contiguous()
+            C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, n1l * Nh, _ptr(blk), _ptr(a)))
+            o = rt.empty(self.rshape)
+            C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
+            out.append(RealField(self, o))
+        return out
+
     def _c2r_slab(self, cplx, scale, consume=False):
         rt = self.rt
         P = self.P
@@ -1430,7 +1474,10 @@ def force_apl(pm, dx, q):
         fl = pm.readout3(F[0], F[1], F[2], xl)
         return layout.gather(fl), potk, ForceState(xl, layout, None, None, phi, scale, tabs)
     potk, g = pm.force_kspace(rhok, scale, tabs, want_p=True)
-    F = [pm._c2r(gd, 1.0, consume=True) for gd in g]   # g are temporaries of this call
+    if pm.P > 1:
+        F = pm._c2r_slab_many(g, 1.0)                  # three inverse transforms, one all-to-all
+    else:
+        F = [pm._c2r(gd, 1.0, consume=True) for gd in g]   # g are temporaries of this call
     fl = pm.readout3(F[0], F[1], F[2], xl)
     f = layout.gather(fl)
     if getattr(pm, 'force_recompute', False):
@@ -1470,7 +1517,7 @@ def force_vjp(pm, st, _f, _potk):
             potk_bar = potk_bar + pbar
         rhok_bar = pm._transfer(potk_bar, scale=st.scale, laplace=True)
     else:
-        gbar = [pm._r2c(Fd, 1.0) for Fd in Fbar]
+        gbar = pm._r2c_slab_many(Fbar, 1.0) if pm.P > 1 else [pm._r2c(Fd, 1.0) for Fd in Fbar]
         del Fbar
         out = rt.empty(pm.cshape, _C16)
         C.check(C.lib.vpm_force_kspace_vjp(
