@@ -92,6 +92,12 @@ def build_model(pm, q, stages):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock + clock-event reasons sampled DURING the timed region.
+
+    NVML is read in-process from a background thread (a few cheap driver queries every 100 ms);
+    an external ``nvidia-smi -lms`` loop is only the fallback -- its heavier polling perturbs
+    multi-process runs whose ranks spin on each other's flags.
+    """
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -100,20 +106,67 @@ class ClockSampler(object):
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, handle):
+        masks = [('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown),
+                 ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap)]
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                for name, m in masks:
+                    if bits & m:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
     def start(self):
+        mode = os.environ.get('VMAD_BENCH_CLOCKS', 'nvml')
+        if mode == 'off':
+            return
+        try:
+            if mode == 'smi':
+                raise RuntimeError
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            try:    # CUDA's device numbering may differ from NVML's (CUDA_VISIBLE_DEVICES)
+                import torch
+                uuid = "GPU-%s" % torch.cuda.get_device_properties(self.gpu_index).uuid
+                handle = nv.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)))
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.FIELDS,
-                 '--format=csv,noheader,nounits', '-lms', '200'],
+                 '--format=csv,noheader,nounits', '-lms', '500'],
                 stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(numpy.median(self.sm)), sm_max_mhz=float(max(self.mx)),
+                           reasons=sorted(self.reasons), samples=len(self.sm), source='nvml')
+            return out
         if self.proc is None:
             return out
         try:
@@ -141,7 +194,7 @@ class ClockSampler(object):
                     reasons.add(name)
         if sm:
             out.update(sm_mhz=float(numpy.median(sm)), sm_max_mhz=float(max(mx)),
-                       reasons=sorted(reasons), samples=len(sm))
+                       reasons=sorted(reasons), samples=len(sm), source='nvidia-smi')
         return out
 
 
@@ -294,6 +347,8 @@ def run_gpu(args):
         barrier()
         l0 = C.launch_count()
         total_ms = 0.0
+        per_step = []
+        mallocs = [torch.cuda.memory_stats().get('num_device_alloc', 0)]
         wall0 = time.perf_counter()
         for _ in range(steps):
             flush.fill_(1)
@@ -303,7 +358,13 @@ def run_gpu(args):
             fn()
             e1.record()
             e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
+            per_step.append(e0.elapsed_time(e1))
+            total_ms += per_step[-1]
+            mallocs.append(torch.cuda.memory_stats().get('num_device_alloc', 0))
+        if rank == 0:
+            print("[bench] %s per-step ms: %s; cudaMalloc calls per step: %s" % (
+                fn.__name__, ["%.2f" % v for v in per_step],
+                [b - a for a, b in zip(mallocs[:-1], mallocs[1:])]), file=sys.stderr)
         barrier()
         wall = time.perf_counter() - wall0
         launches = C.launch_count() - l0

@@ -20,6 +20,14 @@ model = bench.build_model(pm, q, numpy.linspace(0.1, 1.0, 11))
 def step():
     r = model.compute_with_vjp(init=dict(x=wn), v=dict(_dx=cot)); torch.cuda.synchronize(); return r
 for _ in range(3): step()
+import gc
+gc.collect(); gc.set_debug(gc.DEBUG_SAVEALL); step(); n = gc.collect()
+if rank == 0:
+    hist = collections.Counter(type(o).__name__ for o in gc.garbage)
+    print("cyclic garbage after one step: %d objects" % n, hist.most_common(12))
+    big = [o for o in gc.garbage if isinstance(o, torch.Tensor)]
+    print("tensors in garbage:", [(tuple(t.shape), t.dtype) for t in big][:20])
+gc.set_debug(0); gc.garbage.clear()
 dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     t0 = time.perf_counter(); step(); wall = time.perf_counter() - t0
@@ -39,4 +47,11 @@ if rank == 0:
             a = cpu[ev.name[:50]]; a[0] += 1; a[1] += ev.cpu_time
     for k, (n, v) in sorted(cpu.items(), key=lambda kv: -kv[1][1])[:12]:
         print("CPU %-48s n=%4d %9.3f ms" % (k, n, v / 1e3))
+import cProfile, pstats
+dist.barrier()
+pr = cProfile.Profile(); pr.enable(); step(); pr.disable()
+if rank == 0:
+    st = pstats.Stats(pr)
+    st.sort_stats('tottime').print_stats(30)
+    st.sort_stats('cumulative').print_stats(50)
 dist.barrier(); dist.destroy_process_group()

@@ -1,0 +1,39 @@
+"""step-by-step check of the peer exchange primitives (2+ GPUs, torchrun)"""
+import os, sys, ctypes
+import torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+local = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+from vmad_b200.dist import TorchComm, PeerExchange
+from vmad_b200 import _capi as C
+from vmad_b200.pm import runtime
+comm = TorchComm()
+P, rank = comm.size, comm.rank
+def say(*a):
+    print('[%d]' % rank, *a, flush=True)
+px = PeerExchange(comm, 1 << 20)
+say('opened', [hex(x) for x in px.buf_ptrs[0][:P]], [hex(x) for x in px.data_flag_ptrs[:P]])
+rt = runtime()
+e, b = px.begin()
+say('begin', e, b)
+px.put(e, torch.zeros(2, dtype=torch.float64, device='cuda'), 0, 0, 0, 0, 0); rt.synchronize(); say('empty put signalled')
+px.commit(e); rt.synchronize(); say('waited')
+px.release(e); rt.synchronize(); say('released')
+n = 1024
+src = torch.arange(P * n * 2, dtype=torch.float64, device='cuda') + 1000 * rank
+e, b = px.begin()
+px.put(e, src, 1, n, 0, n, rank * n); rt.synchronize(); say('put done')
+px.commit(e); rt.synchronize(); say('committed')
+out = torch.empty(P * n * 2, dtype=torch.float64, device='cuda')
+C.check(C.lib.vpm_axpby(rt.ctx, P * n * 2, ctypes.c_double(1.0), px.recv_ptr(b), ctypes.c_double(0.0), None, ctypes.c_double(0.0), ctypes.c_void_p(out.data_ptr())))
+rt.synchronize()
+px.release(e)
+exp = torch.cat([torch.arange(rank * n * 2, (rank + 1) * n * 2, dtype=torch.float64) + 1000 * s for s in range(P)])
+say('recv ok:', bool((out.cpu() == exp).all()))
+for it in range(20):
+    e, b = px.begin(); px.put(e, src, 1, n, 0, n, rank * n); px.commit(e); px.release(e)
+rt.synchronize(); say('20 rounds ok')
+px.close(); say('closed')
+dist.destroy_process_group()

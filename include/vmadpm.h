@@ -181,6 +181,49 @@ int vpm_fft_c2r_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, do
 /* in place, `inner` transforms of length n0 with stride `inner` */
 int vpm_fft_c2c_axis0(vpm_ctx* ctx, int64_t n0, int64_t inner, double* data, int inverse,
                       double scale);
+/* out-of-place variant (the input may be a peer-exchange receive buffer) */
+int vpm_fft_c2c_axis0_oop(vpm_ctx* ctx, int64_t n0, int64_t inner, const double* in, double* out,
+                          int inverse, double scale);
+/* Peer-memory transpose (replaces the MPI_Alltoall inside pfft): the pack kernel stores block d
+ * of the local array straight into rank d's receive buffer over NVLink,
+ *   peer_bufs[d][dst_off + i * inner + c] = src[i * s_row + d * s_dst + c]   (complex128),
+ * peer_bufs / peer_flags are device pointers valid in THIS process for every rank's receive
+ * buffer / flag array (CUDA IPC mappings; entry [me] is the local one).  vpm_peer_signal raises
+ * flags[slot] = epoch on every rank after the preceding kernels of the stream; vpm_peer_wait
+ * spins on the local flag array until all nranks entries reach epoch (traps after ~minutes). */
+/* receive areas live outside the caller's allocator so that they can be exported: alloc returns
+ * a zeroed device buffer and its 64-byte CUDA IPC handle; open maps another process's buffer. */
+int vpm_peer_alloc(vpm_ctx* ctx, int64_t nbytes, void** ptr, unsigned char* handle64);
+int vpm_peer_open(vpm_ctx* ctx, const unsigned char* handle64, void** ptr);
+int vpm_peer_close(vpm_ctx* ctx, void* ptr);
+int vpm_peer_free(vpm_ctx* ctx, void* ptr);
+/* optional flag traffic carried by a put launch (NULL: none): wait until my ack flags reached
+ * ack_epoch before storing (ack_flags NULL: no wait); after the stores raise data flag `slot` =
+ * epoch on every rank (peer_flags NULL: no signal; counter = zeroed device word owned by the
+ * caller, used to find the last thread block). */
+typedef struct vpm_peer_sync {
+    const int64_t* ack_flags;
+    int64_t ack_epoch;
+    const uint64_t* peer_flags;
+    int32_t slot;
+    int32_t reserved;
+    int64_t epoch;
+    uint32_t* counter;
+} vpm_peer_sync;
+int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
+                 int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
+                 const vpm_peer_sync* sync);
+/* Particle rows (Layout.exchange / Layout.gather across ranks; replaces pmesh's MPI_Alltoallv):
+ * pack and transfer in one kernel.  Position p of the routing order lies in segment d when
+ * seg_start[d] <= p < seg_start[d+1] (host array, nranks+1) and is stored to row
+ * dst_base[d] + p - seg_start[d] of peer d's receive area (ncomp doubles per row).
+ * idx_is_src=1: p = j, source row idx[j] (exchange); idx_is_src=0: p = idx[j], source row j
+ * (gather, idx = the local sort permutation). */
+int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
+                      const int32_t* idx, int idx_is_src, const int32_t* seg_start,
+                      const int64_t* dst_base, const uint64_t* peer_bufs, const vpm_peer_sync* sync);
+int vpm_peer_signal(vpm_ctx* ctx, int nranks, int slot, const uint64_t* peer_flags, int64_t epoch);
+int vpm_peer_wait(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int64_t epoch);
 /* dst[b][a][:] = src[a][b][:] for [a, b, c] complex128 */
 int vpm_swap_leading_axes(vpm_ctx* ctx, int64_t a, int64_t b, int64_t c, const double* src,
                           double* dst);

@@ -40,6 +40,11 @@ def main():
     send_counts = [r + 1 + d for d in range(P)]
     recv_counts = comm.alltoall_counts(send_counts)
     assert recv_counts == [s + 1 + r for s in range(P)]
+    # the whole count matrix (shared-memory board on one node; repeated rounds reuse the tables)
+    for it in range(5):
+        m = comm.allgather_counts([c + it for c in send_counts])
+        assert m.shape == (P, P) and m.tolist() == [[s + 1 + d + it for d in range(P)] for s in range(P)]
+    assert comm._board, "single-node ranks should use the host board"
     rows = torch.cat([torch.full((c, 3), 10.0 * r + d, dtype=torch.float64)
                       for d, c in enumerate(send_counts)])
     got = comm.alltoallv_rows(rows, send_counts, recv_counts)

@@ -5,7 +5,8 @@ context without a CUDA device, raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64,
+                    c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvmadpm.so')
@@ -42,6 +43,11 @@ _P = c_void_p  # device pointers travel as integers
 _I3 = c_int64 * 3
 
 # name -> (restype, argtypes); every name here must be declared in include/vmadpm.h
+class vpm_peer_sync(Structure):
+    _fields_ = [('ack_flags', c_void_p), ('ack_epoch', c_int64), ('peer_flags', POINTER(c_uint64)),
+                ('slot', c_int32), ('reserved', c_int32), ('epoch', c_int64), ('counter', c_void_p)]
+
+
 SIGNATURES = {
     'vpm_ctx_create': (c_int, [POINTER(c_void_p), c_int, c_void_p]),
     'vpm_ctx_destroy': (c_int, [c_void_p]),
@@ -79,6 +85,17 @@ SIGNATURES = {
     'vpm_fft_r2c_planes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P]),
     'vpm_fft_c2r_planes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P, c_double]),
     'vpm_fft_c2c_axis0': (c_int, [c_void_p, c_int64, c_int64, _P, c_int, c_double]),
+    'vpm_fft_c2c_axis0_oop': (c_int, [c_void_p, c_int64, c_int64, _P, _P, c_int, c_double]),
+    'vpm_peer_alloc': (c_int, [c_void_p, c_int64, POINTER(c_void_p), ctypes.c_char_p]),
+    'vpm_peer_open': (c_int, [c_void_p, ctypes.c_char_p, POINTER(c_void_p)]),
+    'vpm_peer_close': (c_int, [c_void_p, c_void_p]),
+    'vpm_peer_free': (c_int, [c_void_p, c_void_p]),
+    'vpm_peer_put': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, _P, POINTER(c_uint64), c_int64,
+                             POINTER(vpm_peer_sync)]),
+    'vpm_peer_put_rows': (c_int, [c_void_p, c_int, c_int64, c_int, _P, _P, c_int, POINTER(c_int32),
+                                  POINTER(c_int64), POINTER(c_uint64), POINTER(vpm_peer_sync)]),
+    'vpm_peer_signal': (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_int64]),
+    'vpm_peer_wait': (c_int, [c_void_p, c_int, _P, c_int64]),
     'vpm_swap_leading_axes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P]),
     'vpm_transfer': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double, c_int, _P, _P, _P,
                              _P, _P, _P, c_int]),

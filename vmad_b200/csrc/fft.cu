@@ -194,6 +194,24 @@ int vpm_fft_c2c_axis0(vpm_ctx* ctx, int64_t n0, int64_t inner, double* data, int
     VPM_API_END
 }
 
+int vpm_fft_c2c_axis0_oop(vpm_ctx* ctx, int64_t n0, int64_t inner, const double* in, double* out,
+                          int inverse, double scale) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && in && out && n0 >= 1 && inner >= 1, "bad argument");
+    VPM_REQUIRE(inner < (1LL << 31), "too many transforms for one plan");
+    cufftHandle h = slab_plan(ctx, 12, n0, inner, 0);
+    VPM_CUFFT(cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(const_cast<double*>(in)),
+                           reinterpret_cast<cufftDoubleComplex*>(out),
+                           inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (scale != 1.0) {
+        long long nd = 2LL * n0 * inner;
+        VPM_LAUNCH(k_scale_inplace, (unsigned)ceil_div(nd, EW_THREADS * EW_UNROLL), EW_THREADS, 0,
+                   ctx->stream, nd, scale, out);
+    }
+    VPM_API_END
+}
+
 int vpm_swap_leading_axes(vpm_ctx* ctx, int64_t a, int64_t b, int64_t c, const double* src,
                           double* dst) {
     VPM_API_BEGIN

@@ -24,6 +24,52 @@ def slab(n, size, rank):
     return rank * c, c
 
 
+class HostBoard(object):
+    """A P x (1 + width) int64 table in node-local shared memory (a file under /dev/shm mapped
+    by every rank) for the tiny host-side all-gathers of a decompose (per-peer particle
+    counts): a rank writes its row, then its sequence number; readers spin until all P sequence
+    numbers arrived.  Two tables alternate so that a fast rank can post the next round while a
+    slow one still reads.  Microseconds instead of a gloo collective; single node only (the
+    stores are ordered as written on x86; the sequence number is written last)."""
+
+    def __init__(self, comm, width=16):
+        import mmap
+        import os
+        self.P, self.rank, self.width = comm.size, comm.rank, width
+        nbytes = 8 * 2 * self.P * (1 + width)
+        name = [None]
+        if self.rank == 0:
+            path = '/dev/shm/vmad_b200_board_%d_%x' % (os.getpid(), int.from_bytes(os.urandom(4), 'little'))
+            with open(path, 'wb') as f:
+                f.write(b'\0' * nbytes)
+            name[0] = path
+        dist.broadcast_object_list(name, src=dist.get_global_rank(comm.group, 0) if comm.group else 0,
+                                   group=comm.group)
+        self._f = open(name[0], 'r+b')
+        self._map = mmap.mmap(self._f.fileno(), nbytes)
+        self.table = numpy.frombuffer(self._map, dtype='i8').reshape(2, self.P, 1 + width)
+        comm.barrier()
+        if self.rank == 0:
+            os.unlink(name[0])
+        self.seq = 0
+
+    def allgather(self, row):
+        row = numpy.asarray(row, dtype='i8')
+        n = len(row)
+        assert n <= self.width
+        self.seq += 1
+        t = self.table[self.seq & 1]
+        t[self.rank, 1:1 + n] = row
+        t[self.rank, 0] = self.seq
+        flags = t[:, 0]
+        spins = 0
+        while (flags < self.seq).any():
+            spins += 1
+            if spins > 200000000:
+                raise RuntimeError("host board: a peer did not post its counts")
+        return t[:, 1:1 + n].copy()
+
+
 class TorchComm(object):
     def __init__(self, group=None, device=None):
         if not dist.is_initialized():
@@ -51,6 +97,15 @@ class TorchComm(object):
         if isinstance(x, complex):
             r = self.allreduce(numpy.array([x.real, x.imag]))
             return complex(r[0], r[1])
+        # python scalars (particle counts, norms already reduced on the device) never touch the
+        # GPU on one node: all-gather the 8-byte words through the host board, sum in rank order
+        board = self._host_board() if isinstance(x, (int, float, numpy.integer, numpy.floating)) \
+            and not isinstance(x, bool) else None
+        if board:
+            if isinstance(x, (int, numpy.integer)):
+                return int(board.allgather([int(x)]).sum())
+            bits = numpy.array([float(x)], dtype='f8').view('i8')
+            return float(board.allgather(bits).view('f8').sum())
         if isinstance(x, (int, numpy.integer)) and not isinstance(x, bool):
             t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
             dist.all_reduce(t, group=self.group)
@@ -68,6 +123,37 @@ class TorchComm(object):
         dist.barrier(group=self.group)
 
     # -- exchanges --------------------------------------------------------------------------
+    def allgather_counts(self, row):
+        """every rank's ``row`` (a short list of ints): [P, len(row)] int64 on the host"""
+        row = [int(c) for c in row]
+        if self.size == 1:
+            return numpy.array([row], dtype='i8')
+        board = self._host_board()
+        if board and len(row) <= board.width:
+            return board.allgather(row)
+        group = self._cpu_group if self._cpu_group is not None else self.group
+        dev = 'cpu' if self._cpu_group is not None else self.device
+        mine = torch.tensor(row, dtype=torch.int64, device=dev)
+        out = [torch.empty_like(mine) for _ in range(self.size)]
+        dist.all_gather(out, mine, group=group)
+        return numpy.array([o.tolist() for o in out], dtype='i8')
+
+    def _host_board(self):
+        if getattr(self, '_board', None) is None:
+            self._board = False
+            if self.size > 1 and self._single_node():
+                try:
+                    self._board = HostBoard(self)
+                except OSError:
+                    self._board = False
+        return self._board
+
+    def _single_node(self):
+        import socket
+        names = [None] * self.size
+        dist.all_gather_object(names, socket.gethostname(), group=self.group)
+        return len(set(names)) == 1
+
     def alltoall_counts(self, send_counts):
         if self._cpu_group is not None:
             s = torch.tensor([int(c) for c in send_counts], dtype=torch.int64)
@@ -98,3 +184,128 @@ class TorchComm(object):
         out = torch.empty_like(s)
         dist.all_to_all_single(out, s, group=self.group)
         return torch.view_as_complex(out) if cplx else out
+
+
+class PeerExchange(object):
+    """Double-buffered receive areas + flag arrays of every rank, mapped into this process
+    through CUDA IPC, for the peer-memory transposes of the slab FFT and the particle exchange
+    (vmad_b200/csrc/peer.cu).  One per communicator; ``nbytes`` is the capacity of one
+    receive area.
+
+    Protocol for transfer number e (buffer e % 2): [put kernel: wait until every peer acknowledged
+    transfer e - 2 (it has finished reading the area about to be overwritten) -> store blocks into
+    the peers' areas -> last thread block raises data[me] = e everywhere] -> wait kernel: all data
+    flags here reached e -> consume -> release kernel: raise ack[me] = e everywhere.
+    """
+
+    def __init__(self, comm, nbytes):
+        import ctypes
+        from . import _capi as C
+        self.C = C
+        self.ctypes = ctypes
+        self.comm = comm
+        self.P, self.rank = comm.size, comm.rank
+        if self.P > 8:
+            raise ValueError("peer exchange supports up to 8 ranks")
+        self.nbytes = int(nbytes)
+        ctx = self._ctx()
+        self._own, self._opened = [], []
+        mine = []
+        for size in (self.nbytes, self.nbytes, 8 * (2 * self.P + 1)):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            C.check(C.lib.vpm_peer_alloc(ctx, size, ctypes.byref(ptr), handle))
+            self._own.append(ptr.value)
+            mine.append(handle.raw)
+        C.check(C.lib.vpm_sync(ctx))
+        everyone = [None] * self.P
+        dist.all_gather_object(everyone, mine, group=comm.group)
+        ptrs = [[0] * self.P for _ in range(3)]
+        for d in range(self.P):
+            for k in range(3):
+                if d == self.rank:
+                    ptrs[k][d] = self._own[k]
+                else:
+                    ptr = ctypes.c_void_p()
+                    C.check(C.lib.vpm_peer_open(ctx, everyone[d][k], ctypes.byref(ptr)))
+                    self._opened.append(ptr.value)
+                    ptrs[k][d] = ptr.value
+        A = ctypes.c_uint64 * 8
+        pad = lambda v: A(*(list(v) + [0] * (8 - len(v))))
+        self.buf_ptrs = [pad(ptrs[0]), pad(ptrs[1])]
+        self.data_flag_ptrs = pad(ptrs[2])
+        self.my_bufs = [self._own[0], self._own[1]]
+        self.my_flags = self._own[2]
+        self.epoch = 0
+        comm.barrier()
+
+    def close(self):
+        C = self.C
+        if self._own:
+            ctx = self._ctx()
+            C.lib.vpm_sync(ctx)
+            self.comm.barrier()
+            for p in self._opened:
+                C.lib.vpm_peer_close(ctx, p)
+            self.comm.barrier()
+            for p in self._own:
+                C.lib.vpm_peer_free(ctx, p)
+            self._own, self._opened = [], []
+
+    def _ctx(self):
+        from .pm import runtime
+        rt = runtime()
+        rt.sync_stream()
+        return rt.ctx
+
+    def begin(self):
+        self.epoch += 1
+        return self.epoch, self.epoch % 2
+
+    def _sync(self, e, last):
+        """flag traffic riding on a put launch: wait for the acks of transfer e - 2 (the previous
+        use of this receive area) before storing; the last put of a transfer raises my data flag"""
+        C, ct = self.C, self.ctypes
+        sy = C.vpm_peer_sync()
+        sy.ack_flags = (self.my_flags + 8 * self.P) if e > 2 else None
+        sy.ack_epoch = e - 2
+        if last:
+            sy.peer_flags = ct.cast(self.data_flag_ptrs, ct.POINTER(ct.c_uint64))
+            sy.slot = self.rank
+            sy.epoch = e
+            sy.counter = self.my_flags + 8 * 2 * self.P
+        return ct.byref(sy)
+
+    def put(self, e, src, rows, inner, s_row, s_dst, dst_off, last=True):
+        C, ct = self.C, self.ctypes
+        C.check(C.lib.vpm_peer_put(self._ctx(), self.P, int(rows), int(inner), int(s_row), int(s_dst),
+                                   ct.c_void_p(src.data_ptr()), self.buf_ptrs[e % 2], int(dst_off),
+                                   self._sync(e, last)))
+
+    def put_rows(self, e, src, idx, n, ncomp, idx_is_src, seg_start, dst_base):
+        """particle rows to their destination ranks (vpm_peer_put_rows)"""
+        C, ct = self.C, self.ctypes
+        P = self.P
+        seg = (ct.c_int32 * (P + 1))(*[int(v) for v in seg_start])
+        base = (ct.c_int64 * P)(*[int(v) for v in dst_base])
+        C.check(C.lib.vpm_peer_put_rows(self._ctx(), P, int(n), int(ncomp), ct.c_void_p(src.data_ptr()),
+                                        ct.c_void_p(idx.data_ptr()), int(idx_is_src), seg, base,
+                                        self.buf_ptrs[e % 2], self._sync(e, True)))
+
+    def ensure(self, nbytes):
+        """collective: grow the receive areas (every rank must call with the same value)"""
+        if nbytes > self.nbytes:
+            self.close()
+            self.__init__(self.comm, int(1.25 * nbytes))
+
+    def commit(self, e):
+        C, ct = self.C, self.ctypes
+        C.check(C.lib.vpm_peer_wait(self._ctx(), self.P, ct.c_void_p(self.my_flags), e))
+
+    def recv_ptr(self, b, offset_elems=0):
+        """device pointer (as c_void_p) to complex element ``offset_elems`` of my receive area b"""
+        return self.ctypes.c_void_p(self.my_bufs[b] + 16 * int(offset_elems))
+
+    def release(self, e):
+        C = self.C
+        C.check(C.lib.vpm_peer_signal(self._ctx(), self.P, self.P + self.rank, self.data_flag_ptrs, e))

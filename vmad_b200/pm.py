@@ -712,11 +712,21 @@ class DistLayout(object):
         start = (ctypes.c_int32 * (P + 1))()
         C.check(C.lib.vpm_route_build(rt.ctx, ctypes.byref(pm._mesh), P, _ptr(x3), n,
                                       _ptr(send_idx), send_idx.shape[0], start))
+        self.send_start = [int(start[d]) for d in range(P + 1)]
         self.send_counts = [start[d + 1] - start[d] for d in range(P)]
         self.nsend = int(start[P])
         self.send_idx = send_idx[:self.nsend].clone()  # drop the over-allocation
-        self.recv_counts = comm.alltoall_counts(self.send_counts)
+        # counts[s][d] = rows rank s sends to rank d: every rank sees the whole matrix, so the
+        # row offsets inside every peer's receive area are known without a second exchange
+        counts = comm.allgather_counts(self.send_counts)
+        me = pm.rank
+        self.recv_counts = [int(c) for c in counts[:, me]]
         self.nrecv = int(sum(self.recv_counts))
+        self.recv_start = [0] + [int(v) for v in numpy.cumsum(self.recv_counts)]
+        self._fwd_base = [int(counts[:me, d].sum()) for d in range(P)]     # my rows in d's area
+        self._back_base = [int(counts[s, :me].sum()) for s in range(P)]    # my rows in s's send order
+        self._max_rows = int(max(counts.sum(axis=0).max(), counts.sum(axis=1).max()))
+        self.px = pm._peer()
         # positions travel once here; the local cell sort is built on what arrived
         xr = self._forward(x3)
         local = pm._decompose_local(DeviceArray(xr), keep_index)
@@ -731,14 +741,32 @@ class DistLayout(object):
         if self._src is not None:
             xs = rt.empty(tuple(xr.shape))
             C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(xr), _ptr(self.indices), self.nrecv, 3, _ptr(xs)))
-            self._xs = DeviceArray(xs, cellindex=self)
+            self._xs = xs       # the bare tensor: a DeviceArray tagged with this layout would form a
+                                # reference cycle and keep ~50 MB alive until the cyclic GC runs
         else:
             self._xs = None
+
+    def _peer_forward(self, t, ncomp):
+        """rows -> the peers' receive areas (pack fused with the NVLink stores); returns the
+        transfer handle (epoch, buffer) -- the caller consumes my receive area, then releases"""
+        px = self.px
+        px.ensure(8 * self._max_rows * ncomp)
+        e, b = px.begin()
+        px.put_rows(e, t, self.send_idx, self.nsend, ncomp, 1, self.send_start, self._fwd_base)
+        px.commit(e)
+        return e, b
 
     def _forward(self, t):
         """rows of a local [oldlength, ...] tensor -> rows received here, ordered by source"""
         rt = self.pm.rt
         ncomp = _ncomp(t)
+        if self.px is not None:
+            e, b = self._peer_forward(t, ncomp)
+            out = rt.empty((self.nrecv,) + tuple(t.shape[1:]))
+            C.check(C.lib.vpm_axpby(rt.ctx, self.nrecv * ncomp, 1.0, self.px.recv_ptr(b), 0.0, None, 0.0,
+                                    _ptr(out)))
+            self.px.release(e)
+            return out
         send = rt.empty((self.nsend,) + tuple(t.shape[1:]))
         C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.send_idx), self.nsend, ncomp, _ptr(send)))
         return self.pm.comm.alltoallv_rows(send, self.send_counts, self.recv_counts)
@@ -747,9 +775,19 @@ class DistLayout(object):
         """fastpm.py:289,301,308"""
         data = asdevice(data)
         if self._xs is not None and self._src is not None and self._src() is data:
-            return self._xs
+            return DeviceArray(self._xs, cellindex=self)
         rt = self.pm.rt
         rt.sync_stream()
+        if self.px is not None:
+            # put -> (flags) -> the local sort gathers straight out of the receive area
+            t = data.t
+            ncomp = _ncomp(t)
+            e, b = self._peer_forward(t, ncomp)
+            out = rt.empty((self.nrecv,) + tuple(t.shape[1:]))
+            C.check(C.lib.vpm_take_rows(rt.ctx, self.px.recv_ptr(b), _ptr(self.indices), self.nrecv, ncomp,
+                                        _ptr(out)))
+            self.px.release(e)
+            return DeviceArray(out, cellindex=self)
         recv = self._forward(data.t)
         ncomp = _ncomp(recv)
         out = rt.empty(tuple(recv.shape))
@@ -763,6 +801,19 @@ class DistLayout(object):
         rt.sync_stream()
         t = data.t
         ncomp = _ncomp(t)
+        if self.px is not None:
+            # sorted row k sits at receive position indices[k]; it goes back to its source rank,
+            # into the row it had in that rank's send order, and is summed into its home row there
+            px = self.px
+            px.ensure(8 * self._max_rows * ncomp)
+            e, b = px.begin()
+            px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base)
+            px.commit(e)
+            out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
+            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), self.nsend, ncomp,
+                                               _ptr(out)))
+            px.release(e)
+            return DeviceArray(out)
         unsorted = rt.empty(tuple(t.shape))
         C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), self.nrecv, ncomp, _ptr(unsorted)))
         back = self.pm.comm.alltoallv_rows(unsorted, self.recv_counts, self.send_counts)
@@ -1243,6 +1294,28 @@ class ParticleMesh(object):
         C.check(fn(rt.ctx, C.i3(self._n3), _ptr(cplx.t), _ptr(o), float(scale)))
         return RealField(self, o)
 
+    def _peer(self):
+        """peer-memory exchange for the FFT transposes (None: fall back to NCCL all-to-all)"""
+        if getattr(self, '_peer_x', False) is False:
+            self._peer_x = None
+            import os
+            if os.environ.get('VMAD_B200_TRANSPOSE', 'peer') == 'peer' and 1 < self.P <= 8 \
+                    and getattr(self.comm, 'device', None) is not None and self.comm.device.type == 'cuda':
+                from .dist import PeerExchange
+                slab_bytes = 16 * int(numpy.prod(self.cshape))
+                px, why = None, None
+                try:
+                    px = PeerExchange(self.comm, 3 * slab_bytes)
+                except Exception as e:  # no peer access / IPC on this rank
+                    why = e
+                # all ranks or none: a mixed choice would deadlock
+                if self.comm.allreduce(int(px is not None)) == self.P:
+                    self._peer_x = px
+                else:
+                    import warnings
+                    warnings.warn("peer-memory exchange unavailable (%r); using NCCL all-to-all" % (why,))
+        return self._peer_x
+
     # slab-decomposed transforms: local cuFFT, one all-to-all transpose each -------------------
     def _r2c_slab(self, real, scale):
         """[n0l, N1, N2] real -> [N0, n1l, Nh] complex: 2-D D2Z over the local planes, pack,
@@ -1253,6 +1326,18 @@ class ParticleMesh(object):
         N0, n1l, Nh = self.cshape
         a = rt.empty((n0l, N1, Nh), _C16)
         C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
+        px = self._peer()
+        if px is not None:
+            # pack + transfer in one kernel: block d is stored straight into rank d's buffer
+            inner = n1l * Nh
+            e, b = px.begin()
+            px.put(e, a, n0l, inner, P * inner, inner, self.rank * n0l * inner)
+            px.commit(e)
+            o = rt.empty(self.cshape, _C16)
+            C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, px.recv_ptr(b),
+                                                _ptr(o), 0, float(scale)))
+            px.release(e)
+            return ComplexField(self, o)
         # [n0l, P, n1l*Nh] -> [P, n0l, n1l*Nh]: block d goes to rank d
         send = rt.empty((P, n0l, n1l, Nh), _C16)
         C.check(C.lib.vpm_swap_leading_axes(rt.ctx, n0l, P, n1l * Nh, _ptr(a), _ptr(send)))
@@ -1267,6 +1352,24 @@ class ParticleMesh(object):
         P, K = self.P, len(reals)
         n0l, N1, N2 = self.rshape
         N0, n1l, Nh = self.cshape
+        px = self._peer()
+        if px is not None and K <= 3:
+            inner = n1l * Nh
+            slab = N0 * inner
+            e, b = px.begin()
+            for k, real in enumerate(reals):
+                a = rt.empty((n0l, N1, Nh), _C16)
+                C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
+                px.put(e, a, n0l, inner, P * inner, inner, k * slab + self.rank * n0l * inner, last=(k == K - 1))
+            px.commit(e)
+            out = []
+            for k in range(K):
+                o = rt.empty(self.cshape, _C16)
+                C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, px.recv_ptr(b, k * slab),
+                                                    _ptr(o), 0, float(scale)))
+                out.append(ComplexField(self, o))
+            px.release(e)
+            return out
         send = rt.empty((P, K, n0l, n1l, Nh), _C16)
         a = rt.empty((n0l, N1, Nh), _C16)
         tmp = rt.empty((P, n0l, n1l, Nh), _C16)
@@ -1289,6 +1392,26 @@ class ParticleMesh(object):
         P, K = self.P, len(cplxs)
         n0l, N1, N2 = self.rshape
         N0, n1l, Nh = self.cshape
+        px = self._peer()
+        if px is not None and K <= 3:
+            inner = n1l * Nh
+            blk = n0l * inner
+            slab = P * blk
+            e, b = px.begin()
+            for k, c in enumerate(cplxs):
+                C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, inner, _ptr(c.t), 1, 1.0))
+                px.put(e, c.t, 1, blk, 0, blk, k * slab + self.rank * blk, last=(k == K - 1))
+            px.commit(e)
+            out = []
+            for k in range(K):
+                a = rt.empty((n0l, N1, Nh), _C16)
+                C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner,
+                                                    px.recv_ptr(b, k * slab), _ptr(a)))
+                o = rt.empty(self.rshape)
+                C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
+                out.append(RealField(self, o))
+            px.release(e)
+            return out
         send = rt.empty((P, K, n0l, n1l, Nh), _C16)
         for k, c in enumerate(cplxs):
             C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(c.t), 1, 1.0))
@@ -1309,6 +1432,21 @@ class ParticleMesh(object):
         P = self.P
         n0l, N1, N2 = self.rshape
         N0, n1l, Nh = self.cshape
+        px = self._peer()
+        if px is not None:
+            inner = n1l * Nh
+            blk = n0l * inner
+            work = rt.empty(self.cshape, _C16)
+            C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, _ptr(cplx.t), _ptr(work), 1, 1.0))
+            e, b = px.begin()
+            px.put(e, work, 1, blk, 0, blk, self.rank * blk)
+            px.commit(e)
+            a = rt.empty((n0l, N1, Nh), _C16)
+            C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner, px.recv_ptr(b), _ptr(a)))
+            px.release(e)
+            o = rt.empty(self.rshape)
+            C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
+            return RealField(self, o)
         work = cplx.t if consume else cplx.t.clone()    # operators must not mutate their inputs
         C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(work), 1, 1.0))
         recv = self.comm.alltoall_blocks(work.view(P, n0l, n1l, Nh))   # [P (column block), n0l, n1l, Nh]
