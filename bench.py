@@ -16,12 +16,13 @@ kernels are launched on, an L2 flush (256 MiB write) between steps outside the e
 barrier + synchronize on both sides, max over ranks.
 
 N > 1 (torchrun, one rank per GPU): ONE problem, slab-decomposed over the N GPUs (mesh planes
-and the particles on them per rank, NCCL all-to-all for the particle exchange and the FFT
-transposes; vmad_b200/dist.py).  Weak scaling: the global mesh grows with N so that every GPU
+and the particles on them per rank; particle exchange and FFT transposes are stores into the
+peers' memory over NVLink -- vmad_b200/csrc/peer.cu -- with NCCL all-to-all as the fallback).  Weak scaling: the global mesh grows with N so that every GPU
 keeps nmesh^3 cells and particles ([nmesh*a, nmesh*b, nmesh*c] with a*b*c = N, cell size
 fixed); ``value`` = N * nsteps / seconds, i.e. steps/s in units of the N = 1 problem.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -344,6 +345,11 @@ def run_gpu(args):
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        # the graph, plans and layout caches built during warm-up are long-lived: move them out
+        # of the cyclic collector's generations so that a full collection (tens of ms of host
+        # time, which lock-stepped ranks all wait for) does not land inside the timed steps
+        gc.collect()
+        gc.freeze()
         barrier()
         l0 = C.launch_count()
         total_ms = 0.0
@@ -468,9 +474,11 @@ def run_gpu(args):
         "config": {"workload": workload_name(N, args.nsteps), "nmesh": N, "nsteps": args.nsteps,
                    "global_mesh": dims, "np": int(numpy.prod(dims)),
                    "boxsize": [100.0 * n / 32 for n in dims],
-                   "parallelism": ("slab decomposition over %d GPUs (mesh axis 0; NCCL all-to-all "
+                   "parallelism": ("slab decomposition over %d GPUs (mesh axis 0; %s "
                                    "for particle exchange and FFT transposes), %d^3 cells per GPU"
-                                   % (world, N)) if world > 1 else "1 gpu",
+                                   % (world, "peer-memory stores over NVLink (CUDA IPC)"
+                                      if pm._peer() is not None else "NCCL all-to-all", N))
+                   if world > 1 else "1 gpu",
                    "l2": "256 MiB flush write between timed steps",
                    "step": "one Model.compute_with_vjp = %d FastPM steps forward + reverse" % args.nsteps},
         "clocks": clocks,

@@ -79,9 +79,22 @@ int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t 
 /* dst[perm[i], :] = src[i, :]  for a permutation (Layout.gather on one rank) */
 int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
                      int ncomp, double* dst);
-/* dst[idx[i], :] += src[i, :]  (gather with duplicated copies; dst pre-zeroed) */
+/* dst[idx[i], :] += src[i, :]  (gather with duplicated copies; dst pre-zeroed).  Rows with a
+ * negative index are skipped (vpm_scatter_rows too). */
 int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n,
                          int ncomp, double* dst);
+/* dst[i, :] = idx[i] >= 0 ? a[idx[i], :] : b[-1 - idx[i], :]   (Layout.exchange across ranks: rows
+ * that stay on this rank are read from the home array a, the rest from the receive area b) */
+int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
+                   int ncomp, double* dst);
+/* Index composition for a cross-rank layout.  sorted_to_recv = the local sort permutation over the
+ * receive order; the self segment is rows [recv_lo, recv_hi) of the receive order and rows
+ * [send_lo, send_lo + recv_hi - recv_lo) of the send order.
+ *   take[k]   = send_idx[send_lo + r - recv_lo] if r = sorted_to_recv[k] is a self row, else -1 - r
+ *   remote[j] = send_idx[j] outside the self segment, -1 inside */
+int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv,
+                      const int32_t* send_idx, int64_t nsend, int64_t recv_lo, int64_t recv_hi,
+                      int64_t send_lo, int32_t* take, int32_t* remote);
 
 /* Routing for the slab decomposition over `nranks` ranks (rank r owns planes
  * [r n0/nranks, (r+1) n0/nranks)): a particle is sent to the owner of its floor plane and, when
@@ -218,9 +231,10 @@ int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t 
  * seg_start[d] <= p < seg_start[d+1] (host array, nranks+1) and is stored to row
  * dst_base[d] + p - seg_start[d] of peer d's receive area (ncomp doubles per row).
  * idx_is_src=1: p = j, source row idx[j] (exchange); idx_is_src=0: p = idx[j], source row j
- * (gather, idx = the local sort permutation). */
+ * (gather, idx = the local sort permutation).  Rows of segment skip_seg (-1: none) are not
+ * transferred: rows staying on this rank bypass the receive area (vpm_route_compose). */
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
-                      const int32_t* idx, int idx_is_src, const int32_t* seg_start,
+                      const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
                       const int64_t* dst_base, const uint64_t* peer_bufs, const vpm_peer_sync* sync);
 int vpm_peer_signal(vpm_ctx* ctx, int nranks, int slot, const uint64_t* peer_flags, int64_t epoch);
 int vpm_peer_wait(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int64_t epoch);

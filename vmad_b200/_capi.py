@@ -65,6 +65,8 @@ SIGNATURES = {
     'vpm_take_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
+    'vpm_take_rows2': (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, _P]),
+    'vpm_route_compose': (c_int, [c_void_p, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
     'vpm_paint_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
     'vpm_paint_sorted_col': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int, c_int, c_int64, _P, _P]),
     'vpm_paint_set_algorithm': (c_int, [c_int]),
@@ -92,7 +94,7 @@ SIGNATURES = {
     'vpm_peer_free': (c_int, [c_void_p, c_void_p]),
     'vpm_peer_put': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, _P, POINTER(c_uint64), c_int64,
                              POINTER(vpm_peer_sync)]),
-    'vpm_peer_put_rows': (c_int, [c_void_p, c_int, c_int64, c_int, _P, _P, c_int, POINTER(c_int32),
+    'vpm_peer_put_rows': (c_int, [c_void_p, c_int, c_int64, c_int, _P, _P, c_int, c_int, POINTER(c_int32),
                                   POINTER(c_int64), POINTER(c_uint64), POINTER(vpm_peer_sync)]),
     'vpm_peer_signal': (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_int64]),
     'vpm_peer_wait': (c_int, [c_void_p, c_int, _P, c_int64]),

@@ -265,10 +265,44 @@ __global__ void k_scatter_rows(const double* __restrict__ src, const int* __rest
     if (e >= n * nc) return;
     long long i = e / nc;
     int c = (int)(e - i * nc);
+    const int p = perm[i];
+    if (p < 0) return;              // masked row (lives on another rank / arrives separately)
     double v = src[e];
-    double* d = dst + (long long)perm[i] * nc + c;
+    double* d = dst + (long long)p * nc + c;
     if (ADD) atomicAdd(d, v);
     else *d = v;
+}
+
+// out[k] = idx[k] >= 0 ? a[idx[k]] : b[-1 - idx[k]]   (rows of NC doubles)
+template <int NC>
+__global__ void k_take_rows2(const double* __restrict__ a, const double* __restrict__ b,
+                             const int* __restrict__ idx, long long n, int ncomp,
+                             double* __restrict__ dst) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int nc = NC > 0 ? NC : ncomp;
+    if (e >= n * nc) return;
+    long long i = e / nc;
+    int c = (int)(e - i * nc);
+    const int p = idx[i];
+    dst[e] = p >= 0 ? a[(long long)p * nc + c] : b[(long long)(-1 - p) * nc + c];
+}
+
+// Index composition for a cross-rank layout: rows that stay on this rank skip the receive area.
+//   take[k]   = the home row sorted slot k reads directly, or -1 - (receive-area row)
+//   remote[j] = send_idx[j] for rows sent to other ranks, -1 inside the self segment
+__global__ void k_route_compose(const int* __restrict__ sorted_to_recv, int nrecv,
+                                const int* __restrict__ send_idx, int nsend, int recv_lo,
+                                int recv_hi, int send_lo, int* __restrict__ take,
+                                int* __restrict__ remote) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nrecv) {
+        const int r = sorted_to_recv[t];
+        take[t] = (r >= recv_lo && r < recv_hi) ? send_idx[send_lo + (r - recv_lo)] : -1 - r;
+    }
+    if (t < nsend) {
+        const int send_hi = send_lo + (recv_hi - recv_lo);
+        remote[t] = (t >= send_lo && t < send_hi) ? -1 : send_idx[t];
+    }
 }
 
 // ---- routing of particles to slab owners (stable multisplit) -----------------------------
@@ -472,6 +506,38 @@ int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64
         if (ncomp == 1) VPM_LAUNCH((k_scatter_rows<1, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
         else if (ncomp == 3) VPM_LAUNCH((k_scatter_rows<3, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
         else VPM_LAUNCH((k_scatter_rows<0, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
+    }
+    VPM_API_END
+}
+
+int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
+                   int ncomp, double* dst) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx, "ctx is NULL");
+    VPM_REQUIRE(ncomp >= 1, "ncomp must be >= 1");
+    if (n > 0) {
+        VPM_REQUIRE(a && b && idx && dst, "NULL array");
+        unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
+        if (ncomp == 1) VPM_LAUNCH(k_take_rows2<1>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows2<3>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, dst);
+        else VPM_LAUNCH(k_take_rows2<0>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, dst);
+    }
+    VPM_API_END
+}
+
+int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv,
+                      const int32_t* send_idx, int64_t nsend, int64_t recv_lo, int64_t recv_hi,
+                      int64_t send_lo, int32_t* take, int32_t* remote) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx, "ctx is NULL");
+    VPM_REQUIRE(nrecv >= 0 && nsend >= 0 && nrecv < (1LL << 31) && nsend < (1LL << 31), "bad counts");
+    const long long n = std::max<long long>(nrecv, nsend);
+    if (n > 0) {
+        VPM_REQUIRE((nrecv == 0 || (sorted_to_recv && take)) && (nsend == 0 || (send_idx && remote)),
+                    "NULL array");
+        VPM_LAUNCH(k_route_compose, (unsigned)ceil_div(n, 256), 256, 0, ctx->stream, sorted_to_recv,
+                   (int)nrecv, send_idx, (int)nsend, (int)recv_lo, (int)recv_hi, (int)send_lo, take,
+                   remote);
     }
     VPM_API_END
 }

@@ -52,7 +52,7 @@ __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned done = atomicAdd(sy.counter, 1u);
-        if (done == gridDim.x - 1) {
+        if (done == gridDim.x * gridDim.y * gridDim.z - 1) {
             *sy.counter = 0;
             __threadfence_system();
             for (int d = 0; d < P; ++d) {
@@ -65,20 +65,19 @@ __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
 }
 
 // dst_d[dst_off + i * inner + c] = src[i * s_row + d * s_dst + c]   for every peer d
+// grid = (chunks of a row, rows, peers): no index divisions, 16-byte coalesced loads / stores
 __global__ void __launch_bounds__(256)
 k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_dst,
            const double2* __restrict__ src, PeerPtrs dst, long long dst_off, PeerSync sy) {
     peer_acquire(P, sy);
-    const long long per = rows * inner;
-    const long long total = per * P;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int d = (int)(e / per);
-        const long long r = e - (long long)d * per;
-        const long long i = r / inner;
-        const long long c = r - i * inner;
-        double2* out = reinterpret_cast<double2*>(dst.p[d]) + dst_off;
-        out[r] = src[i * s_row + d * s_dst + c];
+    const int d = blockIdx.z;
+    double2* __restrict__ out = reinterpret_cast<double2*>(dst.p[d]) + dst_off;
+    for (long long i = blockIdx.y; i < rows; i += gridDim.y) {
+        const double2* __restrict__ in = src + i * s_row + d * s_dst;
+        double2* __restrict__ o = out + i * inner;
+        for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < inner;
+             c += (long long)gridDim.x * blockDim.x)
+            o[c] = in[c];
     }
     peer_publish(P, sy);
 }
@@ -96,8 +95,8 @@ struct PeerSegs {
 template <int NC>
 __global__ void __launch_bounds__(256)
 k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
-                const int* __restrict__ idx, int idx_is_src, PeerSegs seg, PeerPtrs dst,
-                PeerSync sy) {
+                const int* __restrict__ idx, int idx_is_src, int skip_seg, PeerSegs seg,
+                PeerPtrs dst, PeerSync sy) {
     peer_acquire(P, sy);
     const int nc = NC > 0 ? NC : ncomp;
     const long long total = (long long)n * nc;
@@ -111,6 +110,7 @@ k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
         int d = 0;
 #pragma unroll
         for (int t = 1; t < 8; ++t) d += (t < P && p >= seg.start[t]) ? 1 : 0;
+        if (d == skip_seg) continue;
         double* out = reinterpret_cast<double*>(dst.p[d]);
         out[(seg.base[d] + (p - seg.start[d])) * nc + c] = src[(long long)row * nc + c];
     }
@@ -219,8 +219,11 @@ int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t 
     VPM_REQUIRE(ctx && src && peer_bufs && nranks >= 1 && nranks <= 8, "bad argument");
     const long long total = (long long)rows * inner * nranks;
     if (total > 0 || sync) {   // an empty put still carries the flag traffic
-        unsigned grid = (unsigned)std::max<long long>(
-            1, std::min<long long>(ceil_div(total, 256), 16LL * ctx->sm_count));
+        // about 16 CTAs per SM in flight: rows along y (capped), the rest along x
+        const long long gy = std::max<long long>(1, std::min<long long>(rows, 1024));
+        const long long want = std::max<long long>(1, 16LL * ctx->sm_count / (gy * nranks));
+        const long long gx = std::max<long long>(1, std::min<long long>(ceil_div(inner, 256), want));
+        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nranks);
         VPM_LAUNCH(k_peer_put, grid, 256, 0, ctx->stream, nranks, (long long)rows, (long long)inner,
                    (long long)s_row, (long long)s_dst, reinterpret_cast<const double2*>(src),
                    make_ptrs(nranks, peer_bufs), (long long)dst_off, make_sync(nranks, sync));
@@ -229,7 +232,7 @@ int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t 
 }
 
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
-                      const int32_t* idx, int idx_is_src, const int32_t* seg_start,
+                      const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
                       const int64_t* dst_base, const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx && seg_start && dst_base && peer_bufs && nranks >= 1 && nranks <= 8,
@@ -247,13 +250,13 @@ int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const doub
             1, std::min<long long>(ceil_div(total, 256), 16LL * ctx->sm_count));
         if (ncomp == 1)
             VPM_LAUNCH(k_peer_put_rows<1>, grid, 256, 0, ctx->stream, nranks, (int)n, ncomp, src, idx,
-                       idx_is_src, seg, dst, sy);
+                       idx_is_src, skip_seg, seg, dst, sy);
         else if (ncomp == 3)
             VPM_LAUNCH(k_peer_put_rows<3>, grid, 256, 0, ctx->stream, nranks, (int)n, ncomp, src, idx,
-                       idx_is_src, seg, dst, sy);
+                       idx_is_src, skip_seg, seg, dst, sy);
         else
             VPM_LAUNCH(k_peer_put_rows<0>, grid, 256, 0, ctx->stream, nranks, (int)n, ncomp, src, idx,
-                       idx_is_src, seg, dst, sy);
+                       idx_is_src, skip_seg, seg, dst, sy);
     }
     VPM_API_END
 }

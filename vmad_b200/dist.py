@@ -282,14 +282,14 @@ class PeerExchange(object):
                                    ct.c_void_p(src.data_ptr()), self.buf_ptrs[e % 2], int(dst_off),
                                    self._sync(e, last)))
 
-    def put_rows(self, e, src, idx, n, ncomp, idx_is_src, seg_start, dst_base):
+    def put_rows(self, e, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1):
         """particle rows to their destination ranks (vpm_peer_put_rows)"""
         C, ct = self.C, self.ctypes
         P = self.P
         seg = (ct.c_int32 * (P + 1))(*[int(v) for v in seg_start])
         base = (ct.c_int64 * P)(*[int(v) for v in dst_base])
         C.check(C.lib.vpm_peer_put_rows(self._ctx(), P, int(n), int(ncomp), ct.c_void_p(src.data_ptr()),
-                                        ct.c_void_p(idx.data_ptr()), int(idx_is_src), seg, base,
+                                        ct.c_void_p(idx.data_ptr()), int(idx_is_src), int(skip), seg, base,
                                         self.buf_ptrs[e % 2], self._sync(e, True)))
 
     def ensure(self, nbytes):

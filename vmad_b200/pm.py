@@ -745,14 +745,22 @@ class DistLayout(object):
                                 # reference cycle and keep ~50 MB alive until the cyclic GC runs
         else:
             self._xs = None
+        if self.px is not None:
+            # rows that stay on this rank (nearly all of them) bypass the receive area: composed
+            # indices let exchange / gather touch the home array directly
+            self.take_idx = rt.empty((max(self.nrecv, 1),), torch.int32)
+            self.send_remote = rt.empty((max(self.nsend, 1),), torch.int32)
+            C.check(C.lib.vpm_route_compose(rt.ctx, _ptr(self.indices), self.nrecv, _ptr(self.send_idx),
+                                            self.nsend, self.recv_start[me], self.recv_start[me + 1],
+                                            self.send_start[me], _ptr(self.take_idx), _ptr(self.send_remote)))
 
-    def _peer_forward(self, t, ncomp):
+    def _peer_forward(self, t, ncomp, skip=-1):
         """rows -> the peers' receive areas (pack fused with the NVLink stores); returns the
         transfer handle (epoch, buffer) -- the caller consumes my receive area, then releases"""
         px = self.px
         px.ensure(8 * self._max_rows * ncomp)
         e, b = px.begin()
-        px.put_rows(e, t, self.send_idx, self.nsend, ncomp, 1, self.send_start, self._fwd_base)
+        px.put_rows(e, t, self.send_idx, self.nsend, ncomp, 1, self.send_start, self._fwd_base, skip)
         px.commit(e)
         return e, b
 
@@ -782,10 +790,10 @@ class DistLayout(object):
             # put -> (flags) -> the local sort gathers straight out of the receive area
             t = data.t
             ncomp = _ncomp(t)
-            e, b = self._peer_forward(t, ncomp)
+            e, b = self._peer_forward(t, ncomp, skip=self.pm.rank)
             out = rt.empty((self.nrecv,) + tuple(t.shape[1:]))
-            C.check(C.lib.vpm_take_rows(rt.ctx, self.px.recv_ptr(b), _ptr(self.indices), self.nrecv, ncomp,
-                                        _ptr(out)))
+            C.check(C.lib.vpm_take_rows2(rt.ctx, _ptr(t), self.px.recv_ptr(b), _ptr(self.take_idx), self.nrecv,
+                                         ncomp, _ptr(out)))
             self.px.release(e)
             return DeviceArray(out, cellindex=self)
         recv = self._forward(data.t)
@@ -807,10 +815,13 @@ class DistLayout(object):
             px = self.px
             px.ensure(8 * self._max_rows * ncomp)
             e, b = px.begin()
-            px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base)
-            px.commit(e)
+            px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base,
+                        skip=self.pm.rank)
+            # rows that never left: straight into their home rows while the peers' rows travel
             out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
-            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), self.nsend, ncomp,
+            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(t), _ptr(self.take_idx), self.nrecv, ncomp, _ptr(out)))
+            px.commit(e)
+            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_remote), self.nsend, ncomp,
                                                _ptr(out)))
             px.release(e)
             return DeviceArray(out)
