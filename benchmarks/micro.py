@@ -73,8 +73,15 @@ def main():
         rec('paint_sorted', lambda: pm.paint(xs, 1.0), 24.0 * n + 8.0 * Nc)
         pmmod.set_paint_algorithm('tile')
         rec('paint_tile(determ.)', lambda: pm.paint(xs, 1.0), 24.0 * n + 8.0 * Nc)
+        m3 = DeviceArray(torch.rand((n, 3), generator=g, device='cuda', dtype=torch.float64))
+        m3s = lay.exchange(m3)
+        pmmod.set_paint_algorithm('gather')
+        rec('paint_gather', lambda: pm.paint(xs, 1.0), 24.0 * n + 8.0 * Nc)
+        rec('paint_gather_mass', lambda: pm.paint(xs, ms), 32.0 * n + 8.0 * Nc)
+        rec('paint_gather_cols3', lambda: pm.paint_cols3(xs, m3s), 48.0 * n + 24.0 * Nc)
         pmmod.set_paint_algorithm('aggregated')
-        rec('paint_agg_unsorted', lambda: pm.paint(x, 1.0, layout=None) if False else pm._paint_any_order(x), 24.0 * n + 8.0 * Nc)
+        rec('paint_agg_cols3', lambda: pm.paint_cols3(xs, m3s), 48.0 * n + 24.0 * Nc)
+        rec('paint_agg_unsorted', lambda: pm._paint_any_order(x), 24.0 * n + 8.0 * Nc)
         rec('paint_rows(ablation)', lambda: pm.paint_rows(xs, 1.0), 24.0 * n + 8.0 * Nc)
         rec('paint_sorted_mass', lambda: pm.paint(xs, ms), 32.0 * n + 8.0 * Nc)
         rec('paint_atomic', lambda: pm.paint_atomic(x, 1.0), 24.0 * n + 8.0 * Nc)

@@ -109,9 +109,10 @@ int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double
  *      mesh half of RealField.readout_vjp) ---------------------------------- */
 /* Particles sorted by cell key (xs = x[perm]); fills every local cell (no prior zero fill
  * needed).  mass: per-particle array (sorted like xs) or NULL -> mass0.
- * Two algorithms (vpm_paint_set_algorithm): 0 (default) warp-aggregated fp64 reductions --
- * fastest, summation order not fixed (results agree to rounding); 1 shared-memory tiles --
- * no atomics, every cell written exactly once, run-to-run bit-identical. */
+ * Algorithms (vpm_paint_set_algorithm): 0 warp-aggregated fp64 reductions into L2 -- needs no
+ * cell_start (may be NULL), summation order not fixed (results agree to rounding); 1 shared-memory
+ * tiles (ablation); 2 block gather -- no atomics, no zero fill, every cell written exactly once,
+ * run-to-run bit-identical; needs cell_start and n[2] <= 512, otherwise falls back to 0. */
 int vpm_paint_set_algorithm(int algo);
 int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                      const double* mass, double mass0, int64_t np,
@@ -122,6 +123,12 @@ int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
 int vpm_paint_sorted_col(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                          const double* mass2d, int ncomp, int col, int64_t np,
                          const int32_t* cell_start, double* out);
+/* the three columns of an interleaved [np, ncomp] array into three meshes, out + c *
+ * out_colstride (c = 0, 1, 2), in one pass over the particles when the block-gather algorithm is
+ * selected (positions and weights are shared); otherwise three aggregated paints. */
+int vpm_paint_sorted_cols3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
+                           const double* mass2d, int ncomp, int64_t np,
+                           const int32_t* cell_start, double* out, int64_t out_colstride);
 /* Tuning knob (benchmarks only): output tile extents of the sorted paint kernel in cells;
  * 0 keeps the default. */
 int vpm_paint_set_tile(int tx, int ty, int tz);

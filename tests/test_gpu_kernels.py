@@ -74,7 +74,7 @@ def test_layout_crowded_cells(oracle_pm, device_pm):
     assert numpy.array_equal(dlay.indices.cpu().numpy(), olay.indices)
 
 
-@pytest.fixture(params=['aggregated', 'tile'])
+@pytest.fixture(params=['aggregated', 'tile', 'gather'])
 def paint_algorithm(request):
     from vmad_b200 import pm as dpm_mod
     dpm_mod.set_paint_algorithm(request.param)
@@ -102,11 +102,18 @@ def test_paint_parity(oracle_pm, device_pm, paint_algorithm, Nmesh, BoxSize, n):
     # atomic baseline kernel and the row-gather ablation kernel
     assert rel_l2(dpm.paint_atomic(x, m).numpy(), ref) < TOL
     assert rel_l2(dpm.paint_rows(x, m).numpy(), ref) < TOL
-    if paint_algorithm == 'tile':
-        # the tile kernel has a fixed summation order: run-to-run bit-identical
+    if paint_algorithm in ('tile', 'gather'):
+        # fixed summation order: run-to-run bit-identical
         a = dpm.paint(x, m).numpy()
         b = dpm.paint(x, m).numpy()
         assert numpy.array_equal(a, b)
+    # three columns in one pass (reverse sweep of the force operator)
+    if len(Nmesh) == 3:
+        m3 = rng.standard_normal((len(x), 3))
+        xs, ms = lay.exchange(x), lay.exchange(m3)
+        got3 = dpm.paint_cols3(xs, ms)
+        for d in range(3):
+            assert rel_l2(got3[d].numpy(), opm.paint(x, m3[:, d]).value) < TOL
 
 
 def test_paint_uniform_grid_is_one(device_pm):

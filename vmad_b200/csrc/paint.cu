@@ -514,6 +514,142 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Block gather (no atomics, no zero fill, fixed summation order).
+//
+// A CTA produces a 2 x 2 x n2 block of OUTPUT cells: planes (l0, l0+1), rows (j0, j0+1), every z;
+// thread t owns the column z = t.  Those cells receive mass from the 3 x 3 source rows
+// (l0-1..l0+1) x (j0-1..j0+1): a particle of source row (ra, rb) feeds output (oa, ob) when
+// ra - oa and rb - ob are in {0, 1} taken from the low side, with weight f (upper neighbour) or
+// 1 - f (own cell) per axis -- 16 (row, output) pairs for 9 row visits, so a particle is
+// visited 2.25 times instead of the 4 of the row formulation, its position is decoded once per
+// visit for up to four outputs, and the loads of a warp are the consecutive particles of 32
+// consecutive cells (coalesced).  Cell z feeds output z (1 - f2) and z + 1 (f2): the second sum
+// moves one lane up by shuffle and across warps / the periodic wrap through shared memory.
+// The cell ranges of all nine rows and the first particle of each are requested before any
+// arithmetic (one load latency per phase instead of nine).  NCOL = 3 paints the three columns
+// of an interleaved [np, mstride] mass array into three meshes sharing positions and weights
+// (reverse sweep of the force operator).
+// -------------------------------------------------------------------------------------------
+template <int NCOL, int MASSKIND>
+__global__ void __launch_bounds__(512)
+k_paint_gather(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, double mass0,
+               int mstride, const int* __restrict__ cs, double* __restrict__ out,
+               long long colstride) {
+    extern __shared__ double sF[];  // [warps][NCOL * 4]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int z = threadIdx.x;
+    const bool zv = z < g.n2;
+    const int l0 = 2 * blockIdx.y, j0 = 2 * blockIdx.x;
+    int sp[3], jy[3];
+    bool vx[3] = {true, true, false}, vy[3] = {true, true, false};
+    if (g.ghost) {
+        sp[0] = l0; sp[1] = l0 + 1; sp[2] = l0 + 2;     // keys count from the lower ghost plane
+    } else {
+        sp[0] = l0 == 0 ? g.n0 - 1 : l0 - 1; sp[1] = l0; sp[2] = l0 + 1;
+    }
+    vx[2] = l0 + 1 < g.nloc0;
+    jy[0] = j0 == 0 ? g.n1 - 1 : j0 - 1; jy[1] = j0; jy[2] = j0 + 1;
+    vy[2] = j0 + 1 < g.n1;
+
+    // phase A: the nine cell ranges; phase B: the first particle of each
+    int lo[9], hi[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int ra = r / 3, rb = r % 3;
+        lo[r] = hi[r] = 0;
+        if (zv && vx[ra] && vy[rb]) {
+            const int key = (sp[ra] * g.n1 + jy[rb]) * g.n2 + z;
+            lo[r] = __ldg(cs + key);
+            hi[r] = __ldg(cs + key + 1);
+        }
+    }
+    double X0[9], X1[9], X2[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        X0[r] = X1[r] = X2[r] = 0.0;
+        if (lo[r] < hi[r]) {
+            const double* xp = xs + 3LL * lo[r];
+            X0[r] = __ldg(xp + 0); X1[r] = __ldg(xp + 1); X2[r] = __ldg(xp + 2);
+        }
+    }
+    double E[NCOL][2][2], F[NCOL][2][2];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { E[c][q >> 1][q & 1] = 0.0; F[c][q >> 1][q & 1] = 0.0; }
+
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int ra = r / 3, rb = r % 3;
+        double x0 = X0[r], x1 = X1[r], x2 = X2[r];
+        for (int k = lo[r]; k < hi[r];) {
+            double u;
+            u = __dmul_rn(x0, g.s0); const double f0 = u - floor(u);
+            u = __dmul_rn(x1, g.s1); const double f1 = u - floor(u);
+            u = __dmul_rn(x2, g.s2); const double f2 = u - floor(u);
+            const double e0 = 1.0 - f0, e1 = 1.0 - f1, e2 = 1.0 - f2;
+            double m[NCOL];
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c)
+                m[c] = MASSKIND == 2 ? __ldg(mass + (long long)k * mstride + c)
+                                     : (MASSKIND == 1 ? mass0 : 1.0);
+            ++k;
+            if (k < hi[r]) {   // next particle of the cell: requested before the arithmetic
+                const double* xp = xs + 3LL * k;
+                x0 = __ldg(xp + 0); x1 = __ldg(xp + 1); x2 = __ldg(xp + 2);
+            }
+            // source row ra feeds output plane oa = ra (as the lower cell: weight f0) and
+            // oa = ra - 1 (as its own cell: weight 1 - f0); same along y
+#pragma unroll
+            for (int oa = 0; oa < 2; ++oa) {
+                if (ra != oa && ra != oa + 1) continue;
+                const double wx = (ra == oa) ? f0 : e0;
+#pragma unroll
+                for (int ob = 0; ob < 2; ++ob) {
+                    if (rb != ob && rb != ob + 1) continue;
+                    const double wxy = wx * ((rb == ob) ? f1 : e1);
+#pragma unroll
+                    for (int c = 0; c < NCOL; ++c) {
+                        const double wm = MASSKIND == 0 ? wxy : wxy * m[c];
+                        E[c][oa][ob] += wm * e2;
+                        F[c][oa][ob] += wm * f2;
+                    }
+                }
+            }
+        }
+    }
+    // the f2 sums belong to the next cell along z: one lane up, across warps through shared
+    // memory, periodic wrap from the last cell of the row
+    const int lastlane = (warp == nwarp - 1) ? ((g.n2 - 1) & 31) : 31;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double f = F[c][q >> 1][q & 1];
+            if (lane == lastlane) sF[warp * (NCOL * 4) + c * 4 + q] = f;
+            F[c][q >> 1][q & 1] = __shfl_up_sync(0xffffffffu, f, 1);
+        }
+    __syncthreads();
+    if (!zv) return;
+    const int pw = warp == 0 ? nwarp - 1 : warp - 1;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+        for (int oa = 0; oa < 2; ++oa) {
+            if (oa == 1 && !vx[2]) continue;
+#pragma unroll
+            for (int ob = 0; ob < 2; ++ob) {
+                if (ob == 1 && !vy[2]) continue;
+                const double left = lane == 0 ? sF[pw * (NCOL * 4) + c * 4 + oa * 2 + ob] : F[c][oa][ob];
+                out[c * colstride + (long long)(l0 + oa) * g.stride0 + (long long)(j0 + ob) * g.stride1 + z] =
+                    E[c][oa][ob] + left;
+            }
+        }
+}
+
 // Baseline: thread per particle, 8 fp64 reductions into global memory (RED.E.ADD.F64).
 template <bool HAS_MASS>
 __global__ void k_paint_atomic(Geo g, const double* __restrict__ x, const double* __restrict__ mass,
@@ -678,16 +814,42 @@ static void launch_paint_tile(vpm_ctx* ctx, const Geo& g, const double* xs, cons
 #undef VPM_TILE
 }
 
+// the block-gather kernel needs the cell offsets, one thread per z cell in a CTA, and either a
+// ghost-keyed slab or the whole periodic mesh
+static bool gather_ok(const Geo& g, const int32_t* cell_start) {
+    return cell_start != nullptr && g.n2 <= 512 && (g.ghost || (g.start0 == 0 && g.nloc0 == g.n0));
+}
+
+template <int NCOL>
+static void launch_paint_gather(vpm_ctx* ctx, const Geo& g, const double* xs, const double* mass,
+                                double mass0, int mstride, const int32_t* cell_start, double* out,
+                                long long colstride) {
+    if (g.nloc0 == 0) return;
+    const int warps = (g.n2 + 31) / 32;
+    dim3 grid((unsigned)((g.n1 + 1) / 2), (unsigned)((g.nloc0 + 1) / 2));
+    VPM_REQUIRE(grid.y <= 65535, "too many planes for one launch");
+    const size_t smem = (size_t)warps * NCOL * 4 * sizeof(double);
+    const int mk = mass ? 2 : (mass0 == 1.0 ? 0 : 1);
+    cudaStream_t st = ctx->stream;
+#define VPM_GATHER(MK_) VPM_LAUNCH((k_paint_gather<NCOL, MK_>), grid, warps * 32, smem, st, g, xs, mass, mass0, mstride, cell_start, out, colstride)
+    if (mk == 2) VPM_GATHER(2);
+    else if (mk == 1) VPM_GATHER(1);
+    else VPM_GATHER(0);
+#undef VPM_GATHER
+}
+
 extern "C" {
 
 int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass,
                      double mass0, int64_t np, const int32_t* cell_start, double* out) {
     VPM_API_BEGIN
-    VPM_REQUIRE(ctx && out && cell_start, "NULL argument");
+    VPM_REQUIRE(ctx && out && (cell_start || g_paint_algo != 1), "NULL argument");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
     Geo g = make_geo(mesh);
-    if (g_paint_algo == 0) launch_paint_agg<0>(ctx, g, xs, mass, mass0, nullptr, nullptr, np, out);
-    else launch_paint_tile<0>(ctx, g, xs, mass, mass0, nullptr, nullptr, cell_start, out);
+    if (g_paint_algo == 2 && gather_ok(g, cell_start))
+        launch_paint_gather<1>(ctx, g, xs, mass, mass0, 1, cell_start, out, 0);
+    else if (g_paint_algo == 1) launch_paint_tile<0>(ctx, g, xs, mass, mass0, nullptr, nullptr, cell_start, out);
+    else launch_paint_agg<0>(ctx, g, xs, mass, mass0, nullptr, nullptr, np, out);
     VPM_API_END
 }
 
@@ -720,13 +882,34 @@ int vpm_paint_sorted_col(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, c
     VPM_REQUIRE(ncomp >= 1 && col >= 0 && col < ncomp, "bad column");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
     Geo g = make_geo(mesh);
-    launch_paint_agg<0>(ctx, g, xs, mass2d + col, 1.0, nullptr, nullptr, np, out, ncomp);
+    if (g_paint_algo == 2 && gather_ok(g, cell_start))
+        launch_paint_gather<1>(ctx, g, xs, mass2d + col, 1.0, ncomp, cell_start, out, 0);
+    else
+        launch_paint_agg<0>(ctx, g, xs, mass2d + col, 1.0, nullptr, nullptr, np, out, ncomp);
+    VPM_API_END
+}
+
+int vpm_paint_sorted_cols3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass2d,
+                           int ncomp, int64_t np, const int32_t* cell_start, double* out,
+                           int64_t out_colstride) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && out && mass2d, "NULL argument");
+    VPM_REQUIRE(ncomp >= 3, "need at least three columns");
+    VPM_REQUIRE(np == 0 || xs, "xs is NULL");
+    Geo g = make_geo(mesh);
+    if (g_paint_algo == 2 && gather_ok(g, cell_start)) {
+        launch_paint_gather<3>(ctx, g, xs, mass2d, 1.0, ncomp, cell_start, out, out_colstride);
+    } else {
+        for (int c = 0; c < 3; ++c)
+            launch_paint_agg<0>(ctx, g, xs, mass2d + c, 1.0, nullptr, nullptr, np, out + c * out_colstride,
+                                ncomp);
+    }
     VPM_API_END
 }
 
 int vpm_paint_set_algorithm(int algo) {
     VPM_API_BEGIN
-    VPM_REQUIRE(algo == 0 || algo == 1, "paint algorithm must be 0 (aggregated) or 1 (tile)");
+    VPM_REQUIRE(algo >= 0 && algo <= 2, "paint algorithm must be 0 (aggregated), 1 (tile) or 2 (block gather)");
     g_paint_algo = algo;
     VPM_API_END
 }

@@ -70,6 +70,7 @@ def _ptr(t):
 
 
 _KEEP_CELL_INDEX = False
+_PAINT_ALGO = 0
 
 # bench.py sets this to a list to time every paint launch of a step in place (CUDA events on
 # the launching stream); entries are (start_event, end_event, algorithmic_bytes)
@@ -98,13 +99,16 @@ class _timed_paint(object):
 
 
 def set_paint_algorithm(name):
-    """'aggregated' (default): warp-aggregated fp64 reductions, fastest; 'tile': shared-memory
-    tiles, no atomics, run-to-run bit-identical meshes (needs the per-cell offsets, so layouts
-    keep them while it is selected)."""
-    global _KEEP_CELL_INDEX
-    algo = {'aggregated': 0, 'tile': 1}[name]
+    """'aggregated': warp-aggregated fp64 reductions into L2 (needs only the sorted positions;
+    summation order not fixed); 'gather': block gather -- no atomics, no zero fill, every cell
+    written once, run-to-run bit-identical; 'tile': the shared-memory tile formulation
+    (ablation).  'gather' and 'tile' need the per-cell offsets, so layouts keep them while one
+    of the two is selected."""
+    global _KEEP_CELL_INDEX, _PAINT_ALGO
+    algo = {'aggregated': 0, 'tile': 1, 'gather': 2}[name]
     C.check(C.lib.vpm_paint_set_algorithm(algo))
-    _KEEP_CELL_INDEX = (algo == 1)
+    _KEEP_CELL_INDEX = (algo != 0)
+    _PAINT_ALGO = algo
 
 
 def _ncomp(t):
@@ -1093,6 +1097,31 @@ class ParticleMesh(object):
                                            x3.shape[0], _ptr(cs), _ptr(o)))
         return RealField(self, o)
 
+    def paint_cols3(self, xs, mass2d, layout=None):
+        """three paints of the columns of a sorted [n, 3] array (the mesh half of the vjp of the
+        three force readouts, fastpm.py:256 x3) -> three RealFields; one pass over the particles
+        with the block-gather algorithm"""
+        rt = self.rt
+        lay, x3, (mass2d,), _ = self._sorted(xs, layout, (mass2d,))
+        rt.sync_stream()
+        n = x3.shape[0]
+        mt = mass2d.t
+        if _PAINT_ALGO == 2:
+            m3 = rt.empty((3,) + tuple(self.rshape))
+            with _timed_paint(48.0 * n + 8.0 * m3.numel()):
+                C.check(C.lib.vpm_paint_sorted_cols3(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(mt), 3, n,
+                                                     _ptr(self._cell_start_of(lay, x3)), _ptr(m3),
+                                                     m3[0].numel()))
+            return [RealField(self, m3[d]) for d in range(3)]
+        out = []
+        for d in range(3):
+            m = rt.empty(self.rshape)
+            with _timed_paint(32.0 * n + 8.0 * m.numel()):
+                C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(mt), 3, d, n,
+                                                   _ptr(self._cell_start_of(lay, x3)), _ptr(m)))
+            out.append(RealField(self, m))
+        return out
+
     def _cell_start_of(self, lay, x3):
         """cell offsets for the kernels that need them (tile / row paint); rebuilt from the
         sorted positions when the layout did not keep them"""
@@ -1659,14 +1688,7 @@ def force_vjp(pm, st, _f, _potk):
     else:
         _fl = lay.exchange(asdevice(_f))
     # readout.vjp (mesh half) x3: three paints of the columns of the force cotangent
-    Fbar = []
-    rt.sync_stream()
-    for d in range(3):
-        m = rt.empty(pm.rshape)
-        with _timed_paint(32.0 * n + 8.0 * m.numel()):
-            C.check(C.lib.vpm_paint_sorted_col(rt.ctx, ctypes.byref(pm._mesh), _ptr(xl.t), _ptr(_fl.t),
-                                               3, d, n, _ptr(pm._dummy_cs()), _ptr(m)))
-        Fbar.append(RealField(pm, m))
+    Fbar = pm.paint_cols3(xl, _fl)
     pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
     if st.phi is not None:
         # adjoint of the stencil, then ONE forward FFT (c2r.vjp of the un-normalised inverse)
