@@ -152,9 +152,11 @@ int vpm_paint_atomic(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x,
 int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const double* x,
                 int64_t np, double* value);
 /* three fields at once, written interleaved [np, 3] (fuses linalg.stack,
- * fastpm.py:349,437) */
+ * fastpm.py:349,437).  out_row (may be NULL): row p is stored at row out_row[p] -- Layout.gather
+ * of a one-rank layout (its slot -> home row permutation) fused into the store. */
 int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
-                 const double* f2, const double* x, int64_t np, double* value3);
+                 const double* f2, const double* x, int64_t np, const int32_t* out_row,
+                 double* value3);
 /* value[p] (optional, may be NULL) and grad[p, d] = w_p * sum_c field[c] dW/dx_d,
  * w_p = weight[p] or weight0 when weight == NULL. */
 int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
@@ -162,10 +164,10 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
                      double* value, double* grad);
 /* grad[p, :] = sum_d w3[p, d] * gradreadout(f_d, x_p) + gradreadout(r, x_p): the particle half
  * of the reverse sweep of the fused force operator (readout.vjp x3 + paint.vjp, fastpm.py:229,
- * 256) in one pass over the particles. */
+ * 256) in one pass over the particles; out_row as in vpm_readout3. */
 int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                       const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, double* grad);
+                      int64_t np, const int32_t* out_row, double* grad);
 /* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);
  * either term may be absent (NULL). */
 int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,

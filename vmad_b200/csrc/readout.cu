@@ -108,16 +108,18 @@ k_readout(Geo g, const double* __restrict__ field, const double* __restrict__ x,
 __global__ void __launch_bounds__(256)
 k_readout3(Geo g, const double* __restrict__ fa, const double* __restrict__ fb,
            const double* __restrict__ fc, const double* __restrict__ x, long long np,
-           double* __restrict__ value3) {
+           const int* __restrict__ out_row, double* __restrict__ value3) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= np) return;
     Stencil s = make_stencil(g, x, p);
     const double a = gather_value(s, fa);
     const double b = gather_value(s, fb);
     const double c = gather_value(s, fc);
-    value3[3 * p + 0] = a;
-    value3[3 * p + 1] = b;
-    value3[3 * p + 2] = c;
+    // out_row: the layout's slot -> home row map (Layout.gather fused into the readout)
+    const long long o = out_row ? (long long)__ldg(out_row + p) : p;
+    value3[3 * o + 0] = a;
+    value3[3 * o + 1] = b;
+    value3[3 * o + 2] = c;
 }
 
 template <bool HAS_W, bool WANT_VALUE>
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256)
 k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__ F1,
                 const double* __restrict__ F2, const double* __restrict__ R,
                 const double* __restrict__ x, const double* __restrict__ w3, long long np,
-                double* __restrict__ grad) {
+                const int* __restrict__ out_row, double* __restrict__ grad) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= np) return;
     Stencil s = make_stencil(g, x, p);
@@ -178,9 +180,10 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
         a1 += u0 * ((w0 * d1) * w2a) + u1 * ((w0 * d1) * w2b);
         a2 += (u1 - u0) * (wxy * g.s2);
     }
-    grad[3 * p + 0] = a0;
-    grad[3 * p + 1] = a1;
-    grad[3 * p + 2] = a2;
+    const long long o = out_row ? (long long)__ldg(out_row + p) : p;
+    grad[3 * o + 0] = a0;
+    grad[3 * o + 1] = a1;
+    grad[3 * o + 2] = a2;
 }
 
 template <bool HAS_FDOT, bool HAS_XDOT>
@@ -222,14 +225,15 @@ int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const d
 }
 
 int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
-                 const double* f2, const double* x, int64_t np, double* value3) {
+                 const double* f2, const double* x, int64_t np, const int32_t* out_row,
+                 double* value3) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
         VPM_REQUIRE(f0 && f1 && f2 && x && value3, "NULL array");
         VPM_LAUNCH(k_readout3, (unsigned)ceil_div(np, 256), 256, 0, ctx->stream, g, f0, f1, f2, x,
-                   (long long)np, value3);
+                   (long long)np, out_row, value3);
     }
     VPM_API_END
 }
@@ -254,14 +258,14 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, co
 
 int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                       const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, double* grad) {
+                      int64_t np, const int32_t* out_row, double* grad) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
         VPM_REQUIRE(f0 && f1 && f2 && r && x && w3 && grad, "NULL array");
         VPM_LAUNCH(k_readout_grad4, (unsigned)ceil_div(np, 256), 256, 0, ctx->stream, g, f0, f1, f2, r,
-                   x, w3, (long long)np, grad);
+                   x, w3, (long long)np, out_row, grad);
     }
     VPM_API_END
 }

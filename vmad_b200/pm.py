@@ -1252,17 +1252,24 @@ class ParticleMesh(object):
             r = layout.gather(r)
         return r
 
-    def readout3(self, f0, f1, f2, pos):
-        """Three fields read at once into ``[Np, 3]`` (readout x3 + linalg.stack fused)."""
+    def readout3(self, f0, f1, f2, pos, gather=None):
+        """Three fields read at once into ``[Np, 3]`` (readout x3 + linalg.stack fused).
+        ``gather``: a one-rank Layout whose ``gather`` is fused into the store (rows land in
+        home order); a cross-rank layout gathers afterwards."""
         rt = self.rt
         pos = asdevice(pos)
         _, x3 = self._pos3(pos)
         rt.sync_stream()
         n = x3.shape[0]
+        fused = isinstance(gather, Layout) and gather.newlength == n == gather.oldlength
         val = rt.empty((n, 3))
         C.check(C.lib.vpm_readout3(rt.ctx, ctypes.byref(self._mesh), _ptr(f0.t), _ptr(f1.t),
-                                   _ptr(f2.t), _ptr(x3), n, _ptr(val)))
-        return DeviceArray(val, cellindex=pos._cellindex)
+                                   _ptr(f2.t), _ptr(x3), n, _ptr(gather.indices) if fused else None,
+                                   _ptr(val)))
+        if fused:
+            return DeviceArray(val)
+        r = DeviceArray(val, cellindex=pos._cellindex)
+        return gather.gather(r) if gather is not None else r
 
     def _readout_vjp(self, field, pos, v, layout):
         rt = self.rt
@@ -1662,15 +1669,14 @@ def force_apl(pm, dx, q):
         potk = pm._transfer(rhok, scale=scale, laplace=True)
         phi = pm._c2r(potk, 1.0)                               # potk is an output: preserved
         F = _fd4(pm, phi)
-        fl = pm.readout3(F[0], F[1], F[2], xl)
-        return layout.gather(fl), potk, ForceState(xl, layout, None, None, phi, scale, tabs)
+        f = pm.readout3(F[0], F[1], F[2], xl, gather=layout)
+        return f, potk, ForceState(xl, layout, None, None, phi, scale, tabs)
     potk, g = pm.force_kspace(rhok, scale, tabs, want_p=True)
     if pm.P > 1:
         F = pm._c2r_slab_many(g, 1.0)                  # three inverse transforms, one all-to-all
     else:
         F = [pm._c2r(gd, 1.0, consume=True) for gd in g]   # g are temporaries of this call
-    fl = pm.readout3(F[0], F[1], F[2], xl)
-    f = layout.gather(fl)
+    f = pm.readout3(F[0], F[1], F[2], xl, gather=layout)
     if getattr(pm, 'force_recompute', False):
         # trade 3 inverse FFTs in the reverse sweep for 2/3 of the mesh memory on the tape
         return f, potk, ForceState(xl, layout, None, potk, None, scale, tabs)
@@ -1716,10 +1722,11 @@ def force_vjp(pm, st, _f, _potk):
     F = st.meshes(pm)
     rt.sync_stream()
     g = rt.empty((n, 3))
+    fused = isinstance(lay, Layout) and lay.newlength == n == lay.oldlength   # gather in the store
     C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
                                     _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
-                                    _ptr(g)))
-    return lay.gather(DeviceArray(g))
+                                    _ptr(lay.indices) if fused else None, _ptr(g)))
+    return DeviceArray(g) if fused else lay.gather(DeviceArray(g))
 
 
 def force_jvp(pm, st, dx_):
