@@ -35,5 +35,22 @@ say('recv ok:', bool((out.cpu() == exp).all()))
 for it in range(20):
     e, b = px.begin(); px.put(e, src, 1, n, 0, n, rank * n); px.commit(e); px.release(e)
 rt.synchronize(); say('20 rounds ok')
+# ---- timing: full protocol per transfer, slab-transpose sized payload vs empty payload
+import time
+px.ensure(64 << 20)
+rows, inner = 128, (128 // P) * 65
+big = torch.randn(rows * P * inner * 2, dtype=torch.float64, device='cuda')
+def loop(nrows, iters=100):
+    comm.barrier(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        e, b = px.begin(); px.put(e, big, nrows, inner, P * inner, inner, rank * rows * inner); px.commit(e); px.release(e)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+for nrows in (0, rows, 0, rows):
+    t = loop(nrows)
+    say('transfer of %5.1f MB per rank (%.1f MB to each peer): %.1f us per put+wait+release' % (
+        nrows * P * inner * 16 / 1e6, nrows * inner * 16 / 1e6, t))
 px.close(); say('closed')
 dist.destroy_process_group()

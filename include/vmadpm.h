@@ -219,16 +219,27 @@ int vpm_peer_alloc(vpm_ctx* ctx, int64_t nbytes, void** ptr, unsigned char* hand
 int vpm_peer_open(vpm_ctx* ctx, const unsigned char* handle64, void** ptr);
 int vpm_peer_close(vpm_ctx* ctx, void* ptr);
 int vpm_peer_free(vpm_ctx* ctx, void* ptr);
-/* optional flag traffic carried by a put launch (NULL: none): wait until my ack flags reached
- * ack_epoch before storing (ack_flags NULL: no wait); after the stores raise data flag `slot` =
- * epoch on every rank (peer_flags NULL: no signal; counter = zeroed device word owned by the
- * caller, used to find the last thread block). */
+/* Flag protocol carried by a put launch (NULL or mode 0: none).  Every rank owns a flag array of
+ * 2 * nranks int64: [0, nranks) data flags (slot s = "rank s delivered transfer e"), [nranks,
+ * 2 nranks) ack flags (slot s = "rank s finished reading its receive area of transfer e").
+ * peer_flags[d] = rank d's array as mapped here, my_flags = my own.  mode bits, for transfer
+ * `epoch` (1, 2, ... in lock step on all ranks; receive area epoch % 2):
+ *   RAISE_ACK  at kernel start raise ack[rank] = epoch - 1 on every rank (the consumer of the
+ *              previous transfer precedes this launch on the stream);
+ *   WAIT_ACK   before storing wait until my ack flags reached epoch - 2;
+ *   SIGNAL     after the stores the last thread block raises data[rank] = epoch on every rank
+ *              (counter = zeroed device word owned by the caller);
+ *   WAIT_DATA  ... and then waits until my data flags reached epoch, so that the kernel's
+ *              completion means "my receive area is complete". */
+#define VPM_PEER_RAISE_ACK 1
+#define VPM_PEER_WAIT_ACK 2
+#define VPM_PEER_SIGNAL 4
+#define VPM_PEER_WAIT_DATA 8
 typedef struct vpm_peer_sync {
-    const int64_t* ack_flags;
-    int64_t ack_epoch;
     const uint64_t* peer_flags;
-    int32_t slot;
-    int32_t reserved;
+    const int64_t* my_flags;
+    int32_t rank;
+    int32_t mode;
     int64_t epoch;
     uint32_t* counter;
 } vpm_peer_sync;

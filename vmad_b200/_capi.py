@@ -44,8 +44,11 @@ _I3 = c_int64 * 3
 
 # name -> (restype, argtypes); every name here must be declared in include/vmadpm.h
 class vpm_peer_sync(Structure):
-    _fields_ = [('ack_flags', c_void_p), ('ack_epoch', c_int64), ('peer_flags', POINTER(c_uint64)),
-                ('slot', c_int32), ('reserved', c_int32), ('epoch', c_int64), ('counter', c_void_p)]
+    _fields_ = [('peer_flags', POINTER(c_uint64)), ('my_flags', c_void_p), ('rank', c_int32),
+                ('mode', c_int32), ('epoch', c_int64), ('counter', c_void_p)]
+
+
+PEER_RAISE_ACK, PEER_WAIT_ACK, PEER_SIGNAL, PEER_WAIT_DATA = 1, 2, 4, 8
 
 
 SIGNATURES = {

@@ -15,40 +15,52 @@ struct PeerPtrs {
     unsigned long long p[8];
 };
 
-// Flag traffic folded into the put kernels (saves two launches per transfer): before storing,
-// every CTA makes sure all peers acknowledged the previous use of the receive area; after the
-// stores the last CTA to finish raises data[slot] = epoch on every peer.
+// The whole flag protocol rides on the put launches (one launch per transfer instead of four):
+//   start  - CTA 0 raises ack[me] = epoch - 1 on every peer (stream order guarantees that the
+//            consumer of the previous transfer has finished reading my receive area);
+//          - every CTA makes sure all peers acknowledged transfer epoch - 2, the previous use of
+//            the receive area about to be overwritten (double buffering);
+//   end    - the last CTA to finish (device counter) raises data[me] = epoch on every peer and
+//            then waits until all of MY data flags reached epoch: when the kernel completes,
+//            the receive area is complete, and the next kernel of the stream (cuFFT, the local
+//            gather) can read it.
+// A rank's put never waits for something that only a later kernel of a peer provides (acks of
+// e - 2 are raised by the peer's put e - 1 at the latest), so the scheme cannot deadlock.
 struct PeerSync {
-    const long long* ack_flags;   // my ack flags (P entries) or nullptr
-    long long ack_epoch;
-    PeerPtrs flags;               // every rank's data flag array
-    int slot;
-    int signal;                   // 0: no signal from this launch
+    PeerPtrs flags;               // every rank's flag array: [0, P) data flags, [P, 2P) ack flags
+    const long long* my_flags;    // my own flag array
+    int rank;
+    int mode;                     // VPM_PEER_* bits
     long long epoch;
     unsigned* counter;            // zero-initialised device word, reset by the last CTA
 };
 
-__device__ __forceinline__ void peer_acquire(int P, const PeerSync& sy) {
-    if (sy.ack_flags != nullptr) {
-        if ((int)threadIdx.x < P) {
-            const volatile long long* f = sy.ack_flags;
-            unsigned long long spins = 0;
-            while (f[threadIdx.x] < sy.ack_epoch) {
-                if (++spins > (1ull << 31)) {
-                    printf("vmadpm: peer ack wait timed out (flag %d = %lld, want %lld)\n",
-                           (int)threadIdx.x, f[threadIdx.x], sy.ack_epoch);
-                    __trap();
-                }
-                __nanosleep(100);
-            }
+__device__ __forceinline__ void peer_spin(const volatile long long* f, long long want, const char* what) {
+    unsigned long long spins = 0;
+    while (*f < want) {
+        if (++spins > (1ull << 31)) {
+            printf("vmadpm: peer %s wait timed out (flag = %lld, want %lld)\n", what, *f, want);
+            __trap();
         }
+        __nanosleep(64);
+    }
+}
+
+__device__ __forceinline__ void peer_acquire(int P, const PeerSync& sy) {
+    if ((sy.mode & VPM_PEER_RAISE_ACK) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
+        (int)threadIdx.x < P) {
+        volatile long long* f = reinterpret_cast<volatile long long*>(sy.flags.p[threadIdx.x]);
+        f[P + sy.rank] = sy.epoch - 1;
+    }
+    if (sy.mode & VPM_PEER_WAIT_ACK) {
+        if ((int)threadIdx.x < P) peer_spin(sy.my_flags + P + threadIdx.x, sy.epoch - 2, "ack");
         __syncthreads();
     }
 }
 
 __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
     __threadfence_system();
-    if (!sy.signal) return;
+    if (!(sy.mode & VPM_PEER_SIGNAL)) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned done = atomicAdd(sy.counter, 1u);
@@ -57,9 +69,13 @@ __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
             __threadfence_system();
             for (int d = 0; d < P; ++d) {
                 volatile long long* f = reinterpret_cast<volatile long long*>(sy.flags.p[d]);
-                f[sy.slot] = sy.epoch;
+                f[sy.rank] = sy.epoch;
             }
             __threadfence_system();
+            if (sy.mode & VPM_PEER_WAIT_DATA) {
+                for (int d = 0; d < P; ++d) peer_spin(sy.my_flags + d, sy.epoch, "data");
+                __threadfence_system();
+            }
         }
     }
 }
@@ -75,9 +91,14 @@ k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_
     for (long long i = blockIdx.y; i < rows; i += gridDim.y) {
         const double2* __restrict__ in = src + i * s_row + d * s_dst;
         double2* __restrict__ o = out + i * inner;
-        for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < inner;
-             c += (long long)gridDim.x * blockDim.x)
-            o[c] = in[c];
+        // four independent 16-B loads in flight per thread before the (posted) stores
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        for (; c + 3 * stride < inner; c += 4 * stride) {
+            const double2 v0 = in[c], v1 = in[c + stride], v2 = in[c + 2 * stride], v3 = in[c + 3 * stride];
+            o[c] = v0; o[c + stride] = v1; o[c + 2 * stride] = v2; o[c + 3 * stride] = v3;
+        }
+        for (; c < inner; c += stride) o[c] = in[c];
     }
     peer_publish(P, sy);
 }
@@ -158,17 +179,17 @@ static PeerPtrs make_ptrs(int P, const uint64_t* p) {
 static PeerSync make_sync(int P, const vpm_peer_sync* h) {
     PeerSync sy;
     memset(&sy, 0, sizeof(sy));
-    if (h) {
-        sy.ack_flags = reinterpret_cast<const long long*>(h->ack_flags);
-        sy.ack_epoch = h->ack_epoch;
-        if (h->peer_flags) {
-            VPM_REQUIRE(h->counter, "peer sync: signalling needs a counter word");
-            sy.flags = make_ptrs(P, h->peer_flags);
-            sy.signal = 1;
-            sy.slot = h->slot;
-            sy.epoch = h->epoch;
-            sy.counter = h->counter;
-        }
+    if (h && h->mode) {
+        VPM_REQUIRE(h->peer_flags && h->my_flags, "peer sync: flag arrays missing");
+        VPM_REQUIRE(!(h->mode & VPM_PEER_SIGNAL) || h->counter, "peer sync: signalling needs a counter word");
+        VPM_REQUIRE(!(h->mode & VPM_PEER_WAIT_DATA) || (h->mode & VPM_PEER_SIGNAL),
+                    "peer sync: waiting for data implies signalling");
+        sy.flags = make_ptrs(P, h->peer_flags);
+        sy.my_flags = reinterpret_cast<const long long*>(h->my_flags);
+        sy.rank = h->rank;
+        sy.mode = h->mode;
+        sy.epoch = h->epoch;
+        sy.counter = h->counter;
     }
     return sy;
 }
@@ -221,7 +242,7 @@ int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t 
     if (total > 0 || sync) {   // an empty put still carries the flag traffic
         // about 16 CTAs per SM in flight: rows along y (capped), the rest along x
         const long long gy = std::max<long long>(1, std::min<long long>(rows, 1024));
-        const long long want = std::max<long long>(1, 16LL * ctx->sm_count / (gy * nranks));
+        const long long want = std::max<long long>(1, 8LL * ctx->sm_count / (gy * nranks));
         const long long gx = std::max<long long>(1, std::min<long long>(ceil_div(inner, 256), want));
         dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nranks);
         VPM_LAUNCH(k_peer_put, grid, 256, 0, ctx->stream, nranks, (long long)rows, (long long)inner,

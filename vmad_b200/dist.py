@@ -192,10 +192,12 @@ class PeerExchange(object):
     (vmad_b200/csrc/peer.cu).  One per communicator; ``nbytes`` is the capacity of one
     receive area.
 
-    Protocol for transfer number e (buffer e % 2): [put kernel: wait until every peer acknowledged
-    transfer e - 2 (it has finished reading the area about to be overwritten) -> store blocks into
-    the peers' areas -> last thread block raises data[me] = e everywhere] -> wait kernel: all data
-    flags here reached e -> consume -> release kernel: raise ack[me] = e everywhere.
+    Protocol for transfer number e (buffer e % 2), all inside the put kernel(s): acknowledge
+    transfer e - 1 to every peer (its consumer precedes this launch on the stream) -> wait until
+    every peer acknowledged transfer e - 2 (it has finished reading the area about to be
+    overwritten) -> store blocks into the peers' areas -> last thread block raises data[me] = e
+    everywhere and waits for all data flags here: when the kernel completes my receive area is
+    complete and the consumer (next kernel on the stream) reads it in place.
     """
 
     def __init__(self, comm, nbytes):
@@ -262,25 +264,30 @@ class PeerExchange(object):
         self.epoch += 1
         return self.epoch, self.epoch % 2
 
-    def _sync(self, e, last):
-        """flag traffic riding on a put launch: wait for the acks of transfer e - 2 (the previous
-        use of this receive area) before storing; the last put of a transfer raises my data flag"""
+    def _sync(self, e, first, last):
+        """flag protocol riding on a put launch (include/vmadpm.h: vpm_peer_sync)"""
         C, ct = self.C, self.ctypes
         sy = C.vpm_peer_sync()
-        sy.ack_flags = (self.my_flags + 8 * self.P) if e > 2 else None
-        sy.ack_epoch = e - 2
+        sy.peer_flags = ct.cast(self.data_flag_ptrs, ct.POINTER(ct.c_uint64))
+        sy.my_flags = self.my_flags
+        sy.rank = self.rank
+        mode = 0
+        if first and e > 1:
+            mode |= C.PEER_RAISE_ACK
+        if e > 2:
+            mode |= C.PEER_WAIT_ACK
         if last:
-            sy.peer_flags = ct.cast(self.data_flag_ptrs, ct.POINTER(ct.c_uint64))
-            sy.slot = self.rank
-            sy.epoch = e
-            sy.counter = self.my_flags + 8 * 2 * self.P
+            mode |= C.PEER_SIGNAL | C.PEER_WAIT_DATA
+        sy.mode = mode
+        sy.epoch = e
+        sy.counter = self.my_flags + 8 * 2 * self.P
         return ct.byref(sy)
 
-    def put(self, e, src, rows, inner, s_row, s_dst, dst_off, last=True):
+    def put(self, e, src, rows, inner, s_row, s_dst, dst_off, first=True, last=True):
         C, ct = self.C, self.ctypes
         C.check(C.lib.vpm_peer_put(self._ctx(), self.P, int(rows), int(inner), int(s_row), int(s_dst),
                                    ct.c_void_p(src.data_ptr()), self.buf_ptrs[e % 2], int(dst_off),
-                                   self._sync(e, last)))
+                                   self._sync(e, first, last)))
 
     def put_rows(self, e, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1):
         """particle rows to their destination ranks (vpm_peer_put_rows)"""
@@ -290,7 +297,7 @@ class PeerExchange(object):
         base = (ct.c_int64 * P)(*[int(v) for v in dst_base])
         C.check(C.lib.vpm_peer_put_rows(self._ctx(), P, int(n), int(ncomp), ct.c_void_p(src.data_ptr()),
                                         ct.c_void_p(idx.data_ptr()), int(idx_is_src), int(skip), seg, base,
-                                        self.buf_ptrs[e % 2], self._sync(e, True)))
+                                        self.buf_ptrs[e % 2], self._sync(e, True, True)))
 
     def ensure(self, nbytes):
         """collective: grow the receive areas (every rank must call with the same value)"""
@@ -299,13 +306,11 @@ class PeerExchange(object):
             self.__init__(self.comm, int(1.25 * nbytes))
 
     def commit(self, e):
-        C, ct = self.C, self.ctypes
-        C.check(C.lib.vpm_peer_wait(self._ctx(), self.P, ct.c_void_p(self.my_flags), e))
+        """nothing to launch: the last put of a transfer returns when my receive area is complete"""
 
     def recv_ptr(self, b, offset_elems=0):
         """device pointer (as c_void_p) to complex element ``offset_elems`` of my receive area b"""
         return self.ctypes.c_void_p(self.my_bufs[b] + 16 * int(offset_elems))
 
     def release(self, e):
-        C = self.C
-        C.check(C.lib.vpm_peer_signal(self._ctx(), self.P, self.P + self.rank, self.data_flag_ptrs, e))
+        """nothing to launch: the first put of the next transfer acknowledges this one"""

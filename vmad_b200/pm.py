@@ -1407,7 +1407,7 @@ class ParticleMesh(object):
             for k, real in enumerate(reals):
                 a = rt.empty((n0l, N1, Nh), _C16)
                 C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
-                px.put(e, a, n0l, inner, P * inner, inner, k * slab + self.rank * n0l * inner, last=(k == K - 1))
+                px.put(e, a, n0l, inner, P * inner, inner, k * slab + self.rank * n0l * inner, first=(k == 0), last=(k == K - 1))
             px.commit(e)
             out = []
             for k in range(K):
@@ -1447,7 +1447,7 @@ class ParticleMesh(object):
             e, b = px.begin()
             for k, c in enumerate(cplxs):
                 C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, inner, _ptr(c.t), 1, 1.0))
-                px.put(e, c.t, 1, blk, 0, blk, k * slab + self.rank * blk, last=(k == K - 1))
+                px.put(e, c.t, 1, blk, 0, blk, k * slab + self.rank * blk, first=(k == 0), last=(k == K - 1))
             px.commit(e)
             out = []
             for k in range(K):
