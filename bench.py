@@ -342,6 +342,32 @@ def run_gpu(args):
         torch.cuda.current_stream().synchronize()
         return dx, g
 
+    # One GPU: nothing in the call waits for the device, so the whole forward+vjp (VM, ctypes,
+    # ~700 launches) is captured once into a CUDA graph and each step is one graph launch on
+    # the same input buffers (vmad_b200/cudagraph.py).  Across ranks the host needs the particle
+    # counts of every decompose, so the call is not capturable and runs eagerly.
+    use_graph = world == 1 and N < 512 and not args.no_graph
+    eager_resident = step_resident
+    launches_per_graph = 0
+    if use_graph:
+        from vmad_b200.cudagraph import GraphedCall
+        for _ in range(2):
+            eager_resident()
+        l0 = C.launch_count()
+        graphed = GraphedCall(eager_resident, warmup=1)
+        launches_per_graph = (C.launch_count() - l0) // 2      # one warm-up call + the captured one
+
+        def step_resident():                                   # noqa: F811
+            return graphed()
+
+        def step_e2e():                                        # noqa: F811
+            wn_d.t.copy_(wn_pin, non_blocking=True)            # the graph's input buffers
+            cot_d.t.copy_(cot_pin, non_blocking=True)
+            dx, g = graphed()
+            grad_pin.copy_(g.t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return dx, g
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -374,6 +400,8 @@ def run_gpu(args):
         barrier()
         wall = time.perf_counter() - wall0
         launches = C.launch_count() - l0
+        if use_graph and fn is not eager_resident:
+            launches = launches_per_graph * steps       # replayed launches are not re-counted
         t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -386,6 +414,10 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
+    eager_ms = None
+    if use_graph:       # the same step without the graph, for the record
+        eager_total, _, _ = timed(eager_resident, args.steps, 1)
+        eager_ms = eager_total / args.steps
     ms_per_step = total_ms / args.steps
     value = world * args.nsteps / (ms_per_step * 1e-3)
     e2e_value = world * args.nsteps / (e2e_ms / args.steps * 1e-3)
@@ -418,7 +450,7 @@ def run_gpu(args):
     # (a) every paint launch of ONE more (untimed, otherwise identical) step, timed in place
     from vmad_b200 import pm as pm_mod
     pm_mod.PAINT_EVENTS = []
-    step_resident()
+    eager_resident()
     torch.cuda.synchronize()
     live = [(e0.elapsed_time(e1) * 1e-3, nb) for e0, e1, nb in pm_mod.PAINT_EVENTS]
     pm_mod.PAINT_EVENTS = None
@@ -480,7 +512,11 @@ def run_gpu(args):
                                       if pm._peer() is not None else "NCCL all-to-all", N))
                    if world > 1 else "1 gpu",
                    "l2": "256 MiB flush write between timed steps",
-                   "step": "one Model.compute_with_vjp = %d FastPM steps forward + reverse" % args.nsteps},
+                   "step": "one Model.compute_with_vjp = %d FastPM steps forward + reverse" % args.nsteps,
+                   "launch": ("CUDA graph replay of the captured compute_with_vjp (same input buffers; "
+                              "%d kernel launches per replay)" % launches_per_graph) if use_graph
+                   else "eager (python VM + ctypes, one launch per kernel)",
+                   "eager_ms_per_step": eager_ms},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(wn_h.nbytes + cot_h.nbytes),
@@ -526,6 +562,7 @@ def main():
     ap.add_argument('--cpu-nmesh', type=int, default=128,
                     help='largest mesh the CPU arm / cpu_baseline leg will run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='run every step eagerly through the VM')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
