@@ -1,5 +1,6 @@
+"""CUPTI kernel totals + cProfile of one multi-GPU forward+vjp step (torchrun, >= 2 GPUs)."""
 import os, sys, time, collections, re
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy, torch, torch.distributed as dist
 from torch.profiler import profile, ProfilerActivity
 local = int(os.environ.get('LOCAL_RANK', '0'))

@@ -1,3 +1,4 @@
+"""CUDA-graph replay of the whole forward+vjp vs the eager run: timing and agreement."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy, torch, bench

@@ -335,3 +335,58 @@ def test_edge_cases_empty_single_and_odd_meshes(oracle_pm, device_pm, paint_algo
         assert abs(dc.cnorm() - oc.cnorm()) < 1e-12 * abs(oc.cnorm())
         tf = lambda k: 1.0 / (1.0 + sum(ki ** 2 for ki in k)) + 0.5j * k[-1]
         assert rel_l2(dc.apply(lambda k, v: v * tf(k)).numpy(), oc.apply(lambda k, v: v * tf(k)).value) < TOL
+
+
+def test_routing_helpers_bit_exact(device_pm):
+    """the index plumbing of the cross-rank layout, driven on one GPU through the C ABI:
+    vpm_route_compose, vpm_take_rows2, masked vpm_scatter_add_rows, and the fused gather of
+    vpm_readout3 (out_row) -- all bit-exact against numpy indexing"""
+    import ctypes
+    import torch
+    from vmad_b200 import _capi as C
+    from vmad_b200.pm import runtime
+    rt = runtime()
+    rng = numpy.random.default_rng(21)
+    nsend, nrecv = 5000, 5200
+    send_idx = rng.integers(0, 4000, size=nsend).astype('i4')
+    perm = rng.permutation(nrecv).astype('i4')                # sorted slot -> receive row
+    recv_lo, send_lo, nself = 700, 1200, 3100                 # self segment in both orders
+    dev = lambda a: torch.from_numpy(numpy.ascontiguousarray(a)).cuda()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    take = torch.empty(nrecv, dtype=torch.int32, device='cuda')
+    remote = torch.empty(nsend, dtype=torch.int32, device='cuda')
+    d_perm, d_send = dev(perm), dev(send_idx)
+    C.check(C.lib.vpm_route_compose(rt.ctx, P(d_perm), nrecv, P(d_send), nsend, recv_lo, recv_lo + nself,
+                                    send_lo, P(take), P(remote)))
+    self_row = (perm >= recv_lo) & (perm < recv_lo + nself)
+    want_take = numpy.where(self_row, send_idx[numpy.clip(send_lo + perm - recv_lo, 0, nsend - 1)], -1 - perm)
+    want_remote = send_idx.copy()
+    want_remote[send_lo:send_lo + nself] = -1
+    assert numpy.array_equal(take.cpu().numpy(), want_take)
+    assert numpy.array_equal(remote.cpu().numpy(), want_remote)
+    # take_rows2: home rows where take >= 0, receive-area rows elsewhere
+    home = rng.standard_normal((4000, 3))
+    recv = rng.standard_normal((nrecv, 3))
+    out = torch.empty((nrecv, 3), dtype=torch.float64, device='cuda')
+    d_home, d_recv = dev(home), dev(recv)
+    C.check(C.lib.vpm_take_rows2(rt.ctx, P(d_home), P(d_recv), P(take), nrecv, 3, P(out)))
+    want = numpy.where(self_row[:, None], home[numpy.clip(want_take, 0, None)], recv[perm])
+    assert numpy.array_equal(out.cpu().numpy(), want)
+    # masked scatter-add: negative rows are skipped
+    acc = torch.zeros((4000, 3), dtype=torch.float64, device='cuda')
+    vals = rng.standard_normal((nsend, 3))
+    d_vals = dev(vals)
+    C.check(C.lib.vpm_scatter_add_rows(rt.ctx, P(d_vals), P(remote), nsend, 3, P(acc)))
+    ref = numpy.zeros((4000, 3))
+    keep = want_remote >= 0
+    numpy.add.at(ref, want_remote[keep], vals[keep])
+    assert rel_l2(acc.cpu().numpy(), ref) < 1e-15
+    # readout3 with the layout's permutation as out_row == readout3 followed by Layout.gather
+    dpm = device_pm([16, 16, 16], 50.0)
+    x = rng.uniform(0, 50.0, size=(3000, 3))
+    fs = [dpm.create('real', value=rng.standard_normal((16, 16, 16))) for _ in range(3)]
+    lay = dpm.decompose(x)
+    xs = lay.exchange(x)
+    a = dpm.readout3(fs[0], fs[1], fs[2], xs, gather=lay).numpy()
+    b = lay.gather(dpm.readout3(fs[0], fs[1], fs[2], xs)).numpy()
+    assert numpy.array_equal(a, b)
