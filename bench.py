@@ -246,6 +246,10 @@ def run_reference(args):
               % (args.nsteps, nmesh, threads))
     if nmesh != args.nmesh:
         sample += " (bounded sample: the GPU arm runs %d^3)" % args.nmesh
+    if args.gpus > 1:
+        sample += ("; bounded sample of the %d-GPU weak-scaling workload: one %d^3 block of the global mesh "
+                   "%s, throughput counted in the same %d^3-problem units as the GPU arm's value"
+                   % (args.gpus, args.nmesh, global_shape(args.nmesh, args.gpus), args.nmesh))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
