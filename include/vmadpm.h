@@ -124,8 +124,9 @@ int vpm_paint_sorted_col(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                          const double* mass2d, int ncomp, int col, int64_t np,
                          const int32_t* cell_start, double* out);
 /* the three columns of an interleaved [np, ncomp] array into three meshes, out + c *
- * out_colstride (c = 0, 1, 2), in one pass over the particles when the block-gather algorithm is
- * selected (positions and weights are shared); otherwise three aggregated paints. */
+ * out_colstride (c = 0, 1, 2), in ONE pass over the particles: positions, cell arithmetic and run
+ * detection are shared by the columns (aggregated reductions, or the block gather when that
+ * algorithm is selected). */
 int vpm_paint_sorted_cols3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                            const double* mass2d, int ncomp, int64_t np,
                            const int32_t* cell_start, double* out, int64_t out_colstride);

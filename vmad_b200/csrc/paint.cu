@@ -514,6 +514,111 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
     }
 }
 
+// Three columns of an interleaved [np, mstride] mass array into three meshes in ONE pass
+// (reverse sweep of the force operator: the three paints of the force cotangent share the
+// positions).  Same algorithm as k_paint_agg; position loads, cell arithmetic, run detection,
+// scan control and target addresses are shared by the three columns, only the weighted sums,
+// their shuffles and the reductions are per column (~45 % fewer instructions than 3 launches).
+__global__ void __launch_bounds__(256)
+k_paint_agg3(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, int mstride,
+             int np, double* __restrict__ out, long long colstride) {
+    const int lane = threadIdx.x & 31;
+    const int nchunk = (np + 31) >> 5;
+    const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
+    const int st0 = (int)g.stride0, st1 = (int)g.stride1;
+    for (int ch = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); ch < nchunk; ch += wstride) {
+        const int p = (ch << 5) + lane;
+        const bool active = p < np;
+        int key = -1 - lane;
+        int i0 = 0, i1 = 0, iz = 0;
+        double S[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) S[c][q] = 0.0;
+        if (active) {
+            const double* xp = xs + 3LL * p;
+            const double x0 = __ldg(xp + 0), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+            const double* mp = mass + (long long)p * mstride;
+            const double m0 = __ldg(mp + 0), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
+            double u, fl;
+            u = __dmul_rn(x0, g.s0); fl = floor(u); const double f0 = u - fl; i0 = wrap_fast(fl, g.n0);
+            u = __dmul_rn(x1, g.s1); fl = floor(u); const double f1 = u - fl; i1 = wrap_fast(fl, g.n1);
+            u = __dmul_rn(x2, g.s2); fl = floor(u); const double f2 = u - fl; iz = wrap_fast(fl, g.n2);
+            key = (i0 * g.n1 + i1) * g.n2 + iz;
+            const double e0 = 1.0 - f0, e1 = 1.0 - f1, e2 = 1.0 - f2;
+            double W[8];   // index a * 4 + b * 2 + cz
+            double w;
+            w = e0 * e1; W[0] = w * e2; W[1] = w * f2;
+            w = e0 * f1; W[2] = w * e2; W[3] = w * f2;
+            w = f0 * e1; W[4] = w * e2; W[5] = w * f2;
+            w = f0 * f1; W[6] = w * e2; W[7] = w * f2;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                S[0][q] = m0 * W[q];
+                S[1][q] = m1 * W[q];
+                S[2][q] = m2 * W[q];
+            }
+        }
+        const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (kprev != key));
+        if (heads != 0xffffffffu) {
+            for (int d = 1; d < 32; d <<= 1) {
+                const int kd = __shfl_up_sync(0xffffffffu, key, d);
+                const int same = (lane >= d) && (kd == key);
+                if (!__any_sync(0xffffffffu, same)) break;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double tv = __shfl_up_sync(0xffffffffu, S[c][q], d);
+                        VPM_ADD_IF(S[c][q], tv, same);
+                    }
+            }
+        }
+        const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+        const bool tail = active && (lane == 31 || knext != key);
+        const bool hand_over = tail && lane < 31 && knext == key + 1 && iz + 1 < g.n2;
+        const int myhead = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const int sl = max(myhead - 1, 0);
+        const int ksrc = __shfl_sync(0xffffffffu, key, sl);
+        const int take = tail && myhead > 0 && ksrc == key - 1 && iz > 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ab = 0; ab < 4; ++ab) {
+                const double t = __shfl_sync(0xffffffffu, S[c][2 * ab + 1], sl);
+                VPM_ADD_IF(S[c][2 * ab], t, take);
+            }
+        if (tail) {
+            const int j1 = wrap_inc(i1, g.n1), jz = wrap_inc(iz, g.n2);
+            const int la = local_plane(g, i0), lb = local_plane(g, wrap_inc(i0, g.n0));
+            const int ra = la * st0, rb = lb * st0;
+            const int c0 = i1 * st1, c1 = j1 * st1;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double* o = out + c * colstride;
+                if (la >= 0) {
+                    atomicAdd(o + (ra + c0 + iz), S[c][0]);
+                    atomicAdd(o + (ra + c1 + iz), S[c][2]);
+                    if (!hand_over) {
+                        atomicAdd(o + (ra + c0 + jz), S[c][1]);
+                        atomicAdd(o + (ra + c1 + jz), S[c][3]);
+                    }
+                }
+                if (lb >= 0) {
+                    atomicAdd(o + (rb + c0 + iz), S[c][4]);
+                    atomicAdd(o + (rb + c1 + iz), S[c][6]);
+                    if (!hand_over) {
+                        atomicAdd(o + (rb + c0 + jz), S[c][5]);
+                        atomicAdd(o + (rb + c1 + jz), S[c][7]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // Block gather (no atomics, no zero fill, fixed summation order).
 //
@@ -900,9 +1005,16 @@ int vpm_paint_sorted_cols3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
     if (g_paint_algo == 2 && gather_ok(g, cell_start)) {
         launch_paint_gather<3>(ctx, g, xs, mass2d, 1.0, ncomp, cell_start, out, out_colstride);
     } else {
-        for (int c = 0; c < 3; ++c)
-            launch_paint_agg<0>(ctx, g, xs, mass2d + c, 1.0, nullptr, nullptr, np, out + c * out_colstride,
-                                ncomp);
+        // one pass for the three columns (shared positions, cell arithmetic and run detection)
+        for (int c = 0; c < 3; ++c) zero_mesh(ctx, g, out + c * out_colstride);
+        if (np > 0) {
+            VPM_REQUIRE(np < (1LL << 31) - 64, "particle count must fit int32");
+            VPM_REQUIRE((long long)g.nloc0 * g.stride0 < (1LL << 31), "local mesh slab must have < 2^31 elements");
+            const long long nchunk = (np + 31) / 32;
+            const unsigned grid = (unsigned)std::min<long long>(ceil_div(nchunk, 8), 64LL * ctx->sm_count);
+            VPM_LAUNCH(k_paint_agg3, grid, 256, 0, ctx->stream, g, xs, mass2d, ncomp, (int)np, out,
+                       (long long)out_colstride);
+        }
     }
     VPM_API_END
 }

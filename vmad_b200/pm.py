@@ -1115,7 +1115,7 @@ class ParticleMesh(object):
         rt.sync_stream()
         n = x3.shape[0]
         mt = mass2d.t
-        if _PAINT_ALGO == 2:
+        if _PAINT_ALGO in (0, 2):
             m3 = rt.empty((3,) + tuple(self.rshape))
             with _timed_paint(48.0 * n + 8.0 * m3.numel()):
                 C.check(C.lib.vpm_paint_sorted_cols3(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(mt), 3, n,
