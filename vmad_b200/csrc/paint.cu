@@ -519,7 +519,7 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
 // positions).  Same algorithm as k_paint_agg; position loads, cell arithmetic, run detection,
 // scan control and target addresses are shared by the three columns, only the weighted sums,
 // their shuffles and the reductions are per column (~45 % fewer instructions than 3 launches).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_paint_agg3(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, int mstride,
              int np, double* __restrict__ out, long long colstride) {
     const int lane = threadIdx.x & 31;

@@ -88,10 +88,11 @@ PAINT_EVENTS = None
 
 class _timed_paint(object):
     """context manager around one paint launch; a no-op unless PAINT_EVENTS is a list"""
-    __slots__ = ('nbytes', 'e0')
+    __slots__ = ('nbytes', 'e0', 'kernel')
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, kernel='k_paint_agg'):
         self.nbytes = nbytes
+        self.kernel = kernel
         self.e0 = None
 
     def __enter__(self):
@@ -103,7 +104,7 @@ class _timed_paint(object):
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PAINT_EVENTS.append((self.e0, e1, self.nbytes))
+            PAINT_EVENTS.append((self.e0, e1, self.nbytes, self.kernel))
         return False
 
 
@@ -1117,7 +1118,7 @@ class ParticleMesh(object):
         mt = mass2d.t
         if _PAINT_ALGO in (0, 2):
             m3 = rt.empty((3,) + tuple(self.rshape))
-            with _timed_paint(48.0 * n + 8.0 * m3.numel()):
+            with _timed_paint(48.0 * n + 8.0 * m3.numel(), 'k_paint_agg3' if _PAINT_ALGO == 0 else 'k_paint_gather<3>'):
                 C.check(C.lib.vpm_paint_sorted_cols3(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(mt), 3, n,
                                                      _ptr(self._cell_start_of(lay, x3)), _ptr(m3),
                                                      m3[0].numel()))
