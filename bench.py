@@ -314,13 +314,20 @@ def run_gpu(args):
         comm = TorchComm()
     pm = ParticleMesh(dims, [100.0 * n / 32 for n in dims], comm=comm)
     pm.force_recompute = N >= 512  # keep potk instead of 3 force meshes per step on the tape
-    wn_g, cot_g = make_inputs(N, dims=dims)
     q = pm.generate_uniform_particle_grid(shift=0.0)
     npl = len(q)
-    # this rank's share: complex slab along axis 1, particles of its planes (lattice order)
-    wn_h = numpy.ascontiguousarray(wn_g[:, pm.cstart1:pm.cstart1 + pm.cshape[1]]) if world > 1 else wn_g
-    cot_h = numpy.ascontiguousarray(cot_g[rank * npl:(rank + 1) * npl])
-    del wn_g, cot_g
+    if int(numpy.prod(dims)) <= 512 ** 3:
+        wn_g, cot_g = make_inputs(N, dims=dims)
+        # this rank's share: complex slab along axis 1, particles of its planes (lattice order)
+        wn_h = numpy.ascontiguousarray(wn_g[:, pm.cstart1:pm.cstart1 + pm.cshape[1]]) if world > 1 else wn_g
+        cot_h = numpy.ascontiguousarray(cot_g[rank * npl:(rank + 1) * npl])
+        del wn_g, cot_g
+    else:
+        # global arrays of this size do not belong on every rank's host: draw the local complex
+        # slab and the local cotangent rows directly (unit-variance modes, per-rank streams)
+        rng = numpy.random.default_rng(300 + N + 1000 * rank)
+        wn_h = (rng.standard_normal(tuple(pm.cshape)) + 1j * rng.standard_normal(tuple(pm.cshape))) / 2 ** 0.5
+        cot_h = rng.standard_normal((npl, 3))
     stages = numpy.linspace(0.1, 1.0, args.nsteps + 1)
     model = build_model(pm, q, stages)
 
@@ -328,8 +335,8 @@ def run_gpu(args):
     wn_d = pm.create('complex', value=wn_h)
     cot_d = DeviceArray.from_host(cot_h)
     # pinned host staging for the end-to-end leg
-    wn_pin = torch.from_numpy(wn_h.copy()).pin_memory()
-    cot_pin = torch.from_numpy(cot_h.copy()).pin_memory()
+    wn_pin = torch.from_numpy(wn_h).pin_memory()
+    cot_pin = torch.from_numpy(cot_h).pin_memory()
     grad_pin = torch.empty(wn_pin.shape, dtype=wn_pin.dtype).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 

@@ -759,9 +759,11 @@ class DistLayout(object):
                                 # reference cycle and keep ~50 MB alive until the cyclic GC runs
         else:
             self._xs = None
-        if self.px is not None:
+        self.take_idx = self.send_remote = None
+        if self.px is not None and not getattr(pm, 'force_recompute', False):
             # rows that stay on this rank (nearly all of them) bypass the receive area: composed
-            # indices let exchange / gather touch the home array directly
+            # indices let exchange / gather touch the home array directly (8 B/particle more on
+            # the tape per layout -- skipped in the memory-lean mode of the largest runs)
             self.take_idx = rt.empty((max(self.nrecv, 1),), torch.int32)
             self.send_remote = rt.empty((max(self.nsend, 1),), torch.int32)
             C.check(C.lib.vpm_route_compose(rt.ctx, _ptr(self.indices), self.nrecv, _ptr(self.send_idx),
@@ -804,10 +806,15 @@ class DistLayout(object):
             # put -> (flags) -> the local sort gathers straight out of the receive area
             t = data.t
             ncomp = _ncomp(t)
-            e, b = self._peer_forward(t, ncomp, skip=self.pm.rank)
             out = rt.empty((self.nrecv,) + tuple(t.shape[1:]))
-            C.check(C.lib.vpm_take_rows2(rt.ctx, _ptr(t), self.px.recv_ptr(b), _ptr(self.take_idx), self.nrecv,
-                                         ncomp, _ptr(out)))
+            if self.take_idx is not None:
+                e, b = self._peer_forward(t, ncomp, skip=self.pm.rank)
+                C.check(C.lib.vpm_take_rows2(rt.ctx, _ptr(t), self.px.recv_ptr(b), _ptr(self.take_idx),
+                                             self.nrecv, ncomp, _ptr(out)))
+            else:
+                e, b = self._peer_forward(t, ncomp)
+                C.check(C.lib.vpm_take_rows(rt.ctx, self.px.recv_ptr(b), _ptr(self.indices), self.nrecv, ncomp,
+                                            _ptr(out)))
             self.px.release(e)
             return DeviceArray(out, cellindex=self)
         recv = self._forward(data.t)
@@ -829,10 +836,16 @@ class DistLayout(object):
             px = self.px
             px.ensure(8 * self._max_rows * ncomp)
             e, b = px.begin()
+            out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
+            if self.take_idx is None:
+                px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base)
+                C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), self.nsend, ncomp,
+                                                   _ptr(out)))
+                px.release(e)
+                return DeviceArray(out)
             px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base,
                         skip=self.pm.rank)
-            # rows that never left: straight into their home rows while the peers' rows travel
-            out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
+            # rows that never left go straight into their home rows
             C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(t), _ptr(self.take_idx), self.nrecv, ncomp, _ptr(out)))
             px.commit(e)
             C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_remote), self.nsend, ncomp,
