@@ -35,12 +35,9 @@ say('recv ok:', bool((out.cpu() == exp).all()))
 for it in range(20):
     e, b = px.begin(); px.put(e, src, 1, n, 0, n, rank * n); px.commit(e); px.release(e)
 rt.synchronize(); say('20 rounds ok')
-# ---- timing: full protocol per transfer, slab-transpose sized payload vs empty payload
-import time
-px.ensure(64 << 20)
-rows, inner = 128, (128 // P) * 65
-big = torch.randn(rows * P * inner * 2, dtype=torch.float64, device='cuda')
-def loop(nrows, iters=100):
+# ---- timing: full protocol per transfer, transpose-shaped payloads of growing size vs empty
+px.ensure(1200 << 20)
+def loop(big, nrows, rows, inner, iters):
     comm.barrier(); torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -48,9 +45,14 @@ def loop(nrows, iters=100):
         e, b = px.begin(); px.put(e, big, nrows, inner, P * inner, inner, rank * rows * inner); px.commit(e); px.release(e)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
-for nrows in (0, rows, 0, rows):
-    t = loop(nrows)
-    say('transfer of %5.1f MB per rank (%.1f MB to each peer): %.1f us per put+wait+release' % (
-        nrows * P * inner * 16 / 1e6, nrows * inner * 16 / 1e6, t))
+for rows, inner, iters in ((128, (128 // P) * 65, 100), (256, (256 // P) * 129, 50), (512, (512 // P) * 65 * 2, 30), (512, (512 // P) * 65 * 4, 20)):
+    big = torch.randn(rows * P * inner * 2, dtype=torch.float64, device='cuda')
+    t0 = loop(big, 0, rows, inner, iters)
+    t = loop(big, rows, rows, inner, iters)
+    mb = rows * inner * 16 / 1e6
+    if rank == 0:
+        say('%7.1f MB to each of %d peers (+ the same kept locally): %8.1f us per transfer (empty: %.1f us) -> %.0f GB/s of '
+            'remote stores per GPU' % (mb, P - 1, t, t0, mb * (P - 1) * 1e6 / ((t - t0) * 1e-6) / 1e9))
+    del big
 px.close(); say('closed')
 dist.destroy_process_group()
