@@ -371,11 +371,28 @@ def run_gpu(args):
         def step_resident():                                   # noqa: F811
             return graphed()
 
-        def step_e2e():                                        # noqa: F811
-            wn_d.t.copy_(wn_pin, non_blocking=True)            # the graph's input buffers
-            cot_d.t.copy_(cot_pin, non_blocking=True)
-            dx, g = graphed()
+        # end-to-end: the host<->device copies are nodes of a second captured graph; the upload
+        # of the cotangent (50 MB) runs on a forked stream beside the forward sweep and joins
+        # before the reverse sweep, which is the first reader (same calls as compute_with_vjp:
+        # compute(return_tape=True) then tape.get_vjp().compute)
+        side = torch.cuda.Stream()
+
+        def e2e_call():
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                cot_d.t.copy_(cot_pin, non_blocking=True)
+            wn_d.t.copy_(wn_pin, non_blocking=True)
+            (dx,), tape = model.compute(['dx'], init=dict(x=wn_d), return_tape=True)
+            cur.wait_stream(side)
+            (g,) = tape.get_vjp().compute(tape.get_vjp_vout(), init=dict(_dx=cot_d))
             grad_pin.copy_(g.t, non_blocking=True)
+            return dx, g
+
+        graphed_e2e = GraphedCall(e2e_call, warmup=1)
+
+        def step_e2e():                                        # noqa: F811
+            dx, g = graphed_e2e()
             torch.cuda.current_stream().synchronize()
             return dx, g
 
@@ -425,6 +442,13 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
+    e2e_check = None
+    if use_graph:       # what came back over PCIe from the replayed pipeline == the eager gradient
+        _, g_e = eager_resident()
+        torch.cuda.synchronize()
+        ref = g_e.t.cpu()
+        e2e_check = float((grad_pin - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt())
+        del ref, g_e
     eager_ms = None
     if use_graph:       # the same step without the graph, for the record
         eager_total, _, _ = timed(eager_resident, args.steps, 1)
@@ -541,7 +565,7 @@ def run_gpu(args):
                    "launch": ("CUDA graph replay of the captured compute_with_vjp (same input buffers; "
                               "%d kernel launches per replay)" % launches_per_graph) if use_graph
                    else "eager (python VM + ctypes, one launch per kernel)",
-                   "eager_ms_per_step": eager_ms},
+                   "eager_ms_per_step": eager_ms, "e2e_gradient_vs_eager_rel_l2": e2e_check},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(wn_h.nbytes + cot_h.nbytes),
