@@ -76,6 +76,10 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
 /* dst[i, :] = src[perm[i], :]            (Layout.exchange on one rank) */
 int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
                   int ncomp, double* dst);
+/* dst[i, :] = scale * src[perm[i], :]  (exchange of a cotangent fused with the constant factor of
+ * the kick it comes from: reverse sweep of the fused drift-force-kick step) */
+int vpm_take_rows_scaled(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
+                         int ncomp, double scale, double* dst);
 /* dst[perm[i], :] = src[i, :]  for a permutation (Layout.gather on one rank) */
 int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
                      int ncomp, double* dst);
@@ -165,10 +169,12 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
                      double* value, double* grad);
 /* grad[p, :] = sum_d w3[p, d] * gradreadout(f_d, x_p) + gradreadout(r, x_p): the particle half
  * of the reverse sweep of the fused force operator (readout.vjp x3 + paint.vjp, fastpm.py:229,
- * 256) in one pass over the particles; out_row as in vpm_readout3. */
+ * 256) in one pass over the particles; out_row as in vpm_readout3; base (may be NULL): an
+ * [np, 3] array added row by row at the rows written (the cotangent reaching dx from its other
+ * consumers -- saves the separate accumulation pass). */
 int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                       const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, const int32_t* out_row, double* grad);
+                      int64_t np, const int32_t* out_row, const double* base, double* grad);
 /* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);
  * either term may be absent (NULL). */
 int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
@@ -312,6 +318,10 @@ int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double 
 /* out = a * x + b * y + c   (y may be NULL) */
 int vpm_axpby(vpm_ctx* ctx, int64_t n, double a, const double* x, double b,
               const double* y, double c, double* out);
+/* dx1 = dx + fac * p  and  x1 = q + dx1 in one pass (drift + the position update of the next force
+ * evaluation, fastpm.py:411,463-464) */
+int vpm_drift_pos(vpm_ctx* ctx, int64_t n, const double* dx, const double* p, double fac,
+                  const double* q, double* dx1, double* x1);
 /* out = x * y */
 int vpm_mul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
 /* out = x / y */

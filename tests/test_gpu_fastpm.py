@@ -15,11 +15,13 @@ def put(x):
     return DeviceArray.from_host(x)
 
 
-@pytest.fixture(params=[True, False], ids=['fused', 'unfused'])
+@pytest.fixture(params=[(True, True), (True, False), (False, False)], ids=['stage', 'fused', 'unfused'])
 def fused(request):
+    """'stage': one drift_force_kick operator per leapfrog stage (default); 'fused': separate
+    force / kick / drift operators; 'unfused': the reference's node-by-node graph"""
     from vmad_b200.lib import fastpm
-    fastpm.set_fused(request.param)
-    yield request.param
+    fastpm.set_fused(*request.param)
+    yield request.param[0]
     fastpm.set_fused(True)
 
 

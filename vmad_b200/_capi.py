@@ -66,6 +66,7 @@ SIGNATURES = {
     'vpm_route_build': (c_int, [c_void_p, POINTER(vpm_mesh), c_int, _P, c_int64, _P, c_int64,
                                 POINTER(c_int32)]),
     'vpm_take_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
+    'vpm_take_rows_scaled': (c_int, [c_void_p, _P, _P, c_int64, c_int, c_double, _P]),
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_take_rows2': (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, _P]),
@@ -83,7 +84,7 @@ SIGNATURES = {
     'vpm_readout3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P, _P]),
     'vpm_readout_grad': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, c_double, c_int64,
                                  _P, _P]),
-    'vpm_readout_grad4': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
+    'vpm_readout_grad4': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
     'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
@@ -114,6 +115,7 @@ SIGNATURES = {
     'vpm_fd4_neg_gradient': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
     'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),
+    'vpm_drift_pos': (c_int, [c_void_p, c_int64, _P, _P, c_double, _P, _P, _P]),
     'vpm_mul': (c_int, [c_void_p, c_int64, _P, _P, _P]),
     'vpm_div': (c_int, [c_void_p, c_int64, _P, _P, _P]),
     'vpm_mul_rows': (c_int, [c_void_p, c_int64, c_int, _P, _P, _P]),

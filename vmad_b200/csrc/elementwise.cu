@@ -30,6 +30,18 @@ k_axpby(long long n, double a, const double* __restrict__ x, double b,
     })
 }
 
+// drift fused with the position update of the next force evaluation:
+//   dx1 = dx + fac * p (one FMA, as k_axpby computes it),  x1 = q + dx1
+__global__ void __launch_bounds__(EW_THREADS)
+k_drift_pos(long long n, const double* __restrict__ dx, const double* __restrict__ p, double fac,
+            const double* __restrict__ q, double* __restrict__ dx1, double* __restrict__ x1) {
+    EW_LOOP(n, {
+        const double d = fma(fac, p[e], dx[e]);
+        dx1[e] = d;
+        x1[e] = q[e] + d;
+    })
+}
+
 template <int OP>  // 0: mul, 1: div
 __global__ void __launch_bounds__(EW_THREADS)
 k_binary(long long n, const double* __restrict__ x, const double* __restrict__ y,
@@ -154,6 +166,17 @@ int vpm_axpby(vpm_ctx* ctx, int64_t n, double a, const double* x, double b, cons
         VPM_REQUIRE(x && out, "NULL array");
         if (y) VPM_LAUNCH(k_axpby<true>, ew_grid(n), EW_THREADS, 0, ctx->stream, (long long)n, a, x, b, y, c, out);
         else VPM_LAUNCH(k_axpby<false>, ew_grid(n), EW_THREADS, 0, ctx->stream, (long long)n, a, x, b, y, c, out);
+    }
+    VPM_API_END
+}
+
+int vpm_drift_pos(vpm_ctx* ctx, int64_t n, const double* dx, const double* p, double fac,
+                  const double* q, double* dx1, double* x1) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx, "ctx is NULL");
+    if (n > 0) {
+        VPM_REQUIRE(dx && p && q && dx1 && x1, "NULL array");
+        VPM_LAUNCH(k_drift_pos, ew_grid(n), EW_THREADS, 0, ctx->stream, (long long)n, dx, p, fac, q, dx1, x1);
     }
     VPM_API_END
 }

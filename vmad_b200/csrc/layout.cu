@@ -248,13 +248,13 @@ __global__ void k_set_last(int* cell_start, long long ncell, int np) { cell_star
 // ---- row permutes -------------------------------------------------------------------
 template <int NC>
 __global__ void k_take_rows(const double* __restrict__ src, const int* __restrict__ perm,
-                            long long n, int ncomp, double* __restrict__ dst) {
+                            long long n, int ncomp, double scale, double* __restrict__ dst) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int nc = NC > 0 ? NC : ncomp;
     if (e >= n * nc) return;
     long long i = e / nc;
     int c = (int)(e - i * nc);
-    dst[e] = __ldg(src + (long long)perm[i] * nc + c);
+    dst[e] = scale * __ldg(src + (long long)perm[i] * nc + c);   // scale = 1 is exact
 }
 
 template <int NC, bool ADD>
@@ -480,18 +480,30 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
     VPM_API_END
 }
 
-int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
-                  double* dst) {
-    VPM_API_BEGIN
+static void launch_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
+                             double scale, double* dst) {
     VPM_REQUIRE(ctx, "ctx is NULL");
     VPM_REQUIRE(ncomp >= 1, "ncomp must be >= 1");
     if (n > 0) {
         VPM_REQUIRE(src && perm && dst, "NULL array");
         unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
-        if (ncomp == 1) VPM_LAUNCH(k_take_rows<1>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
-        else if (ncomp == 3) VPM_LAUNCH(k_take_rows<3>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
-        else VPM_LAUNCH(k_take_rows<0>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
+        if (ncomp == 1) VPM_LAUNCH(k_take_rows<1>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows<3>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, dst);
+        else VPM_LAUNCH(k_take_rows<0>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, dst);
     }
+}
+
+int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
+                  double* dst) {
+    VPM_API_BEGIN
+    launch_take_rows(ctx, src, perm, n, ncomp, 1.0, dst);
+    VPM_API_END
+}
+
+int vpm_take_rows_scaled(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
+                         double scale, double* dst) {
+    VPM_API_BEGIN
+    launch_take_rows(ctx, src, perm, n, ncomp, scale, dst);
     VPM_API_END
 }
 

@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(256)
 k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__ F1,
                 const double* __restrict__ F2, const double* __restrict__ R,
                 const double* __restrict__ x, const double* __restrict__ w3, long long np,
-                const int* __restrict__ out_row, double* __restrict__ grad) {
+                const int* __restrict__ out_row, const double* __restrict__ base,
+                double* __restrict__ grad) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= np) return;
     Stencil s = make_stencil(g, x, p);
@@ -181,6 +182,11 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
         a2 += (u1 - u0) * (wxy * g.s2);
     }
     const long long o = out_row ? (long long)__ldg(out_row + p) : p;
+    if (base) {   // cotangent arriving at the same rows from the other consumers of dx
+        a0 += __ldg(base + 3 * o + 0);
+        a1 += __ldg(base + 3 * o + 1);
+        a2 += __ldg(base + 3 * o + 2);
+    }
     grad[3 * o + 0] = a0;
     grad[3 * o + 1] = a1;
     grad[3 * o + 2] = a2;
@@ -258,14 +264,14 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, co
 
 int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                       const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, const int32_t* out_row, double* grad) {
+                      int64_t np, const int32_t* out_row, const double* base, double* grad) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
         VPM_REQUIRE(f0 && f1 && f2 && r && x && w3 && grad, "NULL array");
         VPM_LAUNCH(k_readout_grad4, (unsigned)ceil_div(np, 256), 256, 0, ctx->stream, g, f0, f1, f2, r,
-                   x, w3, (long long)np, out_row, grad);
+                   x, w3, (long long)np, out_row, base, grad);
     }
     VPM_API_END
 }

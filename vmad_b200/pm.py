@@ -1672,14 +1672,28 @@ def _use_stencil(pm):
     return pm.P == 1 and getattr(pm, 'force_stencil', True) and min(pm.rshape) >= 1
 
 
-def force_apl(pm, dx, q):
-    """f = -grad laplace^-1 (rho Nc / Np) read out at x = q + dx; returns (f, potk, state)"""
+def drift_pos(pm, dx, p, fac, q):
+    """``dx1 = dx + fac p`` and ``x1 = q + dx1`` in one pass (vpm_drift_pos)"""
+    rt = pm.rt
+    dx, p, q = asdevice(dx), asdevice(p), asdevice(q)
+    rt.sync_stream()
+    dx1 = rt.empty(tuple(dx.t.shape))
+    x1 = rt.empty(tuple(dx.t.shape))
+    C.check(C.lib.vpm_drift_pos(rt.ctx, dx.t.numel(), _ptr(dx.t), _ptr(p.t), float(fac), _ptr(q.t),
+                                _ptr(dx1), _ptr(x1)))
+    return DeviceArray(dx1), DeviceArray(x1)
+
+
+def force_apl(pm, dx, q, x=None):
+    """f = -grad laplace^-1 (rho Nc / Np) read out at x = q + dx; returns (f, potk, state).
+    ``x``: the positions when the caller already has them (fused drift)."""
     if pm.ndim != 3:
         raise ValueError("the fused force operator is 3-D only")
     rt = pm.rt
     q = asdevice(q)
-    dx = asdevice(dx)
-    x = q + dx
+    if x is None:
+        dx = asdevice(dx)
+        x = q + dx
     layout = pm.decompose(x)
     xl = layout.exchange(x)
     rho = pm.paint(xl, 1.0)
@@ -1706,16 +1720,28 @@ def force_apl(pm, dx, q):
     return f, potk, ForceState(xl, layout, F, None, None, scale, tabs)
 
 
-def force_vjp(pm, st, _f, _potk):
-    """reverse sweep of force_apl: cotangents of (f, potk) -> cotangent of dx"""
+def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None):
+    """reverse sweep of force_apl: cotangents of (f, potk) -> cotangent of dx.
+    ``f_scale``: the force cotangent is ``f_scale * _f`` (the factor of the kick it comes from,
+    applied while exchanging); ``base``: added to the result (the cotangent reaching dx from its
+    other consumers), inside the store of the last kernel where possible."""
     rt = pm.rt
     lay, xl = st.layout, st.xl
     f_zero = _is_zero_literal(_f)
     n = xl.t.shape[0]
+    one_rank = isinstance(lay, Layout) and lay.newlength == n == lay.oldlength
     if f_zero:
         _fl = DeviceArray(torch.zeros((n, 3), dtype=_F8, device=rt.device))
-    else:
+    elif f_scale == 1.0:
         _fl = lay.exchange(asdevice(_f))
+    elif one_rank:
+        _f = asdevice(_f)
+        rt.sync_stream()
+        t = rt.empty((n, 3))
+        C.check(C.lib.vpm_take_rows_scaled(rt.ctx, _ptr(_f.t), _ptr(lay.indices), n, 3, float(f_scale), _ptr(t)))
+        _fl = DeviceArray(t, cellindex=lay)
+    else:
+        _fl = lay.exchange(asdevice(_f) * float(f_scale))
     # readout.vjp (mesh half) x3: three paints of the columns of the force cotangent
     Fbar = pm.paint_cols3(xl, _fl)
     pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
@@ -1745,11 +1771,19 @@ def force_vjp(pm, st, _f, _potk):
     F = st.meshes(pm)
     rt.sync_stream()
     g = rt.empty((n, 3))
-    fused = isinstance(lay, Layout) and lay.newlength == n == lay.oldlength   # gather in the store
+    if base is not None and _is_zero_literal(base):
+        base = None
+    if one_rank:        # gather (and the accumulation of `base`) in the store
+        bt = asdevice(base).t if base is not None else None
+        C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
+                                        _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
+                                        _ptr(lay.indices), _ptr(bt), _ptr(g)))
+        return DeviceArray(g)
     C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
                                     _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
-                                    _ptr(lay.indices) if fused else None, _ptr(g)))
-    return DeviceArray(g) if fused else lay.gather(DeviceArray(g))
+                                    None, None, _ptr(g)))
+    out = lay.gather(DeviceArray(g))
+    return out + asdevice(base) if base is not None else out
 
 
 def force_jvp(pm, st, dx_):
