@@ -222,3 +222,30 @@ def test_fastpm_simulation_vs_oracle(oracle_pm, device_pm, fused, B):
         res[name] = [host(a) for a in (dx, p, f, gx)]
     errs = [rel_l2(a, b) for a, b in zip(res['device'], res['oracle'])]
     assert all(e < 1e-10 for e in errs), errs
+
+
+def test_scalar_reductions_and_entry_points_vs_oracle(oracle_pm, device_pm):
+    """to_scalar, cdot and as_complex_field (fastpm.py:9-42,512-527) at operator level:
+    values, vjp and jvp on the device == the oracle"""
+    from vmad_b200 import Builder
+    from vmad_b200.lib import fastpm
+    N = 12
+    rng = numpy.random.default_rng(23)
+    pairs = rng.standard_normal((N, N, N // 2 + 1, 2))
+    c2v = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5
+    tan = rng.standard_normal(pairs.shape)
+    res = {}
+    for name, pm in [('oracle', oracle_pm([N] * 3, 30.0)), ('device', device_pm([N] * 3, 30.0))]:
+        with Builder() as m:
+            a, c2 = m.input('a', 'c2')
+            c1 = fastpm.as_complex_field(a, pm)
+            s1 = fastpm.to_scalar(fastpm.c2r(c1))
+            s2 = fastpm.cdot(c1, c2)
+            m.output(y=s1 + s2 * 3.0)
+        init = dict(a=pairs, c2=pm.create('complex', value=c2v))
+        y, (ga, gc2) = m.compute_with_vjp(init=init, v=dict(_y=1.0))
+        _, (y_,) = m.compute_with_jvp(['y'], init=init, v=dict(a_=tan, c2_=0))
+        res[name] = [numpy.asarray(host(v), dtype='c16' if numpy.iscomplexobj(host(v)) else 'f8')
+                     for v in (y[0] if isinstance(y, (list, tuple)) else y, ga, gc2, y_)]
+    for a, b in zip(res['device'], res['oracle']):
+        assert rel_l2(numpy.atleast_1d(a), numpy.atleast_1d(b)) < 1e-12
