@@ -209,6 +209,13 @@ class PeerExchange(object):
         self.P, self.rank = comm.size, comm.rank
         if self.P > 8:
             raise ValueError("peer exchange supports up to 8 ranks")
+        self._own, self._opened = [], []
+        self._allocate(nbytes)
+
+    def _allocate(self, nbytes):
+        """collective: (re)create the receive areas and flag arrays, exchange the IPC handles"""
+        import ctypes
+        C, comm = self.C, self.comm
         self.nbytes = int(nbytes)
         ctx = self._ctx()
         self._own, self._opened = [], []
@@ -303,7 +310,7 @@ class PeerExchange(object):
         """collective: grow the receive areas (every rank must call with the same value)"""
         if nbytes > self.nbytes:
             self.close()
-            self.__init__(self.comm, int(1.25 * nbytes))
+            self._allocate(int(1.25 * nbytes))
 
     def commit(self, e):
         """nothing to launch: the last put of a transfer returns when my receive area is complete"""

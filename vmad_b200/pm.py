@@ -924,6 +924,7 @@ class ParticleMesh(object):
         self._mesh = m
         self._ncell = int(C.lib.vpm_layout_ncell(ctypes.byref(m)))
         self._tables = {}
+        self._frozen_layouts = {}     # id(constant position array) -> (weakref, layout)
         self._tf_cache = {}
 
     # -- host-side tables ---------------------------------------------------------------
@@ -1003,7 +1004,11 @@ class ParticleMesh(object):
             axes[0] = axes[0][self.rstart0:self.rstart0 + self.rshape[0]]
         grid = numpy.meshgrid(*axes, indexing='ij')
         q = numpy.stack([g.ravel() for g in grid], axis=-1).astype('f8')
-        return q if return_host else DeviceArray.from_host(q)
+        if return_host:
+            return q
+        q = DeviceArray.from_host(q)
+        q._frozen = True      # a constant of the graph: decompose() caches its layout
+        return q
 
     def generate_whitenoise(self, seed, unitary=False, type='complex', mean=0.0, mode=None,
                             return_host=False):
@@ -1024,8 +1029,16 @@ class ParticleMesh(object):
         return c if return_host else self.create('complex', value=c)
 
     def asparticles(self, x):
-        """particle array (host or device) -> device array; done once when a graph is built"""
-        return asdevice(numpy.asarray(x) if isinstance(x, (list, tuple)) else x)
+        """particle array (host or device) -> device array; done once when a graph is built.
+        A copy made here from host data is a constant of the graph (``_frozen``): ``decompose``
+        caches the layout of such an array -- the Lagrangian positions ``q`` are decomposed twice
+        per LPT evaluation and never change."""
+        if isinstance(x, DeviceArray):
+            return x
+        d = asdevice(numpy.asarray(x) if isinstance(x, (list, tuple)) else x)
+        if isinstance(d, DeviceArray):
+            d._frozen = True
+        return d
 
     # -- positions --------------------------------------------------------------------------
     def _pos3(self, pos):
@@ -1060,9 +1073,16 @@ class ParticleMesh(object):
     def decompose(self, pos, smoothing=None, keep_index=None):
         """fastpm.py:272.  One rank: the stable cell sort.  Several ranks: route every particle
         to the slab(s) that own the two planes it touches, then cell-sort what arrived."""
-        if self.P > 1:
-            return DistLayout(self, pos, keep_index)
-        return self._decompose_local(pos, keep_index)
+        frozen = isinstance(pos, DeviceArray) and getattr(pos, '_frozen', False) and keep_index is None
+        if frozen:
+            hit = self._frozen_layouts.get(id(pos))
+            if hit is not None and hit[0]() is pos:
+                return hit[1]
+        layout = DistLayout(self, pos, keep_index) if self.P > 1 else self._decompose_local(pos, keep_index)
+        if frozen:
+            cache, key = self._frozen_layouts, id(pos)
+            cache[key] = (weakref.ref(pos, lambda r, cache=cache, key=key: cache.pop(key, None)), layout)
+        return layout
 
     def _decompose_local(self, pos, keep_index=None):
         """``keep_index``: also keep the cell keys and cell offsets on the layout (the sorted
