@@ -95,7 +95,7 @@ def build_model(pm, q, stages):
 class ClockSampler(object):
     """SM clock + clock-event reasons sampled DURING the timed region.
 
-    NVML is read in-process from a background thread (a few cheap driver queries every 100 ms);
+    NVML is read in-process from a background thread (a few cheap driver queries every 20 ms);
     an external ``nvidia-smi -lms`` loop is only the fallback -- its heavier polling perturbs
     multi-process runs whose ranks spin on each other's flags.
     """
@@ -124,7 +124,7 @@ class ClockSampler(object):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         mode = os.environ.get('VMAD_BENCH_CLOCKS', 'nvml')
