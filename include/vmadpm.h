@@ -158,10 +158,12 @@ int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const d
                 int64_t np, double* value);
 /* three fields at once, written interleaved [np, 3] (fuses linalg.stack,
  * fastpm.py:349,437).  out_row (may be NULL): row p is stored at row out_row[p] -- Layout.gather
- * of a one-rank layout (its slot -> home row permutation) fused into the store. */
+ * of a one-rank layout (its slot -> home row permutation) fused into the store.  y_out (may be
+ * NULL): y_out[row] = y_in[row] + fac * value[row] at the rows written -- the kick that consumes
+ * the force (fastpm.py:470-471); value3 may then be NULL when the force itself is not needed. */
 int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                  const double* f2, const double* x, int64_t np, const int32_t* out_row,
-                 double* value3);
+                 double* value3, const double* y_in, double fac, double* y_out);
 /* value[p] (optional, may be NULL) and grad[p, d] = w_p * sum_c field[c] dW/dx_d,
  * w_p = weight[p] or weight0 when weight == NULL. */
 int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
@@ -171,10 +173,12 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
  * of the reverse sweep of the fused force operator (readout.vjp x3 + paint.vjp, fastpm.py:229,
  * 256) in one pass over the particles; out_row as in vpm_readout3; base (may be NULL): an
  * [np, 3] array added row by row at the rows written (the cotangent reaching dx from its other
- * consumers -- saves the separate accumulation pass). */
+ * consumers -- saves the separate accumulation pass); y_out (may be NULL): y_out[row] =
+ * y_in[row] + fac * grad[row] (the momentum cotangent of the drift, fastpm.py:463-464). */
 int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                       const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, const int32_t* out_row, const double* base, double* grad);
+                      int64_t np, const int32_t* out_row, const double* base, double* grad,
+                      const double* y_in, double fac, double* y_out);
 /* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);
  * either term may be absent (NULL). */
 int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,

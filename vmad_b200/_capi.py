@@ -81,10 +81,10 @@ SIGNATURES = {
                                      c_int64, _P, _P]),
     'vpm_paint_atomic': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P]),
     'vpm_readout': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int64, _P]),
-    'vpm_readout3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P, _P]),
+    'vpm_readout3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P, _P, _P, c_double, _P]),
     'vpm_readout_grad': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, c_double, c_int64,
                                  _P, _P]),
-    'vpm_readout_grad4': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
+    'vpm_readout_grad4': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_double, _P]),
     'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),

@@ -108,7 +108,8 @@ k_readout(Geo g, const double* __restrict__ field, const double* __restrict__ x,
 __global__ void __launch_bounds__(256)
 k_readout3(Geo g, const double* __restrict__ fa, const double* __restrict__ fb,
            const double* __restrict__ fc, const double* __restrict__ x, long long np,
-           const int* __restrict__ out_row, double* __restrict__ value3) {
+           const int* __restrict__ out_row, double* __restrict__ value3,
+           const double* __restrict__ y_in, double fac, double* __restrict__ y_out) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= np) return;
     Stencil s = make_stencil(g, x, p);
@@ -117,9 +118,16 @@ k_readout3(Geo g, const double* __restrict__ fa, const double* __restrict__ fb,
     const double c = gather_value(s, fc);
     // out_row: the layout's slot -> home row map (Layout.gather fused into the readout)
     const long long o = out_row ? (long long)__ldg(out_row + p) : p;
-    value3[3 * o + 0] = a;
-    value3[3 * o + 1] = b;
-    value3[3 * o + 2] = c;
+    if (value3) {
+        value3[3 * o + 0] = a;
+        value3[3 * o + 1] = b;
+        value3[3 * o + 2] = c;
+    }
+    if (y_out) {   // the kick that consumes the force: y_out = y_in + fac * value (one FMA each)
+        y_out[3 * o + 0] = fma(fac, a, __ldg(y_in + 3 * o + 0));
+        y_out[3 * o + 1] = fma(fac, b, __ldg(y_in + 3 * o + 1));
+        y_out[3 * o + 2] = fma(fac, c, __ldg(y_in + 3 * o + 2));
+    }
 }
 
 template <bool HAS_W, bool WANT_VALUE>
@@ -147,7 +155,8 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
                 const double* __restrict__ F2, const double* __restrict__ R,
                 const double* __restrict__ x, const double* __restrict__ w3, long long np,
                 const int* __restrict__ out_row, const double* __restrict__ base,
-                double* __restrict__ grad) {
+                double* __restrict__ grad, const double* __restrict__ y_in, double fac,
+                double* __restrict__ y_out) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= np) return;
     Stencil s = make_stencil(g, x, p);
@@ -190,6 +199,11 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
     grad[3 * o + 0] = a0;
     grad[3 * o + 1] = a1;
     grad[3 * o + 2] = a2;
+    if (y_out) {   // the drift's momentum cotangent: y_out = y_in + fac * grad
+        y_out[3 * o + 0] = fma(fac, a0, __ldg(y_in + 3 * o + 0));
+        y_out[3 * o + 1] = fma(fac, a1, __ldg(y_in + 3 * o + 1));
+        y_out[3 * o + 2] = fma(fac, a2, __ldg(y_in + 3 * o + 2));
+    }
 }
 
 template <bool HAS_FDOT, bool HAS_XDOT>
@@ -232,14 +246,15 @@ int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const d
 
 int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                  const double* f2, const double* x, int64_t np, const int32_t* out_row,
-                 double* value3) {
+                 double* value3, const double* y_in, double fac, double* y_out) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
-        VPM_REQUIRE(f0 && f1 && f2 && x && value3, "NULL array");
+        VPM_REQUIRE(f0 && f1 && f2 && x && (value3 || y_out), "NULL array");
+        VPM_REQUIRE(!y_out || y_in, "y_out needs y_in");
         VPM_LAUNCH(k_readout3, (unsigned)ceil_div(np, 256), 256, 0, ctx->stream, g, f0, f1, f2, x,
-                   (long long)np, out_row, value3);
+                   (long long)np, out_row, value3, y_in, fac, y_out);
     }
     VPM_API_END
 }
@@ -264,14 +279,16 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, co
 
 int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                       const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, const int32_t* out_row, const double* base, double* grad) {
+                      int64_t np, const int32_t* out_row, const double* base, double* grad,
+                      const double* y_in, double fac, double* y_out) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
         VPM_REQUIRE(f0 && f1 && f2 && r && x && w3 && grad, "NULL array");
+        VPM_REQUIRE(!y_out || y_in, "y_out needs y_in");
         VPM_LAUNCH(k_readout_grad4, (unsigned)ceil_div(np, 256), 256, 0, ctx->stream, g, f0, f1, f2, r,
-                   x, w3, (long long)np, out_row, base, grad);
+                   x, w3, (long long)np, out_row, base, grad, y_in, fac, y_out);
     }
     VPM_API_END
 }

@@ -523,7 +523,7 @@ def _leapfrog_body(dx, p, stages, pt, force_fn, fused=False, stage_fn=None):
         ac = (ai * af) ** 0.5
         c = closing[i] + (opening[i + 1] if i + 1 < len(pairs) else 0.0)
         if stage_fn is not None:
-            dx, p, f, potk = stage_fn(dx, p, DriftFactor(pt, ai, ac, af), c)
+            dx, p, f, potk = stage_fn(dx, p, DriftFactor(pt, ai, ac, af), c, i + 1 == len(pairs))
             continue
         dx = drift(dx, p, DriftFactor(pt, ai, ac, af))
         f, potk = force_fn(dx)
@@ -537,7 +537,7 @@ def leapfrog(dx_i, p_i, q, stages, pt, pm):
     q = _localize(q, pm)
     if _fusable(pm):
         return _leapfrog_body(dx_i, p_i, stages, pt, lambda dx: force(dx, q, pm), fused=True,
-                              stage_fn=(lambda dx, p, cd, ck: drift_force_kick(dx, p, cd, ck, q, pm))
+                              stage_fn=(lambda dx, p, cd, ck, last: drift_force_kick(dx, p, cd, ck, q, pm, want_f=last))
                               if USE_FUSED_STAGE else None)
     return _leapfrog_body(dx_i, p_i, stages, pt, lambda dx: gravity(dx, q, pm))
 
@@ -627,7 +627,7 @@ class FastPMSimulation(object):
         if _fusable(self.fpm):
             return _leapfrog_body(dx, p, self.stages, self.pt,
                                   lambda dx: force(dx, self.q, self.fpm), fused=True,
-                                  stage_fn=(lambda dx, p, cd, ck: drift_force_kick(dx, p, cd, ck, self.q, self.fpm))
+                                  stage_fn=(lambda dx, p, cd, ck, last: drift_force_kick(dx, p, cd, ck, self.q, self.fpm, want_f=last))
                                   if USE_FUSED_STAGE else None)
         return _leapfrog_body(dx, p, self.stages, self.pt, lambda dx: self.gravity(dx))
 
@@ -692,23 +692,24 @@ class drift_force_kick:
     ain = [('dx', 'ndarray'), ('p', 'ndarray')]
     aout = [('dx1', 'ndarray'), ('p1', 'ndarray'), ('f', 'ndarray'), ('potk', 'ComplexField')]
 
-    def apl(node, dx, p, cd, ck, q, pm):
+    def apl(node, dx, p, cd, ck, q, pm, want_f=True):
         from .. import pm as dev
         dx1, x1 = dev.drift_pos(pm, dx, p, cd, q)
-        f, potk, state = dev.force_apl(pm, dx1, q, x=x1)
-        return dict(dx1=dx1, p1=_axpy(p, f, ck), f=f, potk=potk, state=state)
+        # the kick rides on the store of the force readout; a stage whose force nobody reads
+        # (every stage but the last) does not write it at all
+        f, potk, state, p1 = dev.force_apl(pm, dx1, q, x=x1, kick=(p, ck), want_f=want_f)
+        return dict(dx1=dx1, p1=p1, f=f if f is not None else 0, potk=potk, state=state)
 
     def vjp(node, _dx1, _p1, _f, _potk, state, cd, ck, pm):
         from .. import pm as dev
-        # f feeds p1 (factor ck) and is an output itself
+        # f feeds p1 (factor ck) and is an output itself; g = cotangent of dx1 from both of its
+        # consumers; dx1 = dx + cd p, so _p = _p1 + cd g comes out of the same kernel
         if _is_zero(_p1):
-            g = dev.force_vjp(pm, state, _f, _potk, base=_dx1)
+            g, _p = dev.force_vjp(pm, state, _f, _potk, base=_dx1, update=(_p1, cd))
         elif _is_zero(_f):
-            g = dev.force_vjp(pm, state, _p1, _potk, f_scale=ck, base=_dx1)
+            g, _p = dev.force_vjp(pm, state, _p1, _potk, f_scale=ck, base=_dx1, update=(_p1, cd))
         else:
-            g = dev.force_vjp(pm, state, _axpy(_f, _p1, ck), _potk, base=_dx1)
-        # g = cotangent of dx1 (both consumers); dx1 = dx + cd p
-        _p = g * cd if _is_zero(_p1) else _axpy(_p1, g, cd)
+            g, _p = dev.force_vjp(pm, state, _axpy(_f, _p1, ck), _potk, base=_dx1, update=(_p1, cd))
         return dict(_dx=g, _p=_p)
 
     def jvp(node, dx_, p_, state, cd, ck, pm):

@@ -1301,24 +1301,40 @@ class ParticleMesh(object):
             r = layout.gather(r)
         return r
 
-    def readout3(self, f0, f1, f2, pos, gather=None):
+    def readout3(self, f0, f1, f2, pos, gather=None, kick=None, want_value=True):
         """Three fields read at once into ``[Np, 3]`` (readout x3 + linalg.stack fused).
         ``gather``: a one-rank Layout whose ``gather`` is fused into the store (rows land in
-        home order); a cross-rank layout gathers afterwards."""
+        home order); a cross-rank layout gathers afterwards.  ``kick=(y, fac)``: also return
+        ``y + fac * value`` (in home order), computed in the same store when the gather is fused;
+        ``want_value=False`` then skips the value itself.  Returns ``value`` or
+        ``(value or None, y + fac * value)``."""
         rt = self.rt
         pos = asdevice(pos)
         _, x3 = self._pos3(pos)
         rt.sync_stream()
         n = x3.shape[0]
         fused = isinstance(gather, Layout) and gather.newlength == n == gather.oldlength
+        if kick is not None and fused:
+            y = asdevice(kick[0])
+            val = rt.empty((n, 3)) if want_value else None
+            yo = rt.empty((n, 3))
+            C.check(C.lib.vpm_readout3(rt.ctx, ctypes.byref(self._mesh), _ptr(f0.t), _ptr(f1.t), _ptr(f2.t),
+                                       _ptr(x3), n, _ptr(gather.indices), _ptr(val), _ptr(y.t), float(kick[1]),
+                                       _ptr(yo)))
+            return (DeviceArray(val) if want_value else None), DeviceArray(yo)
         val = rt.empty((n, 3))
         C.check(C.lib.vpm_readout3(rt.ctx, ctypes.byref(self._mesh), _ptr(f0.t), _ptr(f1.t),
                                    _ptr(f2.t), _ptr(x3), n, _ptr(gather.indices) if fused else None,
-                                   _ptr(val)))
+                                   _ptr(val), None, 0.0, None))
         if fused:
-            return DeviceArray(val)
-        r = DeviceArray(val, cellindex=pos._cellindex)
-        return gather.gather(r) if gather is not None else r
+            r = DeviceArray(val)
+        else:
+            r = DeviceArray(val, cellindex=pos._cellindex)
+            if gather is not None:
+                r = gather.gather(r)
+        if kick is not None:
+            return r, asdevice(kick[0])._axpby(1.0, float(kick[1]), r.t)
+        return r
 
     def _readout_vjp(self, field, pos, v, layout):
         rt = self.rt
@@ -1710,9 +1726,11 @@ def drift_pos(pm, dx, p, fac, q):
     return DeviceArray(dx1), DeviceArray(x1)
 
 
-def force_apl(pm, dx, q, x=None):
+def force_apl(pm, dx, q, x=None, kick=None, want_f=True):
     """f = -grad laplace^-1 (rho Nc / Np) read out at x = q + dx; returns (f, potk, state).
-    ``x``: the positions when the caller already has them (fused drift)."""
+    ``x``: the positions when the caller already has them (fused drift).  ``kick=(p, fac)``:
+    returns ``(f, potk, state, p + fac f)`` with the kick folded into the force readout;
+    ``want_f=False`` then returns ``f = None`` (a stage whose force nobody reads)."""
     if pm.ndim != 3:
         raise ValueError("the fused force operator is 3-D only")
     rt = pm.rt
@@ -1732,22 +1750,31 @@ def force_apl(pm, dx, q, x=None):
         potk = pm._transfer(rhok, scale=scale, laplace=True)
         phi = pm._c2r(potk, 1.0)                               # potk is an output: preserved
         F = _fd4(pm, phi)
-        f = pm.readout3(F[0], F[1], F[2], xl, gather=layout)
-        return f, potk, ForceState(xl, layout, None, None, phi, scale, tabs)
+        st = ForceState(xl, layout, None, None, phi, scale, tabs)
+        if kick is not None:
+            f, p1 = pm.readout3(F[0], F[1], F[2], xl, gather=layout, kick=kick, want_value=want_f)
+            return f, potk, st, p1
+        return pm.readout3(F[0], F[1], F[2], xl, gather=layout), potk, st
     potk, g = pm.force_kspace(rhok, scale, tabs, want_p=True)
     if pm.P > 1:
         F = pm._c2r_slab_many(g, 1.0)                  # three inverse transforms, one all-to-all
     else:
         F = [pm._c2r(gd, 1.0, consume=True) for gd in g]   # g are temporaries of this call
-    f = pm.readout3(F[0], F[1], F[2], xl, gather=layout)
     if getattr(pm, 'force_recompute', False):
         # trade 3 inverse FFTs in the reverse sweep for 2/3 of the mesh memory on the tape
-        return f, potk, ForceState(xl, layout, None, potk, None, scale, tabs)
-    return f, potk, ForceState(xl, layout, F, None, None, scale, tabs)
+        st = ForceState(xl, layout, None, potk, None, scale, tabs)
+    else:
+        st = ForceState(xl, layout, F, None, None, scale, tabs)
+    if kick is not None:
+        f, p1 = pm.readout3(F[0], F[1], F[2], xl, gather=layout, kick=kick, want_value=want_f)
+        return f, potk, st, p1
+    return pm.readout3(F[0], F[1], F[2], xl, gather=layout), potk, st
 
 
-def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None):
+def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None, update=None):
     """reverse sweep of force_apl: cotangents of (f, potk) -> cotangent of dx.
+    ``update=(y, fac)``: returns ``(g, y + fac g)`` (y may be a zero literal), the second array
+    written by the same kernel when the layout is one-rank.
     ``f_scale``: the force cotangent is ``f_scale * _f`` (the factor of the kick it comes from,
     applied while exchanging); ``base``: added to the result (the cotangent reaching dx from its
     other consumers), inside the store of the last kernel where possible."""
@@ -1799,17 +1826,31 @@ def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None):
     g = rt.empty((n, 3))
     if base is not None and _is_zero_literal(base):
         base = None
-    if one_rank:        # gather (and the accumulation of `base`) in the store
+    y = fac = None
+    if update is not None:
+        y, fac = update
+        y = None if _is_zero_literal(y) else asdevice(y)
+    if one_rank:        # gather, the accumulation of `base` and the update of `y` in the store
         bt = asdevice(base).t if base is not None else None
+        yo = rt.empty((n, 3)) if y is not None else None
         C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
                                         _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
-                                        _ptr(lay.indices), _ptr(bt), _ptr(g)))
-        return DeviceArray(g)
+                                        _ptr(lay.indices), _ptr(bt), _ptr(g),
+                                        _ptr(y.t) if y is not None else None,
+                                        float(fac) if y is not None else 0.0, _ptr(yo)))
+        out = DeviceArray(g)
+        if update is None:
+            return out
+        return out, (DeviceArray(yo) if y is not None else out * float(fac))
     C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
                                     _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
-                                    None, None, _ptr(g)))
+                                    None, None, _ptr(g), None, 0.0, None))
     out = lay.gather(DeviceArray(g))
-    return out + asdevice(base) if base is not None else out
+    if base is not None:
+        out = out + asdevice(base)
+    if update is None:
+        return out
+    return out, (y._axpby(1.0, float(fac), out.t) if y is not None else out * float(fac))
 
 
 def force_jvp(pm, st, dx_):
