@@ -447,13 +447,42 @@ def induce_correlation(wnk, powerspectrum, pm):
     return dict(c=apply_transfer(wnk, tf))
 
 
+@operator
+class lpt1_at_constant_q:
+    """``lpt1`` (fastpm.py:336-351) for the case every caller in the library has -- ``q`` a
+    constant of the graph -- as ONE operator: Green's function, ONE inverse FFT of the potential,
+    the real-space 4-point stencil that ``fourier_space_neg_gradient(order=1)`` is the symbol of,
+    and the three-mesh readout, instead of 4 transfers + 3 inverse FFTs + 3 readouts + stack
+    (13 nodes).  One-GPU device backend; ``lpt1`` is the portable graph."""
+    ain = {'rhok': 'ComplexField'}
+    aout = {'dx1': 'ndarray'}
+
+    def apl(node, rhok, q, pm):
+        from .. import pm as dev
+        dx1, state = dev.lpt1_apl(pm, rhok, q)
+        return dict(dx1=dx1, state=state)
+
+    def vjp(node, _dx1, state, pm):
+        from .. import pm as dev
+        return dict(_rhok=dev.lpt1_vjp(pm, state, _dx1))
+
+    def jvp(node, rhok_, state, pm):
+        from .. import pm as dev
+        return dict(dx1_=dev.lpt1_jvp(pm, state, rhok_))
+
+
 @autooperator('rhok->dx1,dx2')
 def lpt(rhok, q, pm):
     """fastpm.py:398-406"""
     q = _localize(q, pm)
-    dx1 = lpt1(rhok, q, pm)
+    one = lpt1
+    if _fusable(pm) and USE_FUSED_STAGE:
+        from .. import pm as dev
+        if dev._use_stencil(pm):
+            one = lpt1_at_constant_q
+    dx1 = one(rhok, q, pm)
     rhok2 = r2c(lpt2src(rhok, pm))
-    dx2 = lpt1(rhok2, q, pm)
+    dx2 = one(rhok2, q, pm)
     return dict(dx1=dx1, dx2=dx2)
 
 
@@ -647,7 +676,7 @@ def set_fused(flag, stage=True):
     global USE_FUSED, USE_FUSED_STAGE
     USE_FUSED = bool(flag)
     USE_FUSED_STAGE = bool(stage)
-    for op in (leapfrog, nbody, FastPMSimulation.run):
+    for op in (leapfrog, nbody, lpt, firststep, FastPMSimulation.run, FastPMSimulation.firststep):
         op._model_cache.clear()
 
 

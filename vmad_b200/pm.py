@@ -1853,6 +1853,42 @@ def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None, update=None):
     return out, (y._axpby(1.0, float(fac), out.t) if y is not None else out * float(fac))
 
 
+def lpt1_apl(pm, rhok, q):
+    """Zel'dovich displacement (fastpm.py:336-351) read out at the constant positions ``q``:
+    ONE inverse FFT of the potential + the 4-point stencil (the Fourier symbol of
+    fourier_space_neg_gradient(order=1), as in force_apl) + the three-mesh readout; the layout
+    and the sorted copy of ``q`` are cached with ``q``.  Returns ``(dx1, state)``."""
+    q = asdevice(q)
+    layout = pm.decompose(q)
+    xl = layout.exchange(q)
+    phi = pm._c2r(pm._transfer(pm._as_field(rhok, True), scale=1.0, laplace=True), 1.0, consume=True)
+    F = _fd4(pm, phi)
+    return pm.readout3(F[0], F[1], F[2], xl, gather=layout), (layout, xl)
+
+
+def lpt1_vjp(pm, state, _dx1):
+    """cotangent of dx1 -> cotangent of rhok (``q`` is a constant here)"""
+    rt = pm.rt
+    layout, xl = state
+    _fl = layout.exchange(asdevice(_dx1))
+    Fbar = pm.paint_cols3(xl, _fl)
+    phibar = rt.empty(pm.rshape)
+    C.check(C.lib.vpm_fd4_neg_gradient_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(Fbar[0].t),
+                                               _ptr(Fbar[1].t), _ptr(Fbar[2].t), _ptr(phibar)))
+    del Fbar
+    # c2r.vjp of the un-normalised inverse is the un-normalised forward transform
+    return pm._transfer(pm._r2c(RealField(pm, phibar), 1.0), scale=1.0, laplace=True)
+
+
+def lpt1_jvp(pm, state, rhok_):
+    if _is_zero_literal(rhok_):
+        return 0
+    layout, xl = state
+    phi_ = pm._c2r(pm._transfer(pm._as_field(rhok_, True), scale=1.0, laplace=True), 1.0, consume=True)
+    F_ = _fd4(pm, phi_)
+    return pm.readout3(F_[0], F_[1], F_[2], xl, gather=layout)
+
+
 def force_jvp(pm, st, dx_):
     """forward-mode sweep of force_apl: tangent of dx -> tangents of (f, potk)"""
     rt = pm.rt
