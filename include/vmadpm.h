@@ -315,6 +315,19 @@ int vpm_fd4_neg_gradient(vpm_ctx* ctx, const int64_t n[3], const double h[3], co
 int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3],
                                  const double* f0, const double* f1, const double* f2,
                                  double* phibar);
+/* Second-order LPT source (fastpm.py:353-387) in real space.  With f_j = -D_j phi (the output of
+ * vpm_fd4_neg_gradient) the second derivatives are P_ij = -D_i f_j and
+ *   source = 3/7 (P11 P22 + P22 P00 + P00 P11 - P12^2 - P20^2 - P01^2) = 1/2 B(f, f);
+ * out = scale * B(f, g), B the symmetric bilinear form dsource(f)[g]; g0 = g1 = g2 = NULL means
+ * g = f.  Value: g = NULL, scale = 0.5; tangent: g = f_, scale = 1.  Replaces six inverse FFTs
+ * and thirteen transfers of the reference graph. */
+int vpm_lpt2_source(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* f0,
+                    const double* f1, const double* f2, const double* g0, const double* g1,
+                    const double* g2, double scale, double* out);
+/* its adjoint: cotangent sbar of the source -> cotangents fb_j of f_j (work6: 6 meshes of scratch) */
+int vpm_lpt2_source_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* f0,
+                            const double* f1, const double* f2, const double* sbar, double* work6,
+                            double* fb0, double* fb1, double* fb2);
 
 /* ---- elementwise and reductions on flat fp64 arrays (the stdlib arithmetic that
  *      vmad applies to fields / particle arrays: vmad/core/stdlib/operators.py:14-152;

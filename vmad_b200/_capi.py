@@ -114,6 +114,8 @@ SIGNATURES = {
                                      _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
+    'vpm_lpt2_source': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, c_double, _P]),
+    'vpm_lpt2_source_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, _P, _P]),
     'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),
     'vpm_drift_pos': (c_int, [c_void_p, c_int64, _P, _P, c_double, _P, _P, _P]),
     'vpm_mul': (c_int, [c_void_p, c_int64, _P, _P, _P]),

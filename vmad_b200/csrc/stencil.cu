@@ -91,6 +91,118 @@ k_fd4_adjoint(Grid3 g, const double* __restrict__ F0, const double* __restrict__
     phibar[e] = acc;
 }
 
+// ---- second-order LPT source in real space ------------------------------------------------
+// lpt2src (fastpm.py:353-387) needs the six second derivatives P_ij = c2r(neg_grad_i neg_grad_j
+// potk) = D_i D_j phi: six inverse FFTs and thirteen transfers in the reference graph.  With
+// F_j = -D_j phi already on the mesh (k_fd4_grad3), P_ij = -D_i F_j is one more stencil, and
+//   source = 3/7 (P11 P22 + P22 P00 + P00 P11 - P12^2 - P20^2 - P01^2) = 1/2 B(F, F)
+// with the symmetric bilinear form B(F, G) = dsource(F)[G]: ONE kernel serves the value
+// (G = F, scale 1/2) and the tangent (G = F_, scale 1).
+struct Cell3 {
+    int x, y, z;
+};
+
+__device__ __forceinline__ Cell3 cell_of(const Grid3& g, long long e) {
+    Cell3 c;
+    c.z = (int)(e % g.n2);
+    const long long r = e / g.n2;
+    c.y = (int)(r % g.n1);
+    c.x = (int)(r / g.n1);
+    return c;
+}
+
+// (D_axis f)(cell)
+template <int AXIS>
+__device__ __forceinline__ double dax(const Grid3& g, const double* __restrict__ f, const Cell3& c) {
+    const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
+    if (AXIS == 2) {
+        const double* row = f + (long long)c.x * s0 + (long long)c.y * s1;
+        const double a = __ldg(row + wrapi(c.z + 1, g.n2)) - __ldg(row + wrapi(c.z - 1, g.n2));
+        const double b = __ldg(row + wrapi(c.z + 2, g.n2)) - __ldg(row + wrapi(c.z - 2, g.n2));
+        return (8.0 * a - b) * g.c2;
+    } else if (AXIS == 1) {
+        const double* col = f + (long long)c.x * s0 + c.z;
+        const double a = __ldg(col + wrapi(c.y + 1, g.n1) * s1) - __ldg(col + wrapi(c.y - 1, g.n1) * s1);
+        const double b = __ldg(col + wrapi(c.y + 2, g.n1) * s1) - __ldg(col + wrapi(c.y - 2, g.n1) * s1);
+        return (8.0 * a - b) * g.c1;
+    } else {
+        const double* pil = f + (long long)c.y * s1 + c.z;
+        const double a = __ldg(pil + wrapi(c.x + 1, g.n0) * s0) - __ldg(pil + wrapi(c.x - 1, g.n0) * s0);
+        const double b = __ldg(pil + wrapi(c.x + 2, g.n0) * s0) - __ldg(pil + wrapi(c.x - 2, g.n0) * s0);
+        return (8.0 * a - b) * g.c0;
+    }
+}
+
+struct Hess {
+    double p00, p11, p22, p12, p20, p01;
+};
+
+// P_ij = -D_i F_j
+__device__ __forceinline__ Hess hessian(const Grid3& g, const double* __restrict__ F0,
+                                        const double* __restrict__ F1,
+                                        const double* __restrict__ F2, const Cell3& c) {
+    Hess h;
+    h.p00 = -dax<0>(g, F0, c);
+    h.p11 = -dax<1>(g, F1, c);
+    h.p22 = -dax<2>(g, F2, c);
+    h.p12 = -dax<1>(g, F2, c);
+    h.p20 = -dax<2>(g, F0, c);
+    h.p01 = -dax<0>(g, F1, c);
+    return h;
+}
+
+// out = scale * B(F, G);  SAME: G is F (the value, scale 1/2)
+template <bool SAME>
+__global__ void __launch_bounds__(256)
+k_lpt2_bilinear(Grid3 g, const double* __restrict__ F0, const double* __restrict__ F1,
+                const double* __restrict__ F2, const double* __restrict__ G0,
+                const double* __restrict__ G1, const double* __restrict__ G2, double scale,
+                double* __restrict__ out) {
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const Cell3 c = cell_of(g, e);
+    const Hess p = hessian(g, F0, F1, F2, c);
+    const Hess q = SAME ? p : hessian(g, G0, G1, G2, c);
+    const double diag = p.p11 * q.p22 + q.p11 * p.p22 + p.p22 * q.p00 + q.p22 * p.p00 +
+                        p.p00 * q.p11 + q.p00 * p.p11;
+    const double off = p.p12 * q.p12 + p.p20 * q.p20 + p.p01 * q.p01;
+    out[e] = scale * ((3.0 / 7.0) * diag - (6.0 / 7.0) * off);
+}
+
+// reverse sweep, first half: W_ij = dsource/dP_ij * sbar  (six meshes, W = [00, 11, 22, 12, 20, 01])
+__global__ void __launch_bounds__(256)
+k_lpt2_adjoint_w(Grid3 g, const double* __restrict__ F0, const double* __restrict__ F1,
+                 const double* __restrict__ F2, const double* __restrict__ sbar,
+                 double* __restrict__ W) {
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const Cell3 c = cell_of(g, e);
+    const Hess p = hessian(g, F0, F1, F2, c);
+    const double s = sbar[e];
+    W[e] = (3.0 / 7.0) * (p.p11 + p.p22) * s;
+    W[total + e] = (3.0 / 7.0) * (p.p22 + p.p00) * s;
+    W[2 * total + e] = (3.0 / 7.0) * (p.p00 + p.p11) * s;
+    W[3 * total + e] = -(6.0 / 7.0) * p.p12 * s;
+    W[4 * total + e] = -(6.0 / 7.0) * p.p20 * s;
+    W[5 * total + e] = -(6.0 / 7.0) * p.p01 * s;
+}
+
+// second half: P_ij = -D_i F_j  =>  Fbar_j = sum_i D_i W_ij
+//   Fbar_0 = D_0 W00 + D_2 W20,  Fbar_1 = D_1 W11 + D_0 W01,  Fbar_2 = D_2 W22 + D_1 W12
+__global__ void __launch_bounds__(256)
+k_lpt2_adjoint_f(Grid3 g, const double* __restrict__ W, double* __restrict__ Fb0,
+                 double* __restrict__ Fb1, double* __restrict__ Fb2) {
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const Cell3 c = cell_of(g, e);
+    Fb0[e] = dax<0>(g, W, c) + dax<2>(g, W + 4 * total, c);
+    Fb1[e] = dax<1>(g, W + total, c) + dax<0>(g, W + 5 * total, c);
+    Fb2[e] = dax<2>(g, W + 2 * total, c) + dax<1>(g, W + 3 * total, c);
+}
+
 static Grid3 make_grid(const int64_t n[3], const double h[3]) {
     VPM_REQUIRE(n && h, "NULL argument");
     Grid3 g;
@@ -124,6 +236,35 @@ int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double 
     Grid3 g = make_grid(n, h);
     const long long total = (long long)g.n0 * g.n1 * g.n2;
     VPM_LAUNCH(k_fd4_adjoint, (unsigned)ceil_div(total, 256), 256, 0, ctx->stream, g, f0, f1, f2, phibar);
+    VPM_API_END
+}
+
+int vpm_lpt2_source(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* f0,
+                    const double* f1, const double* f2, const double* g0, const double* g1,
+                    const double* g2, double scale, double* out) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && f0 && f1 && f2 && out, "NULL argument");
+    VPM_REQUIRE((g0 && g1 && g2) || (!g0 && !g1 && !g2), "pass all of g0, g1, g2 or none");
+    Grid3 g = make_grid(n, h);
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    const unsigned grid = (unsigned)ceil_div(total, 256);
+    if (g0)
+        VPM_LAUNCH(k_lpt2_bilinear<false>, grid, 256, 0, ctx->stream, g, f0, f1, f2, g0, g1, g2, scale, out);
+    else
+        VPM_LAUNCH(k_lpt2_bilinear<true>, grid, 256, 0, ctx->stream, g, f0, f1, f2, f0, f1, f2, scale, out);
+    VPM_API_END
+}
+
+int vpm_lpt2_source_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* f0,
+                            const double* f1, const double* f2, const double* sbar, double* work6,
+                            double* fb0, double* fb1, double* fb2) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && f0 && f1 && f2 && sbar && work6 && fb0 && fb1 && fb2, "NULL argument");
+    Grid3 g = make_grid(n, h);
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    const unsigned grid = (unsigned)ceil_div(total, 256);
+    VPM_LAUNCH(k_lpt2_adjoint_w, grid, 256, 0, ctx->stream, g, f0, f1, f2, sbar, work6);
+    VPM_LAUNCH(k_lpt2_adjoint_f, grid, 256, 0, ctx->stream, g, work6, fb0, fb1, fb2);
     VPM_API_END
 }
 

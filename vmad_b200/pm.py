@@ -1711,7 +1711,7 @@ def _force_tables(pm, order=1):
 def _use_stencil(pm):
     """the real-space gradient needs +-2 planes of neighbours: single slab only (a slab
     decomposition would need a halo exchange; it keeps the k-space gradients)"""
-    return pm.P == 1 and getattr(pm, 'force_stencil', True) and min(pm.rshape) >= 1
+    return pm.P == 1 and getattr(pm, 'force_stencil', True) and min(pm.rshape) >= 2
 
 
 def drift_pos(pm, dx, p, fac, q):
@@ -1887,6 +1887,55 @@ def lpt1_jvp(pm, state, rhok_):
     phi_ = pm._c2r(pm._transfer(pm._as_field(rhok_, True), scale=1.0, laplace=True), 1.0, consume=True)
     F_ = _fd4(pm, phi_)
     return pm.readout3(F_[0], F_[1], F_[2], xl, gather=layout)
+
+
+def _lpt2_potential(pm, rhok):
+    """phi = c2r(laplace rhok) and the three meshes F_j = -D_j phi"""
+    phi = pm._c2r(pm._transfer(pm._as_field(rhok, True), scale=1.0, laplace=True), 1.0, consume=True)
+    return phi, _fd4(pm, phi)
+
+
+def _lpt2_bilinear(pm, F, G, scale):
+    rt = pm.rt
+    rt.sync_stream()
+    out = rt.empty(pm.rshape)
+    g = [None, None, None] if G is None else [_ptr(t.t) for t in G]
+    C.check(C.lib.vpm_lpt2_source(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(F[0].t), _ptr(F[1].t), _ptr(F[2].t),
+                                  g[0], g[1], g[2], float(scale), _ptr(out)))
+    return RealField(pm, out)
+
+
+def lpt2src_apl(pm, rhok):
+    """source of the second-order displacement (fastpm.py:353-387) from ONE inverse FFT: the six
+    second derivatives are stencils of the gradient meshes (csrc/stencil.cu).  Returns
+    ``(source, state)``; only the potential stays on the tape."""
+    phi, F = _lpt2_potential(pm, rhok)
+    return _lpt2_bilinear(pm, F, None, 0.5), phi
+
+
+def lpt2src_vjp(pm, phi, _src):
+    rt = pm.rt
+    sbar = pm._as_field(_src, False)
+    F = _fd4(pm, phi)
+    rt.sync_stream()
+    work = rt.empty((6,) + tuple(pm.rshape))
+    Fb = [rt.empty(pm.rshape) for _ in range(3)]
+    C.check(C.lib.vpm_lpt2_source_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(F[0].t), _ptr(F[1].t),
+                                          _ptr(F[2].t), _ptr(sbar.t), _ptr(work), _ptr(Fb[0]), _ptr(Fb[1]),
+                                          _ptr(Fb[2])))
+    del work, F
+    phibar = rt.empty(pm.rshape)
+    C.check(C.lib.vpm_fd4_neg_gradient_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(Fb[0]), _ptr(Fb[1]),
+                                               _ptr(Fb[2]), _ptr(phibar)))
+    del Fb
+    return pm._transfer(pm._r2c(RealField(pm, phibar), 1.0), scale=1.0, laplace=True)
+
+
+def lpt2src_jvp(pm, phi, rhok_):
+    if _is_zero_literal(rhok_):
+        return 0
+    _, F_ = _lpt2_potential(pm, rhok_)
+    return _lpt2_bilinear(pm, _fd4(pm, phi), F_, 1.0)
 
 
 def force_jvp(pm, st, dx_):
