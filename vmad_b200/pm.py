@@ -1750,7 +1750,10 @@ def force_apl(pm, dx, q, x=None, kick=None, want_f=True):
         potk = pm._transfer(rhok, scale=scale, laplace=True)
         phi = pm._c2r(potk, 1.0)                               # potk is an output: preserved
         F = _fd4(pm, phi)
-        st = ForceState(xl, layout, None, None, phi, scale, tabs)
+        # small meshes: the three force meshes stay on the tape (24 B/cell) and the reverse sweep
+        # skips the stencil pass; large ones recompute them from the potential
+        keep = not getattr(pm, 'force_recompute', False) and 24 * phi.t.numel() <= (512 << 20)
+        st = ForceState(xl, layout, F if keep else None, None, phi, scale, tabs)
         if kick is not None:
             f, p1 = pm.readout3(F[0], F[1], F[2], xl, gather=layout, kick=kick, want_value=want_f)
             return f, potk, st, p1
