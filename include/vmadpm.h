@@ -257,6 +257,11 @@ typedef struct vpm_peer_sync {
 int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
                  int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
                  const vpm_peer_sync* sync);
+/* `count` contiguous complex128 elements (= 2 count doubles) to every rank whose bit is set in
+ * dest_mask, stored at element dst_off of its receive area (halo planes for the real-space
+ * stencils: the two boundary planes of a slab go to the neighbouring rank only); sync as above. */
+int vpm_peer_put_to(vpm_ctx* ctx, int nranks, uint32_t dest_mask, int64_t count, const double* src,
+                    const uint64_t* peer_bufs, int64_t dst_off, const vpm_peer_sync* sync);
 /* Particle rows (Layout.exchange / Layout.gather across ranks; replaces pmesh's MPI_Alltoallv):
  * pack and transfer in one kernel.  Position p of the routing order lies in segment d when
  * seg_start[d] <= p < seg_start[d+1] (host array, nranks+1) and is stored to row
@@ -315,6 +320,14 @@ int vpm_fd4_neg_gradient(vpm_ctx* ctx, const int64_t n[3], const double h[3], co
 int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3],
                                  const double* f0, const double* f1, const double* f2,
                                  double* phibar);
+/* the same two stencils on a slab: the inputs carry `pad` (>= 2) halo planes on each side of axis 0
+ * (n[0] + 2 pad planes; delivered by the neighbouring slabs), n[0] = local planes written; only f0
+ * needs valid halo planes in the adjoint. */
+int vpm_fd4_neg_gradient_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
+                              const double* phi_padded, double* f0, double* f1, double* f2);
+int vpm_fd4_neg_gradient_adjoint_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
+                                      const double* f0_padded, const double* f1_padded,
+                                      const double* f2_padded, double* phibar);
 /* Second-order LPT source (fastpm.py:353-387) in real space.  With f_j = -D_j phi (the output of
  * vpm_fd4_neg_gradient) the second derivatives are P_ij = -D_i f_j and
  *   source = 3/7 (P11 P22 + P22 P00 + P00 P11 - P12^2 - P20^2 - P01^2) = 1/2 B(f, f);

@@ -99,6 +99,8 @@ SIGNATURES = {
     'vpm_peer_free': (c_int, [c_void_p, c_void_p]),
     'vpm_peer_put': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, _P, POINTER(c_uint64), c_int64,
                              POINTER(vpm_peer_sync)]),
+    'vpm_peer_put_to': (c_int, [c_void_p, c_int, ctypes.c_uint32, c_int64, _P, POINTER(c_uint64), c_int64,
+                                POINTER(vpm_peer_sync)]),
     'vpm_peer_put_rows': (c_int, [c_void_p, c_int, c_int64, c_int, _P, _P, c_int, c_int, POINTER(c_int32),
                                   POINTER(c_int64), POINTER(c_uint64), POINTER(vpm_peer_sync)]),
     'vpm_peer_signal': (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_int64]),
@@ -114,6 +116,8 @@ SIGNATURES = {
                                      _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
+    'vpm_fd4_neg_gradient_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P]),
+    'vpm_fd4_neg_gradient_adjoint_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P]),
     'vpm_lpt2_source': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, c_double, _P]),
     'vpm_lpt2_source_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, _P, _P]),
     'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),

@@ -84,11 +84,14 @@ __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
 // grid = (chunks of a row, rows, peers): no index divisions, 16-byte coalesced loads / stores
 __global__ void __launch_bounds__(256)
 k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_dst,
-           const double2* __restrict__ src, PeerPtrs dst, long long dst_off, PeerSync sy) {
+           const double2* __restrict__ src, PeerPtrs dst, long long dst_off, unsigned mask,
+           PeerSync sy) {
     peer_acquire(P, sy);
     const int d = blockIdx.z;
     double2* __restrict__ out = reinterpret_cast<double2*>(dst.p[d]) + dst_off;
-    for (long long i = blockIdx.y; i < rows; i += gridDim.y) {
+    // destinations outside the mask get no data; their CTAs still take part in the flag protocol
+    const long long nrows = ((mask >> d) & 1u) ? rows : 0;
+    for (long long i = blockIdx.y; i < nrows; i += gridDim.y) {
         const double2* __restrict__ in = src + i * s_row + d * s_dst;
         double2* __restrict__ o = out + i * inner;
         // four independent 16-B loads in flight per thread before the (posted) stores
@@ -233,9 +236,25 @@ int vpm_peer_free(vpm_ctx* ctx, void* ptr) {
     VPM_API_END
 }
 
+static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
+                         int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
+                         unsigned mask, const vpm_peer_sync* sync);
+
 int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
                  int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
                  const vpm_peer_sync* sync) {
+    return peer_put_impl(ctx, nranks, rows, inner, s_row, s_dst, src, peer_bufs, dst_off, 0xffffffffu, sync);
+}
+
+int vpm_peer_put_to(vpm_ctx* ctx, int nranks, uint32_t dest_mask, int64_t count, const double* src,
+                    const uint64_t* peer_bufs, int64_t dst_off, const vpm_peer_sync* sync) {
+    // `count` contiguous complex128 elements to every rank in dest_mask, at dst_off of its area
+    return peer_put_impl(ctx, nranks, 1, count, 0, 0, src, peer_bufs, dst_off, dest_mask, sync);
+}
+
+static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
+                         int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
+                         unsigned mask, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx && src && peer_bufs && nranks >= 1 && nranks <= 8, "bad argument");
     const long long total = (long long)rows * inner * nranks;
@@ -247,7 +266,7 @@ int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t 
         dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nranks);
         VPM_LAUNCH(k_peer_put, grid, 256, 0, ctx->stream, nranks, (long long)rows, (long long)inner,
                    (long long)s_row, (long long)s_dst, reinterpret_cast<const double2*>(src),
-                   make_ptrs(nranks, peer_bufs), (long long)dst_off, make_sync(nranks, sync));
+                   make_ptrs(nranks, peer_bufs), (long long)dst_off, mask, make_sync(nranks, sync));
     }
     VPM_API_END
 }

@@ -15,8 +15,9 @@
 namespace vpm {
 
 struct Grid3 {
-    int n0, n1, n2;
+    int n0, n1, n2;     // cells written (n0 = local planes)
     double c0, c1, c2;  // 1 / (12 h_d)
+    int pad;            // inputs carry `pad` halo planes on each side of axis 0 (0: periodic wrap)
 };
 
 __device__ __forceinline__ int wrapi(int i, int n) {
@@ -25,7 +26,8 @@ __device__ __forceinline__ int wrapi(int i, int n) {
     return i;
 }
 
-// F_d = -D_d phi
+// F_d = -D_d phi.  phi has n0 + 2 pad planes; with pad > 0 the axis-0 neighbours are halo planes
+// delivered by the neighbouring slabs, with pad = 0 the axis wraps periodically.
 __global__ void __launch_bounds__(256)
 k_fd4_grad3(Grid3 g, const double* __restrict__ phi, double* __restrict__ F0,
             double* __restrict__ F1, double* __restrict__ F2) {
@@ -35,7 +37,8 @@ k_fd4_grad3(Grid3 g, const double* __restrict__ phi, double* __restrict__ F0,
     const int z = (int)(e % g.n2);
     const long long r = e / g.n2;
     const int y = (int)(r % g.n1);
-    const int x = (int)(r / g.n1);
+    const int x = (int)(r / g.n1) + g.pad;
+    const int nx = g.n0 + 2 * g.pad;
     const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
     const double* row = phi + (long long)x * s0 + (long long)y * s1;
     {
@@ -51,13 +54,14 @@ k_fd4_grad3(Grid3 g, const double* __restrict__ phi, double* __restrict__ F0,
     }
     {
         const double* pil = phi + (long long)y * s1 + z;
-        const double a = __ldg(pil + wrapi(x + 1, g.n0) * s0) - __ldg(pil + wrapi(x - 1, g.n0) * s0);
-        const double b = __ldg(pil + wrapi(x + 2, g.n0) * s0) - __ldg(pil + wrapi(x - 2, g.n0) * s0);
+        const double a = __ldg(pil + wrapi(x + 1, nx) * s0) - __ldg(pil + wrapi(x - 1, nx) * s0);
+        const double b = __ldg(pil + wrapi(x + 2, nx) * s0) - __ldg(pil + wrapi(x - 2, nx) * s0);
         F0[e] = -(8.0 * a - b) * g.c0;
     }
 }
 
-// phi_bar = sum_d D_d Fbar_d   (adjoint of k_fd4_grad3)
+// phi_bar = sum_d D_d Fbar_d   (adjoint of k_fd4_grad3).  The three inputs have n0 + 2 pad planes;
+// only Fbar_0 needs valid halo planes (the axis-0 difference).
 __global__ void __launch_bounds__(256)
 k_fd4_adjoint(Grid3 g, const double* __restrict__ F0, const double* __restrict__ F1,
               const double* __restrict__ F2, double* __restrict__ phibar) {
@@ -67,7 +71,8 @@ k_fd4_adjoint(Grid3 g, const double* __restrict__ F0, const double* __restrict__
     const int z = (int)(e % g.n2);
     const long long r = e / g.n2;
     const int y = (int)(r % g.n1);
-    const int x = (int)(r / g.n1);
+    const int x = (int)(r / g.n1) + g.pad;
+    const int nx = g.n0 + 2 * g.pad;
     const long long s1 = g.n2, s0 = (long long)g.n1 * g.n2;
     double acc;
     {
@@ -84,8 +89,8 @@ k_fd4_adjoint(Grid3 g, const double* __restrict__ F0, const double* __restrict__
     }
     {
         const double* pil = F0 + (long long)y * s1 + z;
-        const double a = __ldg(pil + wrapi(x + 1, g.n0) * s0) - __ldg(pil + wrapi(x - 1, g.n0) * s0);
-        const double b = __ldg(pil + wrapi(x + 2, g.n0) * s0) - __ldg(pil + wrapi(x - 2, g.n0) * s0);
+        const double a = __ldg(pil + wrapi(x + 1, nx) * s0) - __ldg(pil + wrapi(x - 1, nx) * s0);
+        const double b = __ldg(pil + wrapi(x + 2, nx) * s0) - __ldg(pil + wrapi(x - 2, nx) * s0);
         acc += (8.0 * a - b) * g.c0;
     }
     phibar[e] = acc;
@@ -209,6 +214,7 @@ static Grid3 make_grid(const int64_t n[3], const double h[3]) {
     for (int d = 0; d < 3; ++d) VPM_REQUIRE(n[d] >= 1 && n[d] < (1 << 20) && h[d] > 0, "bad grid");
     g.n0 = (int)n[0]; g.n1 = (int)n[1]; g.n2 = (int)n[2];
     g.c0 = 1.0 / (12.0 * h[0]); g.c1 = 1.0 / (12.0 * h[1]); g.c2 = 1.0 / (12.0 * h[2]);
+    g.pad = 0;
     return g;
 }
 
@@ -236,6 +242,34 @@ int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double 
     Grid3 g = make_grid(n, h);
     const long long total = (long long)g.n0 * g.n1 * g.n2;
     VPM_LAUNCH(k_fd4_adjoint, (unsigned)ceil_div(total, 256), 256, 0, ctx->stream, g, f0, f1, f2, phibar);
+    VPM_API_END
+}
+
+int vpm_fd4_neg_gradient_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
+                              const double* phi_padded, double* f0, double* f1, double* f2) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && phi_padded && f0 && f1 && f2, "NULL argument");
+    VPM_REQUIRE(pad == 0 || pad >= 2, "the stencil needs two halo planes per side");
+    Grid3 g = make_grid(n, h);
+    g.pad = pad;
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    if (total > 0)
+        VPM_LAUNCH(k_fd4_grad3, (unsigned)ceil_div(total, 256), 256, 0, ctx->stream, g, phi_padded, f0, f1, f2);
+    VPM_API_END
+}
+
+int vpm_fd4_neg_gradient_adjoint_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
+                                      const double* f0_padded, const double* f1_padded,
+                                      const double* f2_padded, double* phibar) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && phibar && f0_padded && f1_padded && f2_padded, "NULL argument");
+    VPM_REQUIRE(pad == 0 || pad >= 2, "the stencil needs two halo planes per side");
+    Grid3 g = make_grid(n, h);
+    g.pad = pad;
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    if (total > 0)
+        VPM_LAUNCH(k_fd4_adjoint, (unsigned)ceil_div(total, 256), 256, 0, ctx->stream, g, f0_padded, f1_padded,
+                   f2_padded, phibar);
     VPM_API_END
 }
 

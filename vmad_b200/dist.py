@@ -296,6 +296,13 @@ class PeerExchange(object):
                                    ct.c_void_p(src.data_ptr()), self.buf_ptrs[e % 2], int(dst_off),
                                    self._sync(e, first, last)))
 
+    def put_to(self, e, src_ptr, count, mask, dst_off, first, last):
+        """``count`` contiguous complex128 elements at device address ``src_ptr`` to the ranks in
+        ``mask`` (halo planes for the real-space stencils)"""
+        C, ct = self.C, self.ctypes
+        C.check(C.lib.vpm_peer_put_to(self._ctx(), self.P, int(mask), int(count), ct.c_void_p(int(src_ptr)),
+                                      self.buf_ptrs[e % 2], int(dst_off), self._sync(e, first, last)))
+
     def put_rows(self, e, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1):
         """particle rows to their destination ranks (vpm_peer_put_rows)"""
         C, ct = self.C, self.ctypes

@@ -502,7 +502,7 @@ def lpt(rhok, q, pm):
     one, src = lpt1, lpt2src
     if _fusable(pm) and USE_FUSED_STAGE:
         from .. import pm as dev
-        if dev._use_stencil(pm):
+        if dev._use_stencil(pm) and getattr(pm, 'P', 1) == 1:
             one, src = lpt1_at_constant_q, lpt2src_real_space
     dx1 = one(rhok, q, pm)
     rhok2 = r2c(src(rhok, pm))

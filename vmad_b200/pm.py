@@ -10,6 +10,7 @@ arithmetic happens in libvmadpm.so (hand-written sm_100a kernels + cuFFT) throug
 There is no CPU path: constructing a ParticleMesh without a CUDA device raises.
 """
 import ctypes
+import os
 import numbers
 import weakref
 
@@ -1146,7 +1147,7 @@ class ParticleMesh(object):
                                            x3.shape[0], _ptr(cs), _ptr(o)))
         return RealField(self, o)
 
-    def paint_cols3(self, xs, mass2d, layout=None):
+    def paint_cols3(self, xs, mass2d, layout=None, pad=0):
         """three paints of the columns of a sorted [n, 3] array (the mesh half of the vjp of the
         three force readouts, fastpm.py:256 x3) -> three RealFields; one pass over the particles
         with the block-gather algorithm"""
@@ -1155,6 +1156,16 @@ class ParticleMesh(object):
         rt.sync_stream()
         n = x3.shape[0]
         mt = mass2d.t
+        if pad:
+            # three slabs with `pad` halo planes on each side of axis 0 (the stencil adjoint reads
+            # the halo of the first one); the paint fills the interiors.  Returns the padded array.
+            n0l, N1, N2 = self.rshape
+            m3 = rt.empty((3, n0l + 2 * pad, N1, N2))
+            with _timed_paint(48.0 * n + 24.0 * n0l * N1 * N2, 'k_paint_agg3'):
+                C.check(C.lib.vpm_paint_sorted_cols3(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), _ptr(mt), 3, n,
+                                                     _ptr(self._cell_start_of(lay, x3)), _ptr(m3[0, pad]),
+                                                     m3[0].numel()))
+            return m3
         if _PAINT_ALGO in (0, 2):
             m3 = rt.empty((3,) + tuple(self.rshape))
             with _timed_paint(48.0 * n + 8.0 * m3.numel(), 'k_paint_agg3' if _PAINT_ALGO == 0 else 'k_paint_gather<3>'):
@@ -1539,7 +1550,9 @@ class ParticleMesh(object):
             out.append(RealField(self, o))
         return out
 
-    def _c2r_slab(self, cplx, scale, consume=False):
+    def _c2r_slab(self, cplx, scale, consume=False, out=None):
+        """``out``: a contiguous [n0l, N1, N2] tensor to receive the result (the interior of a
+        halo-padded array)"""
         rt = self.rt
         P = self.P
         n0l, N1, N2 = self.rshape
@@ -1556,7 +1569,7 @@ class ParticleMesh(object):
             a = rt.empty((n0l, N1, Nh), _C16)
             C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner, px.recv_ptr(b), _ptr(a)))
             px.release(e)
-            o = rt.empty(self.rshape)
+            o = rt.empty(self.rshape) if out is None else out
             C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
             return RealField(self, o)
         work = cplx.t if consume else cplx.t.clone()    # operators must not mutate their inputs
@@ -1564,9 +1577,31 @@ class ParticleMesh(object):
         recv = self.comm.alltoall_blocks(work.view(P, n0l, n1l, Nh))   # [P (column block), n0l, n1l, Nh]
         a = rt.empty((n0l, N1, Nh), _C16)
         C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, n1l * Nh, _ptr(recv), _ptr(a)))
-        o = rt.empty(self.rshape)
+        o = rt.empty(self.rshape) if out is None else out
         C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
         return RealField(self, o)
+
+    def _halo_fill(self, padded):
+        """fill the two halo planes on each side of a [n0l + 4, N1, N2] slab array from the
+        neighbouring ranks' boundary planes: two masked peer puts (my lower planes -> previous
+        rank's upper halo, my upper planes -> next rank's lower halo) + two small copies"""
+        rt = self.rt
+        px = self._peer()
+        n0l, N1, N2 = self.rshape
+        cnt = N1 * N2                       # two planes of doubles = N1 * N2 complex elements
+        plane = N1 * N2 * 8
+        prev, nxt = (self.rank - 1) % self.P, (self.rank + 1) % self.P
+        base = padded.data_ptr()
+        px.ensure(32 * cnt)
+        e, b = px.begin()
+        px.put_to(e, base + 2 * plane, cnt, 1 << prev, cnt, True, False)            # -> prev's HI slot
+        px.put_to(e, base + n0l * plane, cnt, 1 << nxt, 0, False, True)             # -> next's LO slot
+        rt.sync_stream()
+        lo = ctypes.c_void_p(base)
+        hi = ctypes.c_void_p(base + (n0l + 2) * plane)
+        C.check(C.lib.vpm_axpby(rt.ctx, 2 * cnt, 1.0, px.recv_ptr(b, 0), 0.0, None, 0.0, lo))
+        C.check(C.lib.vpm_axpby(rt.ctx, 2 * cnt, 1.0, px.recv_ptr(b, cnt), 0.0, None, 0.0, hi))
+        px.release(e)
 
     # -- k-space (fastpm.py:79,83,87) ---------------------------------------------------------------
     def _transfer(self, cplx, scale=1.0, laplace=False, tables=(None, None, None), conj=False):
@@ -1683,14 +1718,39 @@ def _h3(pm):
     return (ctypes.c_double * 3)(*[float(pm.BoxSize[d] / pm.Nmesh[d]) for d in range(3)])
 
 
+class _Padded(object):
+    """a slab array with two halo planes on each side of axis 0"""
+    __slots__ = ('t',)
+
+    def __init__(self, t):
+        self.t = t
+
+
 def _fd4(pm, phi):
     """F_d = -D_d phi: the three force meshes from the real potential (4-point stencil)"""
     rt = pm.rt
     rt.sync_stream()
     F = [rt.empty(pm.rshape) for _ in range(3)]
-    C.check(C.lib.vpm_fd4_neg_gradient(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(phi.t), _ptr(F[0]),
-                                       _ptr(F[1]), _ptr(F[2])))
+    if isinstance(phi, _Padded):
+        C.check(C.lib.vpm_fd4_neg_gradient_slab(rt.ctx, C.i3(pm.rshape), _h3(pm), 2, _ptr(phi.t), _ptr(F[0]),
+                                                _ptr(F[1]), _ptr(F[2])))
+    else:
+        C.check(C.lib.vpm_fd4_neg_gradient(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(phi.t), _ptr(F[0]),
+                                           _ptr(F[1]), _ptr(F[2])))
     return [RealField(pm, t) for t in F]
+
+
+def _potential(pm, potk, consume=False):
+    """the real potential c2r(potk) in the form the stencil wants: the periodic mesh on one rank,
+    the slab with its halo planes (one extra 0.5 MB exchange) on several"""
+    if pm.P == 1:
+        return pm._c2r(potk, 1.0, consume=consume)
+    n0l, N1, N2 = pm.rshape
+    pad = pm.rt.empty((n0l + 4, N1, N2))
+    pm.rt.sync_stream()
+    pm._c2r_slab(potk, 1.0, consume=consume, out=pad[2:2 + n0l])
+    pm._halo_fill(pad)
+    return _Padded(pad)
 
 
 def _force_tables(pm, order=1):
@@ -1708,10 +1768,18 @@ def _force_tables(pm, order=1):
     return pm._tables[key]
 
 
+_HALO_STENCIL = os.environ.get('VMAD_B200_HALO_STENCIL', '1') == '1'
+
+
 def _use_stencil(pm):
-    """the real-space gradient needs +-2 planes of neighbours: single slab only (a slab
-    decomposition would need a halo exchange; it keeps the k-space gradients)"""
-    return pm.P == 1 and getattr(pm, 'force_stencil', True) and min(pm.rshape) >= 2
+    """the real-space gradient needs +-2 planes of neighbours: the periodic mesh itself on one
+    rank, a halo exchange with the neighbouring slabs on several (else the k-space gradients)"""
+    if not getattr(pm, 'force_stencil', True) or min(pm.rshape) < 2:
+        return False
+    if pm.P == 1:
+        return True
+    # several ranks: halo planes come from the immediate neighbours over peer memory
+    return _HALO_STENCIL and pm.rshape[0] >= 2 and pm._peer() is not None
 
 
 def drift_pos(pm, dx, p, fac, q):
@@ -1748,7 +1816,7 @@ def force_apl(pm, dx, q, x=None, kick=None, want_f=True):
     if _use_stencil(pm):
         # one inverse FFT (of the potential) + a streaming 4-point stencil for the 3 gradients
         potk = pm._transfer(rhok, scale=scale, laplace=True)
-        phi = pm._c2r(potk, 1.0)                               # potk is an output: preserved
+        phi = _potential(pm, potk)                             # potk is an output: preserved
         F = _fd4(pm, phi)
         # small meshes: the three force meshes stay on the tape (24 B/cell) and the reverse sweep
         # skips the stencil pass; large ones recompute them from the potential
@@ -1799,9 +1867,21 @@ def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None, update=None):
     else:
         _fl = lay.exchange(asdevice(_f) * float(f_scale))
     # readout.vjp (mesh half) x3: three paints of the columns of the force cotangent
-    Fbar = pm.paint_cols3(xl, _fl)
+    halo = st.phi is not None and pm.P > 1
+    Fbar = pm.paint_cols3(xl, _fl, pad=2 if halo else 0)
     pbar = None if _is_zero_literal(_potk) else pm._as_field(_potk, True)
-    if st.phi is not None:
+    if halo:
+        # slab: the axis-0 difference of the adjoint needs the neighbours' boundary planes of Fbar_0
+        pm._halo_fill(Fbar[0])
+        phibar = rt.empty(pm.rshape)
+        C.check(C.lib.vpm_fd4_neg_gradient_adjoint_slab(rt.ctx, C.i3(pm.rshape), _h3(pm), 2, _ptr(Fbar[0]),
+                                                        _ptr(Fbar[1]), _ptr(Fbar[2]), _ptr(phibar)))
+        del Fbar
+        potk_bar = pm._r2c(RealField(pm, phibar), 1.0)
+        if pbar is not None:
+            potk_bar = potk_bar + pbar
+        rhok_bar = pm._transfer(potk_bar, scale=st.scale, laplace=True)
+    elif st.phi is not None:
         # adjoint of the stencil, then ONE forward FFT (c2r.vjp of the un-normalised inverse)
         phibar = rt.empty(pm.rshape)
         C.check(C.lib.vpm_fd4_neg_gradient_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(Fbar[0].t),
@@ -1952,7 +2032,7 @@ def force_jvp(pm, st, dx_):
     rhok_ = pm._r2c(rho_, 1.0)
     if st.phi is not None:
         potk_ = pm._transfer(rhok_, scale=st.scale, laplace=True)
-        F_ = _fd4(pm, pm._c2r(potk_, 1.0))
+        F_ = _fd4(pm, _potential(pm, potk_))
     else:
         potk_, g_ = pm.force_kspace(rhok_, st.scale, st.grad_tables, want_p=True)
         F_ = [pm._c2r(g_[d], 1.0, consume=True) for d in range(3)]
