@@ -11,14 +11,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_ranks_match_one_rank_oracle():
+@pytest.mark.parametrize("world", [2, 4])
+def test_ranks_match_one_rank_oracle(world):
+    """world = 4 also exercises distinct previous / next neighbours in the halo exchange"""
     import torch
     n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs at least 2 GPUs")
-    world = 2
+    if n < world:
+        pytest.skip("needs at least %d GPUs" % world)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
-           '--master-addr', '127.0.0.1', '--master-port', '29533',
+           '--master-addr', '127.0.0.1', '--master-port', str(29531 + world),
            os.path.join(ROOT, 'tests', 'mp_gpu_worker.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     tail = (r.stdout + r.stderr)[-4000:]
