@@ -60,6 +60,17 @@ int vpm_version(void);
 int64_t vpm_launch_count(void);
 int vpm_device_sm_count(vpm_ctx* ctx, int* out_host);
 
+/* In-place profiling for the roofline report (no reference counterpart; bench.py's measurement
+ * contract): between _start and _stop every kernel launch / cuFFT execution / memset of this
+ * library is bracketed by two CUDA events on the launching stream.  vpm_profile_read waits for
+ * them and writes one text line per launch, "group\tkernel\tmilliseconds\talgorithmic bytes of
+ * the launch\talgorithmic bytes of the group instance\n" (0 where an entry point states none);
+ * it returns the buffer size the text needs (-1 on error) and releases the records once the text
+ * fitted into buf. */
+int vpm_profile_start(void);
+int vpm_profile_stop(void);
+int64_t vpm_profile_read(char* buf, int64_t cap);
+
 /* ---- decompose / exchange / gather  (fastpm.py:272,286,289,301,304; pmesh
  *      ParticleMesh.decompose, Layout.exchange, Layout.gather) ---------------- */
 /* cell key of every particle: ((i0' * n1) + i1) * n2 + i2 of the wrapped floor cell,

@@ -25,6 +25,10 @@ from scipy.integrate import odeint
 
 
 class MatterDominated(object):
+    def __vmad_hyper_key__(self):
+        """memo key when the repo's VM memoises autooperator models"""
+        return (self.Omega0_m, self.Omega0_lambda, self.Omega0_k, self.lna.tobytes())
+
     def __init__(self, Omega0_m, Omega0_lambda=None, Omega0_k=0, a=None, a_normalize=1.0):
         if Omega0_lambda is None:
             Omega0_lambda = 1 - Omega0_k - Omega0_m

@@ -452,6 +452,10 @@ class ParticleMesh(object):
         # the one rounded fp64 scale used for every position -> cell conversion
         self.scale = self.Nmesh / self.BoxSize
 
+    def __vmad_hyper_key__(self):
+        """memo key when the repo's VM memoises autooperator models (immutable configuration)"""
+        return ('oracle-pm', id(self))
+
     # -- helpers -------------------------------------------------------------
     def freq_index(self, d):
         """Integer frequency along axis ``d`` of the stored complex array."""

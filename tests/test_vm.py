@@ -202,3 +202,86 @@ def test_errors():
         m.output(b=scale(a, 2.0))
     with pytest.raises(UnexpectedOutput):
         m.compute('c', init=dict(a=1))
+
+
+def test_autooperator_memo_is_keyed_by_value():
+    """a hyper-argument mutated between two calls must not replay the stale model (the
+    reference rebuilds on every call, vmad/core/autooperator.py:133-156)"""
+    import numpy
+
+    class Cfg(object):
+        def __init__(self, k):
+            self.k = k
+
+    @autooperator('x->y')
+    def f(x, cfg):
+        return dict(y=x * cfg.k)
+
+    def run(cfg):
+        with Builder() as m:
+            x = m.input('x')
+            m.output(y=f(x, cfg))
+        return m.compute('y', init=dict(x=3.0))
+
+    cfg = Cfg(2)
+    assert run(cfg) == 6.0
+    cfg.k = 5                       # in-place mutation of the same object
+    assert run(cfg) == 15.0
+    n0 = len(f._model_cache)
+    assert run(cfg) == 15.0         # ... while an unchanged one is served from the memo
+    assert len(f._model_cache) == n0
+
+    # a class used as a namespace (the way cosmologies are passed, fastpm.py:504)
+    class Cosmo(object):
+        Om0 = 0.3
+
+    @autooperator('x->y')
+    def g(x, cosmology):
+        return dict(y=x * cosmology.Om0)
+
+    def run_g():
+        with Builder() as m:
+            x = m.input('x')
+            m.output(y=g(x, Cosmo))
+        return m.compute('y', init=dict(x=1.0))
+
+    assert run_g() == 0.3
+    Cosmo.Om0 = 0.25
+    assert run_g() == 0.25
+
+    # large writeable arrays cannot be fingerprinted: no memo, always rebuilt
+    @autooperator('x->y')
+    def h(x, table):
+        return dict(y=x * float(table[0]))
+
+    table = numpy.ones(10000)
+
+    def run_h():
+        with Builder() as m:
+            x = m.input('x')
+            m.output(y=h(x, table))
+        return m.compute('y', init=dict(x=2.0))
+
+    assert run_h() == 2.0
+    table[0] = 4.0
+    assert run_h() == 8.0
+    assert len(h._model_cache) == 0
+
+    # closures are keyed by the values they captured
+    def make(scale_by):
+        def tf(v):
+            return v * scale_by
+        return tf
+
+    @autooperator('x->y')
+    def k(x, fn):
+        return dict(y=x * fn(1.0))
+
+    def run_k(fn):
+        with Builder() as m:
+            x = m.input('x')
+            m.output(y=k(x, fn))
+        return m.compute('y', init=dict(x=1.0))
+
+    assert run_k(make(2.0)) == 2.0
+    assert run_k(make(3.0)) == 3.0

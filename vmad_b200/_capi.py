@@ -60,6 +60,9 @@ SIGNATURES = {
     'vpm_version': (c_int, []),
     'vpm_launch_count': (c_int64, []),
     'vpm_device_sm_count': (c_int, [c_void_p, POINTER(c_int)]),
+    'vpm_profile_start': (c_int, []),
+    'vpm_profile_stop': (c_int, []),
+    'vpm_profile_read': (c_int64, [ctypes.c_char_p, c_int64]),
     'vpm_cell_keys': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P]),
     'vpm_layout_ncell': (c_int64, [POINTER(vpm_mesh)]),
     'vpm_layout_build': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P, _P, _P]),
@@ -152,6 +155,33 @@ def check(status):
 
 def launch_count():
     return int(lib.vpm_launch_count())
+
+
+class profile(object):
+    """``with profile() as p: ...`` -- every launch of the library inside the block is timed in
+    place with CUDA events on the launching stream; afterwards ``p.records`` is a list of
+    ``(group, kernel, ms, algorithmic_bytes, group_bytes)``."""
+
+    def __enter__(self):
+        check(lib.vpm_profile_start())
+        self.records = []
+        return self
+
+    def __exit__(self, *exc):
+        lib.vpm_profile_stop()
+        need = int(lib.vpm_profile_read(None, 0))
+        if need < 0:
+            raise VpmError(last_error())
+        buf = ctypes.create_string_buffer(need)
+        if int(lib.vpm_profile_read(buf, need)) < 0:
+            raise VpmError(last_error())
+        for line in buf.value.decode().splitlines():
+            g, k, ms, b, gb = line.split('\t')
+            k = k.strip()
+            if k.startswith('(') and k.endswith(')'):
+                k = k[1:-1]
+            self.records.append((g, k, float(ms), float(b), float(gb)))
+        return False
 
 
 def i3(values):

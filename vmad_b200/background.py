@@ -44,6 +44,10 @@ class MatterDominated(object):
         self._D1 = [y[0] / n1, y[1] / n1, acc[:, 1] / n1]
         self._D2 = [y[2] / n1 ** 2, y[3] / n1 ** 2, acc[:, 3] / n1 ** 2]
 
+    def __vmad_hyper_key__(self):
+        """memo key as a hyper-argument of an autooperator (vm/ops.py:_hyper_key)"""
+        return (self.Omega0_m, self.Omega0_lambda, self.Omega0_k, self.lna.tobytes())
+
     # -- background expansion ---------------------------------------------------------------
     def efunc(self, a):
         return (self.Omega0_m / a ** 3 + self.Omega0_k / a ** 2 + self.Omega0_lambda) ** 0.5

@@ -32,10 +32,40 @@ inline void check_cuda(cudaError_t e, const char* what, const char* file, int li
         if (!(cond)) throw ::vpm::Error(std::string("vmadpm: ") + (msg));          \
     } while (0)
 
+// ---- in-place profiling (vpm_profile_start / _stop / _read) -------------------------------
+// While profiling is on, every launch that goes through VPM_LAUNCH (and every cuFFT exec /
+// memset wrapped in VPM_PROF_CALL) is bracketed by two CUDA events recorded on the launching
+// stream; an API entry point may name the group the launches belong to and state the
+// ALGORITHMIC bytes of its next launch (or of the whole group), which is what bench.py's
+// roofline divides by the measured time.  Off by default: one predictable branch per launch.
+extern bool g_prof_on;
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+void prof_next_bytes(double bytes);        // algorithmic bytes of the next profiled launch
+struct ProfGroup {                         // RAII: launches inside belong to `group`
+    const char* prev;
+    explicit ProfGroup(const char* group, double group_bytes = 0.0);
+    ~ProfGroup();
+};
+#define VPM_PROF_BYTES(b)                                                          \
+    do {                                                                           \
+        if (::vpm::g_prof_on) ::vpm::prof_next_bytes((double)(b));                 \
+    } while (0)
+#define VPM_PROF_GROUP(name, bytes) \
+    ::vpm::ProfGroup vpm_prof_group_(name, ::vpm::g_prof_on ? (double)(bytes) : 0.0)
+#define VPM_PROF_CALL(name, stream, call)                                          \
+    do {                                                                           \
+        if (::vpm::g_prof_on) ::vpm::prof_begin(name, stream);                     \
+        call;                                                                      \
+        if (::vpm::g_prof_on) ::vpm::prof_end(stream);                             \
+    } while (0)
+
 // Every kernel launch goes through this so that vpm_launch_count() is honest.
 #define VPM_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
     do {                                                                           \
+        if (::vpm::g_prof_on) ::vpm::prof_begin(#kernel, stream);                  \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                \
+        if (::vpm::g_prof_on) ::vpm::prof_end(stream);                             \
         ::vpm::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
         VPM_CUDA(cudaGetLastError());                                              \
     } while (0)
@@ -55,6 +85,8 @@ inline void check_cuda(cudaError_t e, const char* what, const char* file, int li
     }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// local cells of a (slab of a) real mesh: what "8 B/cell" in the algorithmic byte counts refers to
+inline double mesh_cells(const vpm_mesh* m) { return m ? (double)m->nloc0 * (double)m->n[1] * (double)m->n[2] : 0.0; }
 
 }  // namespace vpm
 

@@ -1,9 +1,58 @@
 // Context lifetime, workspace arena, error reporting.
 #include "common.cuh"
 
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
 namespace vpm {
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
+
+// ---- profiling records (one host thread per GPU drives the library) ------------------------
+bool g_prof_on = false;
+namespace {
+struct ProfRec {
+    const char* group;
+    const char* name;
+    double bytes;        // algorithmic bytes stated for this launch (0: none stated)
+    double group_bytes;  // stated once per group instance, on its first launch
+    cudaEvent_t e0, e1;
+};
+std::vector<ProfRec> g_prof;
+const char* g_prof_group = "";
+double g_prof_bytes = 0.0;
+double g_prof_group_bytes = 0.0;
+}  // namespace
+
+void prof_begin(const char* name, cudaStream_t st) {
+    ProfRec r;
+    r.group = g_prof_group;
+    r.name = name;
+    r.bytes = g_prof_bytes;
+    r.group_bytes = g_prof_group_bytes;
+    g_prof_bytes = 0.0;
+    g_prof_group_bytes = 0.0;
+    VPM_CUDA(cudaEventCreate(&r.e0));
+    VPM_CUDA(cudaEventCreate(&r.e1));
+    VPM_CUDA(cudaEventRecord(r.e0, st));
+    g_prof.push_back(r);
+}
+
+void prof_end(cudaStream_t st) {
+    if (!g_prof.empty()) VPM_CUDA(cudaEventRecord(g_prof.back().e1, st));
+}
+
+void prof_next_bytes(double bytes) { g_prof_bytes = bytes; }
+
+ProfGroup::ProfGroup(const char* group, double group_bytes) : prev(g_prof_group) {
+    g_prof_group = group;
+    if (g_prof_on) g_prof_group_bytes = group_bytes;
+}
+ProfGroup::~ProfGroup() {
+    g_prof_group = prev;
+    g_prof_group_bytes = 0.0;
+}
 }  // namespace vpm
 
 void* vpm_ctx::workspace(size_t bytes) {
@@ -82,6 +131,53 @@ const char* vpm_last_error(void) { return vpm::g_last_error.c_str(); }
 int vpm_version(void) { return 100; }
 
 int64_t vpm_launch_count(void) { return vpm::g_launches.load(); }
+
+int vpm_profile_start(void) {
+    VPM_API_BEGIN
+    for (auto& r : vpm::g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    vpm::g_prof.clear();
+    vpm::g_prof_on = true;
+    VPM_API_END
+}
+
+int vpm_profile_stop(void) {
+    vpm::g_prof_on = false;
+    return 0;
+}
+
+// One text line per profiled launch: "group\tname\tmilliseconds\tbytes\tgroup_bytes\n".
+// Synchronises on the recorded events.  Returns the number of bytes the full text needs
+// (call with buf = NULL / cap = 0 first); the records are released when the text fitted.
+int64_t vpm_profile_read(char* buf, int64_t cap) {
+    try {
+        std::string out;
+        char line[512];
+        for (auto& r : vpm::g_prof) {
+            float ms = 0.f;
+            VPM_CUDA(cudaEventSynchronize(r.e1));
+            VPM_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            snprintf(line, sizeof(line), "%s\t%s\t%.6f\t%.1f\t%.1f\n", r.group, r.name, (double)ms,
+                     r.bytes, r.group_bytes);
+            out += line;
+        }
+        const int64_t need = (int64_t)out.size() + 1;
+        if (buf && cap >= need) {
+            memcpy(buf, out.c_str(), (size_t)need);
+            for (auto& r : vpm::g_prof) {
+                cudaEventDestroy(r.e0);
+                cudaEventDestroy(r.e1);
+            }
+            vpm::g_prof.clear();
+        }
+        return need;
+    } catch (const std::exception& e) {
+        vpm::g_last_error = e.what();
+        return -1;
+    }
+}
 
 int vpm_device_sm_count(vpm_ctx* ctx, int* out_host) {
     VPM_API_BEGIN

@@ -161,6 +161,7 @@ extern "C" {
 int vpm_axpby(vpm_ctx* ctx, int64_t n, double a, const double* x, double b, const double* y,
               double c, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("axpby", (16.0 + (y ? 8.0 : 0.0)) * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     if (n > 0) {
         VPM_REQUIRE(x && out, "NULL array");
@@ -173,6 +174,7 @@ int vpm_axpby(vpm_ctx* ctx, int64_t n, double a, const double* x, double b, cons
 int vpm_drift_pos(vpm_ctx* ctx, int64_t n, const double* dx, const double* p, double fac,
                   const double* q, double* dx1, double* x1) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("drift_pos", 40.0 * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     if (n > 0) {
         VPM_REQUIRE(dx && p && q && dx1 && x1, "NULL array");
@@ -183,6 +185,7 @@ int vpm_drift_pos(vpm_ctx* ctx, int64_t n, const double* dx, const double* p, do
 
 int vpm_mul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("mul", 24.0 * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     if (n > 0) {
         VPM_REQUIRE(x && y && out, "NULL array");
@@ -193,6 +196,7 @@ int vpm_mul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* o
 
 int vpm_div(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("div", 24.0 * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     if (n > 0) {
         VPM_REQUIRE(x && y && out, "NULL array");
@@ -204,6 +208,7 @@ int vpm_div(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* o
 int vpm_mul_rows(vpm_ctx* ctx, int64_t n, int ncomp, const double* x, const double* w,
                  double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("mul_rows", (16.0 * ncomp + 8.0) * n);
     VPM_REQUIRE(ctx && ncomp >= 1, "bad argument");
     if (n > 0) {
         VPM_REQUIRE(x && w && out, "NULL array");
@@ -214,6 +219,7 @@ int vpm_mul_rows(vpm_ctx* ctx, int64_t n, int ncomp, const double* x, const doub
 
 int vpm_cmul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, int conj_y, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("cmul", 48.0 * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     if (n > 0) {
         VPM_REQUIRE(x && y && out, "NULL array");
@@ -226,6 +232,7 @@ int vpm_cmul(vpm_ctx* ctx, int64_t n, const double* x, const double* y, int conj
 
 int vpm_fill(vpm_ctx* ctx, int64_t n, double value, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("fill", 8.0 * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     if (n > 0) {
         VPM_REQUIRE(out, "NULL array");
@@ -236,6 +243,7 @@ int vpm_fill(vpm_ctx* ctx, int64_t n, double value, double* out) {
 
 int vpm_stack(vpm_ctx* ctx, int64_t n, int ncomp, const double* const* cols_host, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("stack", 16.0 * n * ncomp);
     VPM_REQUIRE(ctx && cols_host, "NULL argument");
     VPM_REQUIRE(ncomp >= 1 && ncomp <= 8, "stack supports 1..8 columns");
     if (n > 0) {
@@ -250,6 +258,7 @@ int vpm_stack(vpm_ctx* ctx, int64_t n, int ncomp, const double* const* cols_host
 
 int vpm_take_col(vpm_ctx* ctx, int64_t n, int ncomp, int col, const double* x, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("take_col", 16.0 * n);
     VPM_REQUIRE(ctx && ncomp >= 1 && col >= 0 && col < ncomp, "bad argument");
     if (n > 0) {
         VPM_REQUIRE(x && out, "NULL array");
@@ -260,6 +269,7 @@ int vpm_take_col(vpm_ctx* ctx, int64_t n, int ncomp, int col, const double* x, d
 
 int vpm_reduce_sum(vpm_ctx* ctx, int64_t n, const double* x, double* out_host) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("reduce_sum", 8.0 * n);
     VPM_REQUIRE(ctx && out_host && (n <= 0 || x), "NULL argument");
     reduce_to_host(ctx, n, x, nullptr, out_host);
     VPM_API_END
@@ -267,6 +277,7 @@ int vpm_reduce_sum(vpm_ctx* ctx, int64_t n, const double* x, double* out_host) {
 
 int vpm_reduce_dot(vpm_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("reduce_dot", 16.0 * n);
     VPM_REQUIRE(ctx && out_host && (n <= 0 || (x && y)), "NULL argument");
     reduce_to_host(ctx, n, x, y, out_host);
     VPM_API_END

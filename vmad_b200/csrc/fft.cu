@@ -106,10 +106,12 @@ extern "C" {
 int vpm_r2c(vpm_ctx* ctx, const int64_t n[3], const double* real_in, double* cplx_out,
             double scale) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("r2c", 8.0 * ((double)n[0] * n[1] * n[2]) + 16.0 * ((double)n[0] * n[1] * (n[2] / 2 + 1)));
     VPM_REQUIRE(ctx && n && real_in && cplx_out, "NULL argument");
     cufftHandle h = ctx->plan(n, 0);
-    VPM_CUFFT(cufftExecD2Z(h, const_cast<double*>(real_in),
-                           reinterpret_cast<cufftDoubleComplex*>(cplx_out)));
+    VPM_PROF_CALL("cufftExecD2Z", ctx->stream,
+                  VPM_CUFFT(cufftExecD2Z(h, const_cast<double*>(real_in),
+                                         reinterpret_cast<cufftDoubleComplex*>(cplx_out))));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (scale != 1.0) {
         long long nd = 2LL * n[0] * n[1] * (n[2] / 2 + 1);
@@ -122,6 +124,7 @@ int vpm_r2c(vpm_ctx* ctx, const int64_t n[3], const double* real_in, double* cpl
 static int c2r_impl(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, double* real_out,
                     double scale, bool preserve_input) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("c2r", 8.0 * ((double)n[0] * n[1] * n[2]) + 16.0 * ((double)n[0] * n[1] * (n[2] / 2 + 1)));
     VPM_REQUIRE(ctx && n && cplx_in && real_out, "NULL argument");
     cufftHandle h = ctx->plan(n, 1);
     // multi-dimensional Z2D may overwrite its input; operators must not mutate theirs
@@ -129,9 +132,11 @@ static int c2r_impl(vpm_ctx* ctx, const int64_t n[3], const double* cplx_in, dou
     if (preserve_input) {
         size_t bytes = (size_t)16 * n[0] * n[1] * (n[2] / 2 + 1);
         stage = ctx->workspace(bytes);
-        VPM_CUDA(cudaMemcpyAsync(stage, cplx_in, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        VPM_PROF_CALL("memcpy(c2r input)", ctx->stream,
+                      VPM_CUDA(cudaMemcpyAsync(stage, cplx_in, bytes, cudaMemcpyDeviceToDevice, ctx->stream)));
     }
-    VPM_CUFFT(cufftExecZ2D(h, reinterpret_cast<cufftDoubleComplex*>(stage), real_out));
+    VPM_PROF_CALL("cufftExecZ2D", ctx->stream,
+                  VPM_CUFFT(cufftExecZ2D(h, reinterpret_cast<cufftDoubleComplex*>(stage), real_out)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (scale != 1.0) {
         long long nd = (long long)n[0] * n[1] * n[2];
@@ -154,10 +159,12 @@ int vpm_c2r_inplace(vpm_ctx* ctx, const int64_t n[3], double* cplx_scratch, doub
 int vpm_fft_r2c_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, const double* real_in,
                        double* cplx_out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("r2c_planes", (double)nplanes * n1 * (8.0 * n2 + 16.0 * (n2 / 2 + 1)));
     VPM_REQUIRE(ctx && real_in && cplx_out && nplanes >= 1, "bad argument");
     cufftHandle h = slab_plan(ctx, 10, nplanes, n1, n2);
-    VPM_CUFFT(cufftExecD2Z(h, const_cast<double*>(real_in),
-                           reinterpret_cast<cufftDoubleComplex*>(cplx_out)));
+    VPM_PROF_CALL("cufftExecD2Z", ctx->stream,
+                  VPM_CUFFT(cufftExecD2Z(h, const_cast<double*>(real_in),
+                                         reinterpret_cast<cufftDoubleComplex*>(cplx_out))));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     VPM_API_END
 }
@@ -165,9 +172,11 @@ int vpm_fft_r2c_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, co
 int vpm_fft_c2r_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, double* cplx_in,
                        double* real_out, double scale) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("c2r_planes", (double)nplanes * n1 * (8.0 * n2 + 16.0 * (n2 / 2 + 1)));
     VPM_REQUIRE(ctx && real_out && cplx_in && nplanes >= 1, "bad argument");
     cufftHandle h = slab_plan(ctx, 11, nplanes, n1, n2);
-    VPM_CUFFT(cufftExecZ2D(h, reinterpret_cast<cufftDoubleComplex*>(cplx_in), real_out));
+    VPM_PROF_CALL("cufftExecZ2D", ctx->stream,
+                  VPM_CUFFT(cufftExecZ2D(h, reinterpret_cast<cufftDoubleComplex*>(cplx_in), real_out)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (scale != 1.0) {
         long long nd = (long long)nplanes * n1 * n2;
@@ -180,11 +189,13 @@ int vpm_fft_c2r_planes(vpm_ctx* ctx, int64_t nplanes, int64_t n1, int64_t n2, do
 int vpm_fft_c2c_axis0(vpm_ctx* ctx, int64_t n0, int64_t inner, double* data, int inverse,
                       double scale) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("c2c_axis0", 32.0 * n0 * inner);
     VPM_REQUIRE(ctx && data && n0 >= 1 && inner >= 1, "bad argument");
     VPM_REQUIRE(inner < (1LL << 31), "too many transforms for one plan");
     cufftHandle h = slab_plan(ctx, 12, n0, inner, 0);
     cufftDoubleComplex* d = reinterpret_cast<cufftDoubleComplex*>(data);
-    VPM_CUFFT(cufftExecZ2Z(h, d, d, inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    VPM_PROF_CALL("cufftExecZ2Z", ctx->stream,
+                  VPM_CUFFT(cufftExecZ2Z(h, d, d, inverse ? CUFFT_INVERSE : CUFFT_FORWARD)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (scale != 1.0) {
         long long nd = 2LL * n0 * inner;
@@ -197,12 +208,14 @@ int vpm_fft_c2c_axis0(vpm_ctx* ctx, int64_t n0, int64_t inner, double* data, int
 int vpm_fft_c2c_axis0_oop(vpm_ctx* ctx, int64_t n0, int64_t inner, const double* in, double* out,
                           int inverse, double scale) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("c2c_axis0", 32.0 * n0 * inner);
     VPM_REQUIRE(ctx && in && out && n0 >= 1 && inner >= 1, "bad argument");
     VPM_REQUIRE(inner < (1LL << 31), "too many transforms for one plan");
     cufftHandle h = slab_plan(ctx, 12, n0, inner, 0);
-    VPM_CUFFT(cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(const_cast<double*>(in)),
-                           reinterpret_cast<cufftDoubleComplex*>(out),
-                           inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    VPM_PROF_CALL("cufftExecZ2Z", ctx->stream,
+                  VPM_CUFFT(cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(const_cast<double*>(in)),
+                                         reinterpret_cast<cufftDoubleComplex*>(out),
+                                         inverse ? CUFFT_INVERSE : CUFFT_FORWARD)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (scale != 1.0) {
         long long nd = 2LL * n0 * inner;
@@ -215,6 +228,7 @@ int vpm_fft_c2c_axis0_oop(vpm_ctx* ctx, int64_t n0, int64_t inner, const double*
 int vpm_swap_leading_axes(vpm_ctx* ctx, int64_t a, int64_t b, int64_t c, const double* src,
                           double* dst) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("swap_leading_axes", 32.0 * a * b * c);
     VPM_REQUIRE(ctx && src && dst && src != dst, "bad argument");
     long long total = (long long)a * b * c;
     if (total > 0) {

@@ -222,6 +222,7 @@ int vpm_transfer(vpm_ctx* ctx, const int64_t nc[3], const double* in, double* ou
                  int laplace, const double* kk0, const double* kk1, const double* kk2,
                  const double* a0, const double* a1, const double* a2, int conj_tables) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("transfer", 32.0 * ((double)nc[0] * nc[1] * nc[2]));
     VPM_REQUIRE(ctx && in && out, "NULL argument");
     CShape s = make_cshape(nc);
     VPM_REQUIRE(!laplace || (kk0 && kk1 && kk2), "laplace needs the three wavenumber tables");
@@ -237,6 +238,7 @@ int vpm_transfer_table(vpm_ctx* ctx, const int64_t nc[3], const double* in, doub
                        const double* table, const int64_t tstride[3], int table_is_complex,
                        int conj_table) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("transfer", 32.0 * ((double)nc[0] * nc[1] * nc[2]));
     VPM_REQUIRE(ctx && in && out && table && tstride, "NULL argument");
     CShape s = make_cshape(nc);
     unsigned grid = (unsigned)ceil_div(s.total, KS_THREADS);
@@ -252,6 +254,7 @@ int vpm_force_kspace(vpm_ctx* ctx, const int64_t nc[3], const double* rhok, doub
                      const double* a1, const double* a2, double* p_out, double* g0, double* g1,
                      double* g2) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("force_kspace", (64.0 + (p_out ? 16.0 : 0.0)) * ((double)nc[0] * nc[1] * nc[2]));
     VPM_REQUIRE(ctx && rhok && kk0 && kk1 && kk2 && a0 && a1 && a2 && g0 && g1 && g2, "NULL argument");
     CShape s = make_cshape(nc);
     unsigned grid = (unsigned)ceil_div(s.total, KS_THREADS);
@@ -267,6 +270,7 @@ int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, co
                          const double* kk1, const double* kk2, const double* a0, const double* a1,
                          const double* a2, double* rhok_bar) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("force_kspace_vjp", (64.0 + (p_bar ? 16.0 : 0.0)) * ((double)nc[0] * nc[1] * nc[2]));
     VPM_REQUIRE(ctx && g0 && g1 && g2 && kk0 && kk1 && kk2 && a0 && a1 && a2 && rhok_bar, "NULL argument");
     CShape s = make_cshape(nc);
     unsigned grid = (unsigned)ceil_div(s.total, KS_THREADS);
@@ -280,6 +284,7 @@ int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, co
 int vpm_reduce_cdot(vpm_ctx* ctx, const int64_t nc[3], int64_t n_last, const double* x,
                     const double* y, double* out_host) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("reduce_cdot", 32.0 * ((double)nc[0] * nc[1] * nc[2]));
     VPM_REQUIRE(ctx && x && y && out_host, "NULL argument");
     CShape s = make_cshape(nc);
     int nparts = (int)std::min<long long>(ceil_div(s.total, RED_THREADS), 4LL * ctx->sm_count);

@@ -383,6 +383,7 @@ extern "C" {
 int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double* x, int64_t np,
                     int32_t* send_idx, int64_t send_capacity, int32_t* send_start_host) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("route_build", 28.0 * np);
     VPM_REQUIRE(ctx && mesh && send_start_host, "NULL argument");
     VPM_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXP, "unsupported number of ranks");
     VPM_REQUIRE(mesh->n[0] % nranks == 0, "mesh planes must divide evenly over the ranks");
@@ -427,6 +428,7 @@ int64_t vpm_layout_ncell(const vpm_mesh* m) {
 
 int vpm_cell_keys(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_t np, int32_t* keys) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("cell_keys", 28.0 * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
@@ -439,6 +441,7 @@ int vpm_cell_keys(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_t n
 int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_t np,
                      int32_t* keys, int32_t* perm, int32_t* cell_start) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("layout_build", 48.0 * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     VPM_REQUIRE(np >= 0 && np < (1LL << 31) - 1, "particle count must fit int32");
     Geo g = make_geo(mesh);
@@ -455,7 +458,7 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
     int* big_list = tmp + ntmp;          // [0]: medium cells, [1]: huge cells
     int* big_count = big_list + 2 * ncell;
     int* perm2 = big_count + 4;
-    VPM_CUDA(cudaMemsetAsync(count, 0, (size_t)ncell * sizeof(int), st));
+    VPM_PROF_CALL("memset(cell counts)", st, VPM_CUDA(cudaMemsetAsync(count, 0, (size_t)ncell * sizeof(int), st)));
     VPM_CUDA(cudaMemsetAsync(big_count, 0, 4 * sizeof(int), st));
     if (np > 0) {
         VPM_REQUIRE(x && keys && perm, "NULL array");
@@ -496,6 +499,7 @@ static void launch_take_rows(vpm_ctx* ctx, const double* src, const int32_t* per
 int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
                   double* dst) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("take_rows", (16.0 * ncomp + 4.0) * n);
     launch_take_rows(ctx, src, perm, n, ncomp, 1.0, dst);
     VPM_API_END
 }
@@ -503,6 +507,7 @@ int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t 
 int vpm_take_rows_scaled(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
                          double scale, double* dst) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("take_rows", (16.0 * ncomp + 4.0) * n);
     launch_take_rows(ctx, src, perm, n, ncomp, scale, dst);
     VPM_API_END
 }
@@ -510,6 +515,7 @@ int vpm_take_rows_scaled(vpm_ctx* ctx, const double* src, const int32_t* perm, i
 int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n, int ncomp,
                      double* dst) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("scatter_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     VPM_REQUIRE(ncomp >= 1, "ncomp must be >= 1");
     if (n > 0) {
@@ -525,6 +531,7 @@ int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64
 int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
                    int ncomp, double* dst) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("take_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     VPM_REQUIRE(ncomp >= 1, "ncomp must be >= 1");
     if (n > 0) {
@@ -541,6 +548,7 @@ int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv
                       const int32_t* send_idx, int64_t nsend, int64_t recv_lo, int64_t recv_hi,
                       int64_t send_lo, int32_t* take, int32_t* remote) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("route_compose", 8.0 * nrecv + 8.0 * nsend);
     VPM_REQUIRE(ctx, "ctx is NULL");
     VPM_REQUIRE(nrecv >= 0 && nsend >= 0 && nrecv < (1LL << 31) && nsend < (1LL << 31), "bad counts");
     const long long n = std::max<long long>(nrecv, nsend);
@@ -557,6 +565,7 @@ int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv
 int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n, int ncomp,
                          double* dst) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("scatter_add_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
     VPM_REQUIRE(ncomp >= 1, "ncomp must be >= 1");
     if (n > 0) {

@@ -846,7 +846,8 @@ static void zero_mesh(vpm_ctx* ctx, const Geo& g, double* out) {
     const long long total = (long long)g.nloc0 * g.n1 * g.n2;
     if (total == 0) return;
     if (g.stride1 == g.n2 && g.stride0 == (long long)g.n1 * g.n2) {
-        VPM_CUDA(cudaMemsetAsync(out, 0, (size_t)total * sizeof(double), ctx->stream));
+        VPM_PROF_CALL("memset(mesh)", ctx->stream,
+                      VPM_CUDA(cudaMemsetAsync(out, 0, (size_t)total * sizeof(double), ctx->stream)));
     } else {
         unsigned zgrid = (unsigned)std::min<long long>(ceil_div(total, 256), 8LL * ctx->sm_count);
         VPM_LAUNCH(k_zero_mesh, zgrid, 256, 0, ctx->stream, g, out);
@@ -948,6 +949,7 @@ extern "C" {
 int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass,
                      double mass0, int64_t np, const int32_t* cell_start, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("paint", 24.0 * np + (mass ? 8.0 : 0.0) * np + 8.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx && out && (cell_start || g_paint_algo != 1), "NULL argument");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
     Geo g = make_geo(mesh);
@@ -961,6 +963,7 @@ int vpm_paint_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const
 int vpm_paint_sorted_rows(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass,
                           double mass0, int64_t np, const int32_t* cell_start, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("paint_rows", 24.0 * np + (mass ? 8.0 : 0.0) * np + 8.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx && out && cell_start, "NULL argument");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
     Geo g = make_geo(mesh);
@@ -972,6 +975,7 @@ int vpm_paint_jvp_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, c
                          double mass0, const double* vpos, const double* vmass, int64_t np,
                          const int32_t* cell_start, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("paint_jvp", 48.0 * np + (mass ? 8.0 : 0.0) * np + (vmass ? 8.0 : 0.0) * np + 8.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx && out && cell_start, "NULL argument");
     VPM_REQUIRE(np == 0 || (xs && vpos), "xs / vpos is NULL");
     Geo g = make_geo(mesh);
@@ -983,6 +987,7 @@ int vpm_paint_jvp_sorted(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, c
 int vpm_paint_sorted_col(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs, const double* mass2d,
                          int ncomp, int col, int64_t np, const int32_t* cell_start, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("paint", 32.0 * np + 8.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx && out && mass2d, "NULL argument");
     VPM_REQUIRE(ncomp >= 1 && col >= 0 && col < ncomp, "bad column");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
@@ -998,6 +1003,7 @@ int vpm_paint_sorted_cols3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* xs,
                            int ncomp, int64_t np, const int32_t* cell_start, double* out,
                            int64_t out_colstride) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("paint_cols3", 48.0 * np + 24.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx && out && mass2d, "NULL argument");
     VPM_REQUIRE(ncomp >= 3, "need at least three columns");
     VPM_REQUIRE(np == 0 || xs, "xs is NULL");
@@ -1036,6 +1042,7 @@ int vpm_paint_set_tile(int tx, int ty, int tz) {
 int vpm_paint_atomic(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, const double* mass,
                      double mass0, int64_t np, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("paint_atomic", 24.0 * np + (mass ? 8.0 : 0.0) * np + 8.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx && out, "NULL argument");
     Geo g = make_geo(mesh);
     long long total = (long long)g.nloc0 * g.n1 * g.n2;

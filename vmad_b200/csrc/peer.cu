@@ -256,6 +256,7 @@ static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, 
                          int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
                          unsigned mask, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("peer_put", 32.0 * rows * inner * nranks);
     VPM_REQUIRE(ctx && src && peer_bufs && nranks >= 1 && nranks <= 8, "bad argument");
     const long long total = (long long)rows * inner * nranks;
     if (total > 0 || sync) {   // an empty put still carries the flag traffic
@@ -275,6 +276,7 @@ int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const doub
                       const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
                       const int64_t* dst_base, const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("peer_put_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx && seg_start && dst_base && peer_bufs && nranks >= 1 && nranks <= 8,
                 "bad argument");
     VPM_REQUIRE(n >= 0 && n < (1LL << 31) && ncomp >= 1, "row count / columns out of range");

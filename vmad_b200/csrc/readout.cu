@@ -234,6 +234,7 @@ extern "C" {
 int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const double* x,
                 int64_t np, double* value) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("readout", 32.0 * np + 8.0 * mesh_cells(mesh));
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
@@ -248,6 +249,7 @@ int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const dou
                  const double* f2, const double* x, int64_t np, const int32_t* out_row,
                  double* value3, const double* y_in, double fac, double* y_out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("readout3", 24.0 * np + 24.0 * mesh_cells(mesh) + (out_row ? 4.0 : 0.0) * np + (value3 ? 24.0 : 0.0) * np + (y_out ? 48.0 : 0.0) * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
@@ -263,6 +265,7 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, co
                      const double* weight, double weight0, int64_t np, double* value,
                      double* grad) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("readout_grad", 48.0 * np + 8.0 * mesh_cells(mesh) + (weight ? 8.0 : 0.0) * np + (value ? 8.0 : 0.0) * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
@@ -282,6 +285,7 @@ int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, cons
                       int64_t np, const int32_t* out_row, const double* base, double* grad,
                       const double* y_in, double fac, double* y_out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("readout_grad4", 72.0 * np + 32.0 * mesh_cells(mesh) + (out_row ? 4.0 : 0.0) * np + (base ? 24.0 : 0.0) * np + (y_out ? 48.0 : 0.0) * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
@@ -297,6 +301,7 @@ int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
                     const double* field_dot, const double* x, const double* xdot, int64_t np,
                     double* value) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("readout_jvp", 32.0 * np + (field_dot ? 8.0 * mesh_cells(mesh) : 0.0) + (xdot ? 24.0 * np + 8.0 * mesh_cells(mesh) : 0.0));
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {

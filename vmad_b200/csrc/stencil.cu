@@ -227,6 +227,7 @@ extern "C" {
 int vpm_fd4_neg_gradient(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* phi,
                          double* f0, double* f1, double* f2) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("fd4_neg_gradient", 32.0 * ((double)n[0] * n[1] * n[2]));
     VPM_REQUIRE(ctx && phi && f0 && f1 && f2, "NULL argument");
     Grid3 g = make_grid(n, h);
     const long long total = (long long)g.n0 * g.n1 * g.n2;
@@ -238,6 +239,7 @@ int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double 
                                  const double* f0, const double* f1, const double* f2,
                                  double* phibar) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("fd4_neg_gradient_adjoint", 32.0 * ((double)n[0] * n[1] * n[2]));
     VPM_REQUIRE(ctx && phibar && f0 && f1 && f2, "NULL argument");
     Grid3 g = make_grid(n, h);
     const long long total = (long long)g.n0 * g.n1 * g.n2;
@@ -248,6 +250,7 @@ int vpm_fd4_neg_gradient_adjoint(vpm_ctx* ctx, const int64_t n[3], const double 
 int vpm_fd4_neg_gradient_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
                               const double* phi_padded, double* f0, double* f1, double* f2) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("fd4_neg_gradient", 32.0 * ((double)n[0] * n[1] * n[2]));
     VPM_REQUIRE(ctx && phi_padded && f0 && f1 && f2, "NULL argument");
     VPM_REQUIRE(pad == 0 || pad >= 2, "the stencil needs two halo planes per side");
     Grid3 g = make_grid(n, h);
@@ -262,6 +265,7 @@ int vpm_fd4_neg_gradient_adjoint_slab(vpm_ctx* ctx, const int64_t n[3], const do
                                       const double* f0_padded, const double* f1_padded,
                                       const double* f2_padded, double* phibar) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("fd4_neg_gradient_adjoint", 32.0 * ((double)n[0] * n[1] * n[2]));
     VPM_REQUIRE(ctx && phibar && f0_padded && f1_padded && f2_padded, "NULL argument");
     VPM_REQUIRE(pad == 0 || pad >= 2, "the stencil needs two halo planes per side");
     Grid3 g = make_grid(n, h);
@@ -277,6 +281,7 @@ int vpm_lpt2_source(vpm_ctx* ctx, const int64_t n[3], const double h[3], const d
                     const double* f1, const double* f2, const double* g0, const double* g1,
                     const double* g2, double scale, double* out) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("lpt2_source", 56.0 * ((double)n[0] * n[1] * n[2]));
     VPM_REQUIRE(ctx && f0 && f1 && f2 && out, "NULL argument");
     VPM_REQUIRE((g0 && g1 && g2) || (!g0 && !g1 && !g2), "pass all of g0, g1, g2 or none");
     Grid3 g = make_grid(n, h);
@@ -293,6 +298,7 @@ int vpm_lpt2_source_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3],
                             const double* f1, const double* f2, const double* sbar, double* work6,
                             double* fb0, double* fb1, double* fb2) {
     VPM_API_BEGIN
+    VPM_PROF_GROUP("lpt2_source_adjoint", 104.0 * ((double)n[0] * n[1] * n[2]));
     VPM_REQUIRE(ctx && f0 && f1 && f2 && sbar && work6 && fb0 && fb1 && fb2, "NULL argument");
     Grid3 g = make_grid(n, h);
     const long long total = (long long)g.n0 * g.n1 * g.n2;

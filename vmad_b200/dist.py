@@ -63,10 +63,16 @@ class HostBoard(object):
         t[self.rank, 0] = self.seq
         flags = t[:, 0]
         spins = 0
+        import time
+        t0 = None
         while (flags < self.seq).any():
             spins += 1
-            if spins > 200000000:
-                raise RuntimeError("host board: a peer did not post its counts")
+            if spins > 20000:       # ~10 ms of busy polling, then back off
+                if t0 is None:
+                    t0 = time.monotonic()
+                time.sleep(50e-6)
+                if time.monotonic() - t0 > 600.0:
+                    raise RuntimeError("host board: a peer did not post its counts")
         return t[:, 1:1 + n].copy()
 
 
@@ -141,7 +147,10 @@ class TorchComm(object):
     def _host_board(self):
         if getattr(self, '_board', None) is None:
             self._board = False
-            if self.size > 1 and self._single_node():
+            import platform
+            # the board relies on stores becoming visible in program order (x86 TSO); on other
+            # hosts (Grace / ARM) the counts go through the gloo group instead
+            if self.size > 1 and platform.machine() in ('x86_64', 'AMD64') and self._single_node():
                 try:
                     self._board = HostBoard(self)
                 except OSError:

@@ -11,13 +11,24 @@ fused single-pass kernels because the library's own filters (``fourier_space_lap
 Additions named by BASELINE.json ``north_star`` (absent from the reference):
 the fused operators ``force``, ``kick`` and ``drift`` -- see the end of this file.
 """
+import itertools
+
 import numpy
 
 from ..background import MatterDominated
-from ..pm import ParticleMesh  # noqa: F401  (same re-export as the reference, fastpm.py:6)
 from ..vm import autooperator, operator
 from ..vm.ops import ZeroGradient
 from . import linalg
+
+
+def __getattr__(name):
+    """``fastpm.ParticleMesh`` (the reference re-exports pmesh's, fastpm.py:6), resolved on first
+    use: importing the operator library must not load torch / libvmadpm.so (the library also runs
+    on other backends of the pmesh protocol, and bench.py's CPU arm must not map the CUDA library)"""
+    if name == 'ParticleMesh':
+        from ..pm import ParticleMesh
+        return ParticleMesh
+    raise AttributeError(name)
 
 
 def _is_zero(x):
@@ -659,6 +670,16 @@ class FastPMSimulation(object):
         self.fpm = type(pm)(Nmesh=pm.Nmesh * B, BoxSize=pm.BoxSize, dtype=pm.dtype,
                             comm=pm.comm, resampler=pm.resampler)
         self.q = _localize(q, pm)
+        self.B = B
+        # the models of the instance-bound autooperators below are memoised HERE (vm/ops.py:
+        # AutoOperator._build), so they -- and the device arrays they hold -- die with the simulation
+        self._vmad_model_cache = {}
+        self._serial = next(FastPMSimulation._serials)
+
+    _serials = itertools.count()
+
+    def __vmad_hyper_key__(self):
+        return ('sim', self._serial, numpy.asarray(self.stages).tobytes(), self.B)
 
     def KickFactor(self, ai, ac, af):
         return KickFactor(self.pt, ai, ac, af)

@@ -174,6 +174,13 @@ class DeviceArray(object):
     def from_host(kls, a):
         return kls(_upload(a))
 
+    def __vmad_hyper_key__(self):
+        """memo key as a hyper-argument of an autooperator (vm/ops.py:_hyper_key): only a
+        constant of the graph (``_frozen``: q, uploaded once) may be keyed by identity"""
+        if getattr(self, '_frozen', False):
+            return ('frozen', id(self))
+        raise TypeError("a mutable device array cannot key a memoised model")
+
     def _like(self, t):
         r = DeviceArray(t)
         return r
@@ -281,17 +288,21 @@ class DeviceArray(object):
         if s is not None:
             if s == 0.0:
                 return self
+            if self.t.is_complex():
+                raise TypeError("complex array - non-zero scalar is not supported")
             return self._axpby(1.0, c=-s)
         y = self._coerce(o)
         if y is None:
             return NotImplemented
-        if y.shape != self.t.shape:
-            raise ValueError("shape mismatch in sub")
+        if y.shape != self.t.shape or y.is_complex() != self.t.is_complex():
+            raise ValueError("shape/dtype mismatch in sub")
         return self._axpby(1.0, -1.0, y)
 
     def __rsub__(self, o):
         s = self._scalar(o)
         if s is not None:
+            if s != 0.0 and self.t.is_complex():
+                raise TypeError("non-zero scalar - complex array is not supported")
             return self._axpby(-1.0, c=s)
         y = self._coerce(o)
         if y is None:
@@ -328,7 +339,8 @@ class DeviceArray(object):
     def __truediv__(self, o):
         s = self._scalar(o)
         if s is not None:
-            return self._axpby(1.0 / s)
+            with numpy.errstate(divide='ignore'):       # array semantics: x / 0 -> inf / nan
+                return self._axpby(float(numpy.float64(1.0) / numpy.float64(s)))
         y = self._coerce(o)
         if y is None:
             return NotImplemented
@@ -933,6 +945,11 @@ class ParticleMesh(object):
         self._tables = {}
         self._frozen_layouts = {}     # id(constant position array) -> (weakref, layout)
         self._tf_cache = {}
+
+    def __vmad_hyper_key__(self):
+        """memo key as a hyper-argument of an autooperator: the mesh is immutable configuration;
+        the switches a model build reads (lib/fastpm.py:lpt) are part of the key"""
+        return ('pm', id(self), getattr(self, 'force_stencil', True), self.P)
 
     # -- host-side tables ---------------------------------------------------------------
     def freq_index(self, d):
@@ -1656,15 +1673,19 @@ class ParticleMesh(object):
 
     def _transfer_callable(self, cplx, tf, kind, conj):
         """``x * tf(k)`` for an arbitrary python ``tf``: the table is evaluated on the host the
-        first time this very function object is seen and then stays on the device (a model
-        built once keeps calling the same closure, e.g. ``induce_correlation``'s)."""
-        key = (id(tf), kind)
+        first time this function (same object, same closure VALUES) is seen and then stays on the
+        device (a model built once keeps calling the same closure, e.g. ``induce_correlation``'s)."""
+        from .vm.ops import _hyper_key, _Uncacheable
+        try:        # by value: the function, its closure cells and defaults (a callable whose
+            key = (_hyper_key(tf), kind)    # state cannot be fingerprinted is evaluated every time)
+        except _Uncacheable:
+            return self._transfer_table(cplx, tf(cplx._coords(kind)), conj)
         hit = self._tf_cache.get(key)
-        if hit is None or hit[0] is not tf:
+        if hit is None:
             prepared = self._prepare_table(tf(cplx._coords(kind)))
             if len(self._tf_cache) >= 32:
                 self._tf_cache.pop(next(iter(self._tf_cache)))
-            hit = (tf, prepared)  # holding tf keeps its id unique
+            hit = (tf, prepared)  # holding tf keeps the identity part of its key unique
             self._tf_cache[key] = hit
         return self._transfer_table(cplx, None, conj, prepared=hit[1])
 
@@ -1778,8 +1799,12 @@ def _use_stencil(pm):
         return False
     if pm.P == 1:
         return True
-    # several ranks: halo planes come from the immediate neighbours over peer memory
-    return _HALO_STENCIL and pm.rshape[0] >= 2 and pm._peer() is not None
+    # several ranks: halo planes come from the immediate neighbours over peer memory; the put
+    # kernel moves 16-byte words, so a slab must hold an even number of doubles (odd meshes
+    # keep the k-space gradients)
+    n0l, N1, N2 = pm.rshape
+    return _HALO_STENCIL and n0l >= 2 and (n0l * N1 * N2) % 2 == 0 and (N1 * N2) % 2 == 0 \
+        and pm._peer() is not None
 
 
 def drift_pos(pm, dx, p, fac, q):

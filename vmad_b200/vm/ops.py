@@ -16,7 +16,10 @@ The contract (vmad/core/operator.py:218-262, vmad/core/primitive.py:144-178):
 ``@autooperator`` turns a model-building function into an operator whose vjp / jvp replay the
 inner tape (vmad/core/autooperator.py).  Unlike the reference, the inner model is memoised per
 set of hyper-arguments instead of being rebuilt on every call (autooperator.py:133-156), since
-on a GPU backend model construction is pure host overhead.
+on a GPU backend model construction is pure host overhead.  The memo key is BY VALUE
+(``_hyper_key``): mutating a hyper-argument between calls yields the model of the new value, as
+the reference's rebuild would; hyper-arguments that cannot be fingerprinted disable the memo
+for that call.  ``AutoOperator.invalidate()`` drops the memo.
 """
 import inspect
 from collections import OrderedDict
@@ -348,20 +351,77 @@ def operator(kls):
 TAPENAME = '$$tape$$'
 
 
-def _hyper_key(value):
-    """memo key of one hyper-argument: by value for small immutables, else by identity"""
-    if value is None or isinstance(value, (bool, int, float, str)):
+class _Uncacheable(Exception):
+    """a hyper-argument whose state cannot be fingerprinted: the model is rebuilt on every call,
+    which is what the reference always does (vmad/core/autooperator.py:133-156)"""
+
+
+def _hyper_key(value, depth=0):
+    """Memo key of one hyper-argument -- BY VALUE, so that mutating a hyper-argument between two
+    calls selects (or builds) a different model instead of replaying a stale one:
+
+    * python / numpy scalars, strings, small arrays, lists and tuples: their contents;
+    * objects that declare ``__vmad_hyper_key__()`` (ParticleMesh, frozen device arrays,
+      MatterDominated, FastPMSimulation ...): what they return -- they vouch that everything a
+      model build reads from them is covered by that key;
+    * plain functions: identity + the keys of their closure cells and defaults;
+    * read-only numpy arrays: identity (they cannot be mutated in place);
+    * any other object or class: the keys of its public data attributes (a config object whose
+      ``k`` changes from 2 to 5 changes key).
+
+    Whatever does not fit (a writeable large array, an object holding one, recursion deeper
+    than 3) raises ``_Uncacheable`` and the caller rebuilds, like the reference.
+    """
+    if value is None or isinstance(value, (bool, int, float, complex, str, bytes)):
         return ('v', type(value).__name__, value)
     if isinstance(value, numpy.generic):
         return ('v', 'np', value.item())
-    if isinstance(value, numpy.ndarray) and value.size <= 4096 and value.dtype.kind in 'fiub':
-        return ('a', value.shape, value.dtype.str, value.tobytes())
-    if isinstance(value, (list, tuple)) and len(value) <= 4096:
+    if isinstance(value, numpy.ndarray):
+        if value.size <= 4096 and value.dtype.kind in 'fiubc':
+            return ('a', value.shape, value.dtype.str, value.tobytes())
+        if not value.flags.writeable and (value.base is None or not getattr(value.base, 'flags', value.flags).writeable):
+            return ('ro', id(value))
+        raise _Uncacheable("large writeable array")
+    if depth > 3:
+        raise _Uncacheable("nesting too deep")
+    if isinstance(value, (list, tuple)):
+        if len(value) > 4096:
+            raise _Uncacheable("long sequence")
+        return ('t', type(value).__name__, tuple(_hyper_key(v, depth + 1) for v in value))
+    if isinstance(value, dict):
+        if len(value) > 256:
+            raise _Uncacheable("large dict")
+        return ('d', tuple(sorted((repr(k), _hyper_key(v, depth + 1)) for k, v in value.items())))
+    hook = getattr(value, '__vmad_hyper_key__', None)
+    if hook is not None and not inspect.isclass(value):
         try:
-            return ('t', type(value).__name__, tuple(_hyper_key(v) for v in value))
-        except TypeError:
-            pass
-    return ('i', id(value))
+            return ('k', type(value).__name__, hook())
+        except TypeError as e:          # the object declines (e.g. a mutable device array)
+            raise _Uncacheable(str(e))
+    if hasattr(value, '__array__') or hasattr(value, '__cuda_array_interface__') or \
+            type(value).__module__.split('.')[0] in ('torch', 'scipy', 'pandas'):
+        raise _Uncacheable("array-like or foreign object of type %s" % type(value).__name__)
+    if inspect.isfunction(value) or inspect.ismethod(value):
+        fn = value.__func__ if inspect.ismethod(value) else value
+        cells = tuple(_hyper_key(c.cell_contents, depth + 1) for c in (fn.__closure__ or ()))
+        defaults = tuple(_hyper_key(d, depth + 1) for d in (fn.__defaults__ or ()))
+        owner = (_hyper_key(value.__self__, depth + 1),) if inspect.ismethod(value) else ()
+        return ('f', id(fn), cells, defaults, owner)
+    if inspect.isbuiltin(value) or isinstance(value, numpy.ufunc):
+        return ('b', id(value))
+    try:
+        attrs = vars(value)
+    except TypeError:
+        raise _Uncacheable("opaque object of type %s" % type(value).__name__)
+    items = []
+    for name in sorted(attrs):
+        if name.startswith('__') and name.endswith('__'):
+            continue
+        a = attrs[name]
+        if inspect.isroutine(a) or isinstance(a, (staticmethod, classmethod, property)):
+            continue
+        items.append((name, _hyper_key(a, depth + 1)))
+    return ('o', id(value) if inspect.isclass(value) else type(value).__qualname__, tuple(items))
 
 
 class AutoOperator(BaseOperator):
@@ -476,10 +536,29 @@ class AutoOperator(BaseOperator):
         if self.__bound_model__ is not None:
             return self.__bound_model__
         hyper = [(a, kwargs[a]) for a in self.argnames if a not in self.ain and a in kwargs]
-        key = tuple((a, _hyper_key(v)) for a, v in hyper)
-        hit = self._model_cache.get(key)
+        try:
+            key = tuple((a, _hyper_key(v)) for a, v in hyper)
+        except _Uncacheable:
+            return self._build_model(hyper)
+        # an instance-bound autooperator (FastPMSimulation.run ...) memoises on the instance, so
+        # that dropping the simulation drops its models (and the device arrays they hold)
+        cache = self._model_cache
+        if hyper:
+            own = getattr(hyper[0][1], '_vmad_model_cache', None)
+            if isinstance(own, dict):
+                cache = own.setdefault(id(self), OrderedDict())
+        hit = cache.get(key)
         if hit is not None:
+            cache.move_to_end(key)
             return hit[0]
+        m = self._build_model(hyper)
+        # keep the hyper-arguments alive next to the model so identity-based key parts stay unique
+        cache[key] = (m, [v for _, v in hyper] if cache is self._model_cache else None)
+        while len(cache) > 64:
+            cache.popitem(last=False)
+        return m
+
+    def _build_model(self, hyper):
         impl = self.prototype.main
         model_args = dict(hyper)
         with Builder() as m:
@@ -490,11 +569,12 @@ class AutoOperator(BaseOperator):
                 if argname not in r:
                     raise ModelError("output arg '%s' is not produced by the model" % argname)
             m.output(**r)
-        # keep the hyper-arguments alive next to the model so identity keys stay unique
-        self._model_cache[key] = (m, [v for _, v in hyper])
-        while len(self._model_cache) > 64:
-            self._model_cache.popitem(last=False)
         return m
+
+    def invalidate(self):
+        """drop every memoised model of this operator (after changing global state that a model
+        build reads and that no hyper-argument carries)"""
+        self._model_cache.clear()
 
     def build(__self__, **kwargs):
         """the model of this operator for the given hyper-parameters"""
