@@ -390,3 +390,39 @@ def test_routing_helpers_bit_exact(device_pm):
     a = dpm.readout3(fs[0], fs[1], fs[2], xs, gather=lay).numpy()
     b = lay.gather(dpm.readout3(fs[0], fs[1], fs[2], xs)).numpy()
     assert numpy.array_equal(a, b)
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+@pytest.mark.parametrize("Nmesh,BoxSize,n", [([8, 8, 8], 16.0, 3000), ([32, 32, 32], 100.0, 100000),
+                                             ([64, 16, 24], [200.0, 30.0, 11.0], 50000)])
+def test_route_build_bit_exact_vs_p_rank_oracle(oracle_pm, device_pm, P, Nmesh, BoxSize, n):
+    """`north_star`: bit-exact exchange routing.  vpm_route_build (owner of the floor plane + ghost
+    copy to the owner of plane + 1, per-destination input order, per-destination counts) against
+    the P-rank restatement of pmesh's decompose (oracle/pmesh/domain.py), for the particles of one
+    rank -- the routing of a rank does not depend on the others -- including every edge position"""
+    import ctypes
+    import torch
+    from pmesh import domain
+    from vmad_b200 import _capi as C
+    rng = numpy.random.default_rng(5 + P)
+    dpm = device_pm(Nmesh, BoxSize)
+    x = edge_positions(rng, Nmesh, BoxSize, n)
+    L0 = numpy.broadcast_to(numpy.asarray(BoxSize, dtype='f8'), (3,))[0]
+    # particles exactly on the slab boundaries and one ulp below them
+    ppr = Nmesh[0] // P
+    edges = numpy.array([k * ppr * (L0 / Nmesh[0]) for k in range(P + 1)])
+    extra = rng.uniform(0, 1, size=(2 * len(edges), 3)) * numpy.asarray(BoxSize)
+    extra[:len(edges), 0] = edges
+    extra[len(edges):, 0] = numpy.nextafter(edges, -numpy.inf)
+    x = numpy.concatenate([x, extra])
+    want_idx, want_start = domain.route(x, Nmesh, BoxSize, P)
+    xd = torch.from_numpy(numpy.ascontiguousarray(x)).cuda()
+    send_idx = torch.empty(2 * len(x), dtype=torch.int32, device='cuda')
+    start = (ctypes.c_int32 * (P + 1))()
+    rt = dpm.rt
+    rt.sync_stream()
+    C.check(C.lib.vpm_route_build(rt.ctx, ctypes.byref(dpm._mesh), P, ctypes.c_void_p(xd.data_ptr()), len(x),
+                                  ctypes.c_void_p(send_idx.data_ptr()), send_idx.shape[0], start))
+    got_start = numpy.array(list(start), dtype='i8')
+    assert numpy.array_equal(got_start, want_start)
+    assert numpy.array_equal(send_idx[:got_start[-1]].cpu().numpy(), want_idx)

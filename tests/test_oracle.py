@@ -114,3 +114,46 @@ def test_background_against_product():
     pd = P(0.3075)
     assert abs(pd.f1(0.01) - 1) < 1e-2
     assert abs(pd.D2(0.01) / pd.D1(0.01) ** 2 + 3. / 7) < 1e-2
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_p_rank_routing_oracle_matches_one_rank(oracle_pm, P):
+    """the P-rank restatement of decompose (oracle/pmesh/domain.py) pinned by what the reference
+    pins for layouts (test_fastpm.py:151-206: exchange then paint == paint): painting each rank's
+    arrivals onto its own slab only and stacking the slabs equals the 1-rank paint; every particle
+    reaches exactly the owners of the two planes it touches, in input order per destination"""
+    from pmesh import domain
+    N, L = 16, 100.0
+    pm = oracle_pm([N] * 3, L)
+    rng = numpy.random.default_rng(40 + P)
+    pos = [rng.uniform(-0.4 * L, 1.4 * L, size=(700 + 13 * r, 3)) for r in range(P)]
+    for r in range(P):                      # plane edges, the box edges, -eps
+        pos[r][:6, 0] = [0.0, L, -1e-14, L * (1 - 1e-16), L / N * (N // P), L / N * (N // P) - 1e-13]
+    mass = [rng.uniform(0.5, 1.5, size=len(p)) for p in pos]
+    d = domain.decompose_ranks(pos, [N] * 3, L)
+    ppr = N // P
+    full = numpy.zeros((N, N, N))
+    for dst in range(P):
+        xs = numpy.concatenate([pos[s][d['send_idx'][s][d['send_start'][s][dst]:d['send_start'][s][dst + 1]]]
+                                for s in range(P)])
+        ms = numpy.concatenate([mass[s][d['send_idx'][s][d['send_start'][s][dst]:d['send_start'][s][dst + 1]]]
+                                for s in range(P)])
+        assert numpy.array_equal(xs, numpy.concatenate([pos[s] for s in range(P)], axis=0)[
+            numpy.concatenate([numpy.cumsum([0] + [len(p) for p in pos])[s] + d['recv_idx'][dst][d['recv_src'][dst] == s]
+                               for s in range(P)])])
+        full[dst * ppr:(dst + 1) * ppr] = pm.paint(xs, ms).value[dst * ppr:(dst + 1) * ppr]
+        # the local cell sort of what arrived is non-decreasing in the ghost-plane keys and stable
+        keys = domain.ghost_keys(xs, [N] * 3, L, P, dst)
+        assert (numpy.diff(keys[d['perm'][dst]]) >= 0).all()
+        assert numpy.array_equal(d['perm'][dst], numpy.argsort(keys, kind='stable'))
+    one = pm.paint(numpy.concatenate(pos), numpy.concatenate(mass)).value
+    assert numpy.abs(full - one).max() < 1e-12
+    for s in range(P):
+        i0 = domain.floor_plane(pos[s][:, 0], N, L)
+        copies = numpy.bincount(d['send_idx'][s], minlength=len(pos[s]))
+        want = 1 + ((i0 // ppr) != (numpy.mod(i0 + 1, N) // ppr))
+        assert numpy.array_equal(copies, want)
+        for dst in range(P):                # input order within a destination
+            seg = d['send_idx'][s][d['send_start'][s][dst]:d['send_start'][s][dst + 1]]
+            assert (numpy.diff(seg) > 0).all()
+    assert d['counts'].sum() == sum(len(x) for x in d['send_idx'])

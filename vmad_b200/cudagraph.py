@@ -20,7 +20,7 @@ from .pm import runtime
 
 
 class GraphedCall(object):
-    def __init__(self, fn, warmup=2):
+    def __init__(self, fn, warmup=2, release_memory=False):
         rt = runtime()
         self.fn = fn
         self.stream = torch.cuda.Stream(device=rt.device)
@@ -33,6 +33,12 @@ class GraphedCall(object):
             for _ in range(max(1, warmup)):
                 fn()
         self.stream.synchronize()
+        if release_memory:
+            # the capture allocates from a private pool: hand the blocks the warm-up cached back
+            # to the driver first, or a tape-sized problem (100 GB at 512^3) is resident twice
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             self.outputs = fn()
