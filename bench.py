@@ -43,7 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-METRIC = "FastPM forward+vjp steps/s at 512^3"
+METRIC_FMT = "FastPM forward+vjp steps/s at %d^3"
 UNIT = "steps/s"
 SEED = 300
 
@@ -291,7 +291,7 @@ def run_reference(args):
     scale = (float(nm) / args.nmesh) ** 3
     value = args.nsteps / sec * scale
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "impl": "reference", "metric": METRIC_FMT % args.nmesh, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3 / scale, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -563,10 +563,35 @@ def run_main_problem(env, args, dims, label, steps, warmup, want_profile=True, w
     for _ in range(2):
         prob.step_resident()
     torch.cuda.synchronize()
+    res = dict()
+    if env.world > 1:
+        # the first steps ran with the exact routing (per-peer counts read back by the host on every
+        # decompose) and recorded those counts; now switch to fixed-capacity segments with the counts
+        # left on the device -- no host synchronisation inside a step, so it can be captured
+        ex_ms, _, _ = timed(env, prob.step_resident, 2, 0, label + " exact routing")
+        res['exact_routing_eager_ms_per_step'] = ex_ms / 2
+        dx_x, g_x = prob.step_resident()
+        res['routing'] = "exact (host reads the per-peer counts of every decompose)"
+        if not args.no_static:
+            try:
+                plan = prob.pm.plan_static_routing()
+                prob.step_resident()
+                dx_s, g_s = prob.step_resident()
+                prob.pm.check_routing()
+                res['static_routing_vs_exact'] = dict(
+                    gradient_rel_l2=rel_l2_across_ranks(env, g_s.t, g_x.t), dx_rel_l2=rel_l2_across_ranks(env, dx_s.t, dx_x.t),
+                    what="fixed-capacity routing (counts stay on the device) vs the exact routing, same step")
+                res['routing'] = ("fixed-capacity segments planned from the warm-up step (capacity matrix %s), counts "
+                                  "stay on the device: no host synchronisation inside a step" % plan.cap.tolist())
+                del dx_s, g_s
+            except Exception as e:
+                env.log("%s: static routing unavailable (%s)" % (label, str(e).splitlines()[0][:200]))
+                prob.pm._route_plan = None
+        del dx_x, g_x
     l0 = C.launch_count()
     prob.step_resident()
     launches_per_step = C.launch_count() - l0
-    res = dict(launches_per_step=int(launches_per_step))
+    res['launches_per_step'] = int(launches_per_step)
     # eager timing first (its memory goes back to the driver before a graph takes its own pool)
     eager_ms, eager_launches, _ = timed(env, prob.step_resident, max(2, min(steps, 5)), 1, label + " eager")
     res['eager_ms_per_step'] = eager_ms / max(2, min(steps, 5))
@@ -595,18 +620,22 @@ def run_main_problem(env, args, dims, label, steps, warmup, want_profile=True, w
     sampler = ClockSampler(env.local)
     use_graph = False
     fn = prob.step_resident
-    if try_graph and env.world == 1 and not args.no_graph:
+    if try_graph and not args.no_graph and (env.world == 1 or prob.pm._route_plan is not None):
         from vmad_b200.cudagraph import GraphedCall
         try:
             gc.collect()
             torch.cuda.empty_cache()
             graphed = GraphedCall(prob.step_resident, warmup=1, release_memory=True)
             use_graph = True
-
-            def fn():
-                return graphed()
         except Exception as e:      # typically: the graph's private pool does not fit beside the tape
             env.log("%s: CUDA graph capture failed (%s); timing the eager step" % (label, str(e).splitlines()[0][:200]))
+        if env.world > 1 and int(round(env.sum_over_ranks(1.0 if use_graph else 0.0)[0])) != env.world:
+            use_graph = False       # all ranks or none: a replay spins on flags only another replay raises
+        if use_graph:
+            def fn():
+                return graphed()
+        else:
+            graphed = None
             gc.collect()
             torch.cuda.empty_cache()
     if clocks and env.rank == 0:
@@ -614,6 +643,8 @@ def run_main_problem(env, args, dims, label, steps, warmup, want_profile=True, w
     total_ms, launches, wall = timed(env, fn, steps, warmup, label + (" graph" if use_graph else " resident"),
                                      launches_per_call=launches_per_step if use_graph else None)
     res['clocks'] = sampler.stop() if (clocks and env.rank == 0) else None
+    if env.world > 1:
+        prob.pm.check_routing()
     res.update(ms_per_step=total_ms / steps, launches=launches, use_graph=use_graph, host_wall_s=wall)
     if use_graph:
         dx_g, g_g = fn()
@@ -855,6 +886,8 @@ def run_gpu(args):
         parity['e2e_host_results_vs_resident'] = main['e2e_result_vs_resident']
     if main.get('graph_vs_eager_rel_l2') is not None:
         parity['graph_replay_vs_eager_gradient_rel_l2'] = main['graph_vs_eager_rel_l2']
+    if main.get('static_routing_vs_exact') is not None:
+        parity['static_routing_vs_exact'] = main['static_routing_vs_exact']
     eager_result = main.pop('eager_result')
     if world > 1 and not args.no_side:
         try:
@@ -886,6 +919,8 @@ def run_gpu(args):
             value=world * args.nsteps / (w['ms_per_step'] * 1e-3), unit=UNIT, ms_per_step=w['ms_per_step'],
             e2e_value=world * args.nsteps / (w['e2e_ms_per_step'] * 1e-3), eager_ms_per_step=w['eager_ms_per_step'],
             global_mesh=dims, launches_per_step=w['launches_per_step'], cuda_graph=w['use_graph'],
+            routing=w.get('routing'), exact_routing_eager_ms_per_step=w.get('exact_routing_eager_ms_per_step'),
+            static_routing_vs_exact=w.get('static_routing_vs_exact'),
             graph_vs_eager_rel_l2=w.get('graph_vs_eager_rel_l2'),
             roofline=roofline_from_profile(wprof, args.side_nmesh, sum(e.get('algorithmic_bytes_per_call', 0.0) * e['calls'] for e in wprof['entry_points']), w['ms_per_step']))
         env.log("side record done at %.0f s" % (time.perf_counter() - t_start))
@@ -941,7 +976,7 @@ def run_gpu(args):
                         bad.append((k, kk, vv))
         gvals = [v for k, d in parity.items() if isinstance(d, dict) for kk, v in d.items() if kk == 'gradient_rel_l2']
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_FMT % args.nmesh, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(N, args.nsteps),
@@ -954,6 +989,7 @@ def run_gpu(args):
                                "launches per replay)" % main['launches_per_step']) if main['use_graph']
                     else "eager (python VM + ctypes, one launch per kernel)",
                     "eager_ms_per_step": main['eager_ms_per_step'], "launches_per_step": main['launches_per_step'],
+                    "routing": main.get('routing'), "exact_routing_eager_ms_per_step": main.get('exact_routing_eager_ms_per_step'),
                     "peak_hbm_gb": main['peak_hbm_gb'], "wall_s_total": time.perf_counter() - t_start},
             "clocks": main['clocks'],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main['h2d'], "d2h_bytes_per_step": main['d2h'],
@@ -1098,6 +1134,7 @@ def main():
                     help='largest mesh the CPU arm / cpu_baseline leg will run (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run every step eagerly through the VM')
+    ap.add_argument('--no-static', action='store_true', help='keep the exact (host-synchronised) particle routing across ranks')
     ap.add_argument('--no-side', action='store_true', help='main record only')
     ap.add_argument('--no-large', action='store_true', help='skip the 8-GPU configs[3] / configs[4] side records')
     ap.add_argument('--micro', action='store_true', help='CIC paint / readout microbenchmark instead')

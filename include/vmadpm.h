@@ -119,6 +119,15 @@ int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv
  * MPI_Alltoall of counts does inside pmesh's decompose).  send_capacity >= 2 np is always safe. */
 int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double* x, int64_t np,
                     int32_t* send_idx, int64_t send_capacity, int32_t* send_start_host);
+/* The same routing with FIXED-CAPACITY segments and no host synchronisation (what makes a
+ * multi-rank step capturable in a CUDA graph): destination d owns positions
+ * [seg_start_host[d], seg_start_host[d+1]) of send_idx; positions beyond the rows actually bound
+ * for d hold -1.  counts (device, nranks + 1 ints; counts[nranks] must be zero-initialised by the
+ * caller once) receives the number of rows per destination and, in counts[nranks], a sticky flag
+ * that is set when a segment was too small (the surplus rows are dropped: the caller checks the
+ * flag when it next synchronises and re-plans the capacities). */
+int vpm_route_build_static(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double* x, int64_t np,
+                           const int32_t* seg_start_host, int32_t* send_idx, int32_t* counts);
 
 /* ---- paint  (fastpm.py:224,238,256; pmesh ParticleMesh.paint / paint_jvp and the
  *      mesh half of RealField.readout_vjp) ---------------------------------- */
@@ -232,38 +241,42 @@ int vpm_fft_c2c_axis0_oop(vpm_ctx* ctx, int64_t n0, int64_t inner, const double*
  * of the local array straight into rank d's receive buffer over NVLink,
  *   peer_bufs[d][dst_off + i * inner + c] = src[i * s_row + d * s_dst + c]   (complex128),
  * peer_bufs / peer_flags are device pointers valid in THIS process for every rank's receive
- * buffer / flag array (CUDA IPC mappings; entry [me] is the local one).  vpm_peer_signal raises
- * flags[slot] = epoch on every rank after the preceding kernels of the stream; vpm_peer_wait
- * spins on the local flag array until all nranks entries reach epoch (traps after ~minutes). */
+ * buffer / flag block (CUDA IPC mappings; entry [me] is the local one). */
 /* receive areas live outside the caller's allocator so that they can be exported: alloc returns
  * a zeroed device buffer and its 64-byte CUDA IPC handle; open maps another process's buffer. */
 int vpm_peer_alloc(vpm_ctx* ctx, int64_t nbytes, void** ptr, unsigned char* handle64);
 int vpm_peer_open(vpm_ctx* ctx, const unsigned char* handle64, void** ptr);
 int vpm_peer_close(vpm_ctx* ctx, void* ptr);
 int vpm_peer_free(vpm_ctx* ctx, void* ptr);
-/* Flag protocol carried by a put launch (NULL or mode 0: none).  Every rank owns a flag array of
- * 2 * nranks int64: [0, nranks) data flags (slot s = "rank s delivered transfer e"), [nranks,
- * 2 nranks) ack flags (slot s = "rank s finished reading its receive area of transfer e").
- * peer_flags[d] = rank d's array as mapped here, my_flags = my own.  mode bits, for transfer
- * `epoch` (1, 2, ... in lock step on all ranks; receive area epoch % 2):
- *   RAISE_ACK  at kernel start raise ack[rank] = epoch - 1 on every rank (the consumer of the
- *              previous transfer precedes this launch on the stream);
- *   WAIT_ACK   before storing wait until my ack flags reached epoch - 2;
- *   SIGNAL     after the stores the last thread block raises data[rank] = epoch on every rank
- *              (counter = zeroed device word owned by the caller);
- *   WAIT_DATA  ... and then waits until my data flags reached epoch, so that the kernel's
- *              completion means "my receive area is complete". */
+/* Flag protocol carried by a put launch (NULL or mode 0: none).  Every rank owns a flag block
+ * of VPM_PEER_FLAG_WORDS int64 (vpm_peer_alloc, zero-initialised, mapped by every peer):
+ * data[b][s] ("rank s delivered its transfer number e on receive buffer b"), ack[b][s] ("rank s
+ * finished reading what transfer e put into its buffer b"), a four-word mailbox per (b, s) and the
+ * rank's own protocol state (transfers completed per buffer, buffer of the last transfer).  The
+ * transfer numbering lives in that state ON THE DEVICE -- the host only alternates `buf` -- so a
+ * CUDA graph holding put launches can be replayed.  peer_flags[d] = rank d's block as mapped
+ * here, my_flags = my own.  mode bits for a transfer on receive buffer `buf`:
+ *   RAISE_ACK  at kernel start acknowledge my previous transfer to every rank (its consumer
+ *              precedes this launch on the stream);
+ *   WAIT_ACK   before storing wait until every rank acknowledged the previous transfer that used
+ *              buffer `buf`;
+ *   SIGNAL     after the stores the last thread block raises data[buf][rank] on every rank;
+ *   WAIT_DATA  ... and then waits until all of my data flags arrived, so that the kernel's
+ *              completion means "my receive area is complete".
+ * A wait that exceeds the spin limit (default 2^31 naps of 64 ns; vpm_peer_set_spin_limit)
+ * prints a message and traps: a dead peer produces a launch failure, not a hung device. */
 #define VPM_PEER_RAISE_ACK 1
 #define VPM_PEER_WAIT_ACK 2
 #define VPM_PEER_SIGNAL 4
 #define VPM_PEER_WAIT_DATA 8
+#define VPM_PEER_FLAG_WORDS 128
 typedef struct vpm_peer_sync {
     const uint64_t* peer_flags;
-    const int64_t* my_flags;
+    int64_t* my_flags;
     int32_t rank;
     int32_t mode;
-    int64_t epoch;
-    uint32_t* counter;
+    int32_t buf;
+    int32_t reserved;
 } vpm_peer_sync;
 int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
                  int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
@@ -279,12 +292,21 @@ int vpm_peer_put_to(vpm_ctx* ctx, int nranks, uint32_t dest_mask, int64_t count,
  * dst_base[d] + p - seg_start[d] of peer d's receive area (ncomp doubles per row).
  * idx_is_src=1: p = j, source row idx[j] (exchange); idx_is_src=0: p = idx[j], source row j
  * (gather, idx = the local sort permutation).  Rows of segment skip_seg (-1: none) are not
- * transferred: rows staying on this rank bypass the receive area (vpm_route_compose). */
+ * transferred: rows staying on this rank bypass the receive area (vpm_route_compose).
+ * Fixed-capacity segments (vpm_route_build_static; the counts stay on the device):
+ *   seg_count  (device, nranks ints or NULL) gather direction: only the first seg_count[d] rows
+ *              of segment d hold particles;
+ *   mail       (device, nranks ints or NULL) posted to the peers' mailboxes with this transfer
+ *              (the per-destination row counts of the routing; vpm_peer_read_mail);
+ *   sentinel3  (host, 3 doubles or NULL) exchange direction: a row without a particle
+ *              (idx[j] < 0) is stored as this position instead of being skipped. */
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
                       const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
-                      const int64_t* dst_base, const uint64_t* peer_bufs, const vpm_peer_sync* sync);
-int vpm_peer_signal(vpm_ctx* ctx, int nranks, int slot, const uint64_t* peer_flags, int64_t epoch);
-int vpm_peer_wait(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int64_t epoch);
+                      const int64_t* dst_base, const int32_t* seg_count, const int32_t* mail,
+                      const double* sentinel3, const uint64_t* peer_bufs, const vpm_peer_sync* sync);
+/* counts[s] = what rank s posted with the last transfer on receive buffer `buf` */
+int vpm_peer_read_mail(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int buf, int32_t* counts);
+int vpm_peer_set_spin_limit(vpm_ctx* ctx, uint64_t spins);
 /* dst[b][a][:] = src[a][b][:] for [a, b, c] complex128 */
 int vpm_swap_leading_axes(vpm_ctx* ctx, int64_t a, int64_t b, int64_t c, const double* src,
                           double* dst);

@@ -66,6 +66,39 @@ def main():
     omesh, ox = of.readout_vjp(x_all, v_all)
     errs['readout_vjp_mesh'] = rel(_mesh.numpy(), omesh.value[rs])
     errs['readout_vjp_x'] = rel(_x.numpy(), ox[mine])
+    # ---- bit-exact exchange routing against the P-rank restatement of pmesh's decompose ------------
+    from pmesh import domain
+    orc = domain.decompose_ranks([x_all[slice(r, None, P)] for r in range(P)], [N] * 3, L)
+
+    def check_routing(lay, tag):
+        bad = 0
+        if hasattr(lay, 'plan'):        # fixed-capacity segments: compare segment by segment
+            plan = lay.plan
+            sidx = lay.send_idx.cpu().numpy()
+            idx = lay.indices.cpu().numpy()
+            for d in range(P):
+                want = orc['send_idx'][rank][orc['send_start'][rank][d]:orc['send_start'][rank][d + 1]]
+                seg = sidx[plan.sbase[d]:plan.sbase[d + 1]]
+                bad += not numpy.array_equal(seg[:len(want)], want)
+                bad += not (seg[len(want):] == -1).all()
+            bad += not numpy.array_equal(lay.scnt.cpu().numpy()[:P], orc['counts'][rank])
+            bad += not numpy.array_equal(lay.rcnt.cpu().numpy(), orc['counts'][:, rank])
+            # sorted slot -> physical receive row -> (source, k) -> position in the packed receive order
+            nrecv = int(orc['counts'][:, rank].sum())
+            rb = numpy.array(plan.rbase)
+            src = numpy.searchsorted(rb, idx[:nrecv], side='right') - 1
+            k = idx[:nrecv] - rb[src]
+            packed = numpy.concatenate([[0], numpy.cumsum(orc['counts'][:, rank])])[src] + k
+            bad += not (k < orc['counts'][src, rank]).all()
+            bad += not numpy.array_equal(packed, orc['perm'][rank])
+        else:
+            bad += not numpy.array_equal(lay.send_idx.cpu().numpy(), orc['send_idx'][rank])
+            bad += not numpy.array_equal(numpy.array(lay.send_start), orc['send_start'][rank])
+            bad += not numpy.array_equal(numpy.array(lay.recv_counts), orc['counts'][:, rank])
+            bad += not numpy.array_equal(lay.indices.cpu().numpy(), orc['perm'][rank])
+        errs['routing_bit_exact_' + tag] = float(bad)
+
+    check_routing(lay, 'exact')
     a = rng.standard_normal((20000, 3))
     errs['gather_exchange'] = rel(lay.gather(lay.exchange(a[mine])).numpy() /
                                   numpy.maximum(1.0, lay.gather(lay.exchange(numpy.ones(len(x)))).numpy()[:, None]),
@@ -101,6 +134,48 @@ def main():
     errs['lean_dx'] = rel(ddx.numpy(), odx[ps])
     errs['lean_vjp'] = rel(dg.numpy(), numpy.asarray(og)[:, cs])
     pm.force_recompute = False
+
+    # ---- fixed-capacity routing (counts stay on the device): same integers, same results ---------
+    pm.plan_static_routing()
+    lay = pm.decompose(x)
+    check_routing(lay, 'static')
+    errs['static_paint'] = rel(pm.paint(x, m, layout=lay).numpy(), opm.paint(x_all, m_all).value[rs])
+    errs['static_readout'] = rel(df.readout(x, layout=lay).numpy(), of.readout(x_all)[mine])
+    _mesh, _x = df.readout_vjp(x, v_all[mine], layout=lay)
+    errs['static_readout_vjp_mesh'] = rel(_mesh.numpy(), omesh.value[rs])
+    errs['static_readout_vjp_x'] = rel(_x.numpy(), ox[mine])
+    md = nbody_model(pm, q, stages)
+    cots = dict(_dx=put(cot_all[ps]), _p=put(cot_all[ps] * 0.5), _f=put(cot_all[ps] * 0.25))
+    x0 = pm.create('complex', value=wn)
+    (ddx, dp, dfo), (dg,) = md.compute_with_vjp(init=dict(x=x0), v=cots)
+    pm.check_routing()
+    errs['static_nbody_dx'] = rel(ddx.numpy(), odx[ps])
+    errs['static_nbody_p'] = rel(dp.numpy(), op_[ps])
+    errs['static_nbody_f'] = rel(dfo.numpy(), of_[ps])
+    errs['static_nbody_vjp'] = rel(dg.numpy(), numpy.asarray(og)[:, cs])
+    # ... and the whole P-rank forward + vjp captured into a CUDA graph on every rank and replayed
+    from vmad_b200.cudagraph import GraphedCall
+
+    def call():
+        (a_, b_, c_), (g_,) = md.compute_with_vjp(init=dict(x=x0), v=cots)
+        return a_, g_
+
+    step = GraphedCall(call, warmup=1)
+    for _ in range(3):
+        gdx, gg = step()
+    torch.cuda.synchronize()
+    pm.check_routing()
+    errs['graph_nbody_dx'] = rel(gdx.numpy(), odx[ps])
+    errs['graph_nbody_vjp'] = rel(gg.numpy(), numpy.asarray(og)[:, cs])
+    # an overflowing plan is reported, collectively
+    small = numpy.full((P, P), 8, dtype='i8')
+    pm.plan_static_routing(cap=small)
+    pm.decompose(x)
+    try:
+        pm.check_routing()
+        errs['overflow_detected'] = 1.0
+    except Exception:
+        errs['overflow_detected'] = 0.0
 
     bad = {k: v for k, v in errs.items() if not v < 1e-10}
     print("rank %d/%d: %s" % (rank, P, {k: '%.1e' % v for k, v in errs.items()}), flush=True)

@@ -175,7 +175,10 @@ def test_cuda_graph_replay_matches_eager(oracle_pm, device_pm):
     q = opm.generate_uniform_particle_grid(shift=0.0)
     stages = numpy.linspace(0.1, 1.0, nsteps + 1)
     cot = rng.standard_normal(q.shape)
-    m = nbody_model(dpm, q, stages)
+    # a constant of the graph must be a device array (or a read-only host array): a writeable
+    # numpy q cannot key the model memo, so every call would rebuild the model and upload q again
+    # -- as the reference does -- which a capture forbids
+    m = nbody_model(dpm, dpm.asparticles(q), stages)
     x = dpm.create('complex', value=wn1)
     c = put(cot)
 

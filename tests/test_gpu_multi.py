@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_ranks_match_one_rank_oracle(world):
     """world = 4 also exercises distinct previous / next neighbours in the halo exchange"""
     import torch
@@ -25,3 +25,12 @@ def test_ranks_match_one_rank_oracle(world):
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     assert 'FAILED' not in r.stdout, tail
+
+
+def test_peer_wait_traps_instead_of_hanging():
+    """a dead peer produces an error, not a hung device: the flag wait of a put gives up after the
+    spin limit (one GPU is enough: the 'peer' is a second flag block nobody signals)"""
+    cmd = [sys.executable, os.path.join(ROOT, 'tests', 'peer_timeout_worker.py')]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert 'TRAPPED' in r.stdout

@@ -45,10 +45,11 @@ _I3 = c_int64 * 3
 # name -> (restype, argtypes); every name here must be declared in include/vmadpm.h
 class vpm_peer_sync(Structure):
     _fields_ = [('peer_flags', POINTER(c_uint64)), ('my_flags', c_void_p), ('rank', c_int32),
-                ('mode', c_int32), ('epoch', c_int64), ('counter', c_void_p)]
+                ('mode', c_int32), ('buf', c_int32), ('reserved', c_int32)]
 
 
 PEER_RAISE_ACK, PEER_WAIT_ACK, PEER_SIGNAL, PEER_WAIT_DATA = 1, 2, 4, 8
+PEER_FLAG_WORDS = 128
 
 
 SIGNATURES = {
@@ -68,6 +69,7 @@ SIGNATURES = {
     'vpm_layout_build': (c_int, [c_void_p, POINTER(vpm_mesh), _P, c_int64, _P, _P, _P]),
     'vpm_route_build': (c_int, [c_void_p, POINTER(vpm_mesh), c_int, _P, c_int64, _P, c_int64,
                                 POINTER(c_int32)]),
+    'vpm_route_build_static': (c_int, [c_void_p, POINTER(vpm_mesh), c_int, _P, c_int64, POINTER(c_int32), _P, _P]),
     'vpm_take_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_take_rows_scaled': (c_int, [c_void_p, _P, _P, c_int64, c_int, c_double, _P]),
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
@@ -105,9 +107,10 @@ SIGNATURES = {
     'vpm_peer_put_to': (c_int, [c_void_p, c_int, ctypes.c_uint32, c_int64, _P, POINTER(c_uint64), c_int64,
                                 POINTER(vpm_peer_sync)]),
     'vpm_peer_put_rows': (c_int, [c_void_p, c_int, c_int64, c_int, _P, _P, c_int, c_int, POINTER(c_int32),
-                                  POINTER(c_int64), POINTER(c_uint64), POINTER(vpm_peer_sync)]),
-    'vpm_peer_signal': (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_int64]),
-    'vpm_peer_wait': (c_int, [c_void_p, c_int, _P, c_int64]),
+                                  POINTER(c_int64), _P, _P, POINTER(c_double), POINTER(c_uint64),
+                                  POINTER(vpm_peer_sync)]),
+    'vpm_peer_read_mail': (c_int, [c_void_p, c_int, _P, c_int, _P]),
+    'vpm_peer_set_spin_limit': (c_int, [c_void_p, c_uint64]),
     'vpm_swap_leading_axes': (c_int, [c_void_p, c_int64, c_int64, c_int64, _P, _P]),
     'vpm_transfer': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double, c_int, _P, _P, _P,
                              _P, _P, _P, c_int]),

@@ -363,6 +363,54 @@ k_route_scatter(Geo g, int planes_per_rank, int P, const double* __restrict__ x,
     }
 }
 
+// fixed-capacity variant: destination d owns positions [seg[d], seg[d + 1]) of the send order
+struct RouteSegs {
+    int start[ROUTE_MAXP + 1];
+};
+
+__global__ void __launch_bounds__(ROUTE_THREADS)
+k_route_scatter_static(Geo g, int planes_per_rank, int P, const double* __restrict__ x, long long np,
+                       long long nblocks, const int* __restrict__ offsets /* [P][nblocks] */,
+                       RouteSegs seg, int* __restrict__ send_idx) {
+    __shared__ int warp_cnt[ROUTE_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int r0 = -1, r1 = -1;
+    if (p < np) route_of(g, planes_per_rank, x, p, r0, r1);
+    for (int d = 0; d < P; ++d) {
+        const bool mine = (r0 == d) || (r1 == d);
+        const unsigned b = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) warp_cnt[w] = __popc(b);
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < w; ++k) base += warp_cnt[k];
+        if (mine) {
+            // rank of this row among the rows bound for d (input order): rows before this block +
+            // rows of this block before this thread
+            const int rank = offsets[d * nblocks + blockIdx.x] - offsets[d * nblocks] + base +
+                             __popc(b & ((1u << lane) - 1));
+            if (rank < seg.start[d + 1] - seg.start[d]) send_idx[seg.start[d] + rank] = (int)p;
+        }
+        __syncthreads();
+    }
+}
+
+// counts[d] = rows bound for d (clipped to the capacity), counts[P] = 1 when a segment overflowed
+// (sticky: OR-ed into what is there)
+__global__ void k_route_totals_static(int P, long long nblocks, const int* __restrict__ offsets,
+                                      const int* __restrict__ counts_in, RouteSegs seg,
+                                      int* __restrict__ counts /* [P + 1] */) {
+    int d = threadIdx.x;
+    if (d < P) {
+        const long long first = (long long)d * nblocks;
+        const long long end = (long long)(d + 1) * nblocks - 1;
+        const int total = offsets[end] + counts_in[end] - offsets[first];
+        const int cap = seg.start[d + 1] - seg.start[d];
+        counts[d] = min(total, cap);
+        if (total > cap) atomicOr(counts + P, 1);
+    }
+}
+
 __global__ void k_route_totals(int P, long long nblocks, long long nsend_total_index,
                                const int* __restrict__ offsets, const int* __restrict__ counts,
                                int* __restrict__ totals /* [P + 1] */) {
@@ -416,6 +464,46 @@ int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double
         VPM_REQUIRE(x && send_idx, "NULL array");
         VPM_LAUNCH(k_route_scatter, (unsigned)nblocks, ROUTE_THREADS, 0, st, g, ppr, nranks, x,
                    (long long)np, nblocks, offsets, send_idx);
+    }
+    VPM_API_END
+}
+
+int vpm_route_build_static(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double* x, int64_t np,
+                           const int32_t* seg_start_host, int32_t* send_idx, int32_t* counts) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("route_build", 28.0 * np);
+    VPM_REQUIRE(ctx && mesh && seg_start_host && send_idx && counts, "NULL argument");
+    VPM_REQUIRE(nranks >= 1 && nranks <= ROUTE_MAXP, "unsupported number of ranks");
+    VPM_REQUIRE(mesh->n[0] % nranks == 0, "mesh planes must divide evenly over the ranks");
+    VPM_REQUIRE(np >= 0 && 2 * np < (1LL << 31) - 1, "particle count must fit int32");
+    vpm_mesh m = *mesh;  // routing only needs the global geometry
+    m.start0 = 0;
+    m.nloc0 = m.n[0];
+    m.ghost = 0;
+    Geo g = make_geo(&m);
+    const int ppr = (int)(mesh->n[0] / nranks);
+    cudaStream_t st = ctx->stream;
+    RouteSegs seg;
+    for (int d = 0; d <= ROUTE_MAXP; ++d) seg.start[d] = seg_start_host[d <= nranks ? d : nranks];
+    for (int d = 0; d < nranks; ++d) VPM_REQUIRE(seg.start[d + 1] >= seg.start[d], "segments must be ordered");
+    // positions without a particle keep -1
+    VPM_PROF_CALL("memset(send_idx)", st,
+                  VPM_CUDA(cudaMemsetAsync(send_idx, 0xff, (size_t)seg.start[nranks] * sizeof(int), st)));
+    const long long nblocks = std::max<long long>(1, ceil_div(np, ROUTE_THREADS));
+    const long long ncount = (long long)nranks * nblocks;
+    const long long ntmp = scan_tmp_ints(ncount);
+    int* ws = (int*)ctx->workspace((size_t)(2 * ncount + ntmp + 8) * sizeof(int));
+    int* blk_counts = ws;
+    int* offsets = blk_counts + ncount;
+    int* tmp = offsets + ncount;
+    VPM_LAUNCH(k_route_count, (unsigned)nblocks, ROUTE_THREADS, 0, st, g, ppr, nranks, x,
+               (long long)np, nblocks, blk_counts);
+    exclusive_scan(st, blk_counts, ncount, offsets, tmp);
+    VPM_LAUNCH(k_route_totals_static, 1, ROUTE_MAXP, 0, st, nranks, nblocks, offsets, blk_counts, seg, counts);
+    if (np > 0) {
+        VPM_REQUIRE(x, "NULL array");
+        VPM_LAUNCH(k_route_scatter_static, (unsigned)nblocks, ROUTE_THREADS, 0, st, g, ppr, nranks, x,
+                   (long long)np, nblocks, offsets, seg, send_idx);
     }
     VPM_API_END
 }

@@ -15,30 +15,43 @@ struct PeerPtrs {
     unsigned long long p[8];
 };
 
-// The whole flag protocol rides on the put launches (one launch per transfer instead of four):
-//   start  - CTA 0 raises ack[me] = epoch - 1 on every peer (stream order guarantees that the
-//            consumer of the previous transfer has finished reading my receive area);
-//          - every CTA makes sure all peers acknowledged transfer epoch - 2, the previous use of
-//            the receive area about to be overwritten (double buffering);
-//   end    - the last CTA to finish (device counter) raises data[me] = epoch on every peer and
-//            then waits until all of MY data flags reached epoch: when the kernel completes,
-//            the receive area is complete, and the next kernel of the stream (cuFFT, the local
-//            gather) can read it.
-// A rank's put never waits for something that only a later kernel of a peer provides (acks of
-// e - 2 are raised by the peer's put e - 1 at the latest), so the scheme cannot deadlock.
+// The whole flag protocol rides on the put launches (one launch per transfer instead of four)
+// and its state lives ON THE DEVICE, so that a captured CUDA graph can be replayed: a rank's
+// flag block (VPM_PEER_FLAG_WORDS int64, allocated by vpm_peer_alloc, mapped by every peer) holds
+//   data[b][s]  "rank s delivered its transfer number e on receive buffer b"
+//   ack[b][s]   "rank s finished reading what transfer e put into ITS buffer b"
+//   mail[b][s]  four words rank s may post together with a transfer (per-destination row counts)
+//   eb[b], last_b   my own state: transfers completed on buffer b, buffer of my last transfer
+// For a transfer on buffer b (the host alternates b; the numbering e = eb[b] + 1 is read from the
+// device, in lock step on all ranks because all ranks issue the same sequence of transfers):
+//   start  - CTA 0 acknowledges my previous transfer (buffer last_b, number eb[last_b]) to every
+//            peer: stream order guarantees that its consumer has finished reading my receive area;
+//          - every CTA makes sure all peers acknowledged transfer e - 1 of buffer b, the previous
+//            use of the receive area about to be overwritten (double buffering);
+//   end    - the last CTA to finish (device counter) raises data[b][me] = e on every peer, waits
+//            until all of MY data flags reached e, then advances eb[b] and last_b: when the kernel
+//            completes, the receive area is complete, and the next kernel of the stream (cuFFT,
+//            the local gather) can read it.
+// Every put raises its acknowledgement BEFORE it waits for anything, and waits only for
+// acknowledgements that the peers' next put raises unconditionally, so the scheme cannot deadlock
+// (also when a replayed graph starts on the buffer the previous replay ended on).
+constexpr int W_DATA = 0, W_ACK = 16, W_MAIL = 32, W_EB = 96, W_LASTB = 98, W_COUNTER = 99, W_ERROR = 100;
+static_assert(W_ERROR < VPM_PEER_FLAG_WORDS, "flag block too small");
+
 struct PeerSync {
-    PeerPtrs flags;               // every rank's flag array: [0, P) data flags, [P, 2P) ack flags
-    const long long* my_flags;    // my own flag array
+    PeerPtrs flags;               // every rank's flag block as mapped here
+    long long* mine;              // my own flag block
     int rank;
     int mode;                     // VPM_PEER_* bits
-    long long epoch;
-    unsigned* counter;            // zero-initialised device word, reset by the last CTA
+    int buf;                      // receive buffer of this transfer (0 / 1)
 };
+
+__device__ unsigned long long g_peer_spin_limit = 1ull << 31;   // ~2 minutes of 64 ns naps
 
 __device__ __forceinline__ void peer_spin(const volatile long long* f, long long want, const char* what) {
     unsigned long long spins = 0;
     while (*f < want) {
-        if (++spins > (1ull << 31)) {
+        if (++spins > g_peer_spin_limit) {
             printf("vmadpm: peer %s wait timed out (flag = %lld, want %lld)\n", what, *f, want);
             __trap();
         }
@@ -46,14 +59,23 @@ __device__ __forceinline__ void peer_spin(const volatile long long* f, long long
     }
 }
 
+// number of the transfer this launch belongs to (my previous launches on the stream wrote eb[])
+__device__ __forceinline__ long long peer_epoch(const PeerSync& sy) { return sy.mine[W_EB + sy.buf] + 1; }
+
 __device__ __forceinline__ void peer_acquire(int P, const PeerSync& sy) {
+    if (!sy.mode) return;
+    const long long e = peer_epoch(sy);
     if ((sy.mode & VPM_PEER_RAISE_ACK) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 &&
         (int)threadIdx.x < P) {
-        volatile long long* f = reinterpret_cast<volatile long long*>(sy.flags.p[threadIdx.x]);
-        f[P + sy.rank] = sy.epoch - 1;
+        const int pb = (int)sy.mine[W_LASTB];
+        const long long pe = sy.mine[W_EB + pb];
+        if (pe > 0) {
+            volatile long long* f = reinterpret_cast<volatile long long*>(sy.flags.p[threadIdx.x]);
+            f[W_ACK + 8 * pb + sy.rank] = pe;
+        }
     }
     if (sy.mode & VPM_PEER_WAIT_ACK) {
-        if ((int)threadIdx.x < P) peer_spin(sy.my_flags + P + threadIdx.x, sy.epoch - 2, "ack");
+        if ((int)threadIdx.x < P) peer_spin(sy.mine + W_ACK + 8 * sy.buf + threadIdx.x, e - 1, "ack");
         __syncthreads();
     }
 }
@@ -61,21 +83,25 @@ __device__ __forceinline__ void peer_acquire(int P, const PeerSync& sy) {
 __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
     __threadfence_system();
     if (!(sy.mode & VPM_PEER_SIGNAL)) return;
+    const long long e = peer_epoch(sy);     // read before the last CTA advances it
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(sy.counter, 1u);
+        unsigned* counter = reinterpret_cast<unsigned*>(sy.mine + W_COUNTER);
+        const unsigned done = atomicAdd(counter, 1u);
         if (done == gridDim.x * gridDim.y * gridDim.z - 1) {
-            *sy.counter = 0;
+            *counter = 0;
             __threadfence_system();
             for (int d = 0; d < P; ++d) {
                 volatile long long* f = reinterpret_cast<volatile long long*>(sy.flags.p[d]);
-                f[sy.rank] = sy.epoch;
+                f[W_DATA + 8 * sy.buf + sy.rank] = e;
             }
             __threadfence_system();
             if (sy.mode & VPM_PEER_WAIT_DATA) {
-                for (int d = 0; d < P; ++d) peer_spin(sy.my_flags + d, sy.epoch, "data");
+                for (int d = 0; d < P; ++d) peer_spin(sy.mine + W_DATA + 8 * sy.buf + d, e, "data");
                 __threadfence_system();
             }
+            sy.mine[W_EB + sy.buf] = e;
+            sy.mine[W_LASTB] = sy.buf;
         }
     }
 }
@@ -109,6 +135,11 @@ k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_
 struct PeerSegs {
     int start[9];            // segment boundaries in the routing order (P + 1 used)
     long long base[8];       // first destination row of my segment in peer d's receive area
+    const int* cnt;          // fixed-capacity segments, gather direction: only rows [start[d], start[d] +
+                             // cnt[d]) of segment d hold particles (NULL: every row does)
+    const int* mail;         // my per-destination row counts, posted to peer d's mailbox (NULL: none)
+    int fill;                // exchange direction: positions without a particle (idx < 0) are stored as
+    double sentinel[3];      // this row (a position no rank's slab covers); else they are skipped
 };
 
 // Particle rows to their destination ranks, pack and transfer fused.  Routing order position p
@@ -122,6 +153,11 @@ k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
                 const int* __restrict__ idx, int idx_is_src, int skip_seg, PeerSegs seg,
                 PeerPtrs dst, PeerSync sy) {
     peer_acquire(P, sy);
+    if (seg.mail && blockIdx.x == 0 && (int)threadIdx.x < P) {
+        // (made visible by the fences of peer_publish before the data flag is raised)
+        volatile long long* f = reinterpret_cast<volatile long long*>(sy.flags.p[threadIdx.x]);
+        f[W_MAIL + 4 * (8 * sy.buf + sy.rank)] = seg.mail[threadIdx.x];
+    }
     const int nc = NC > 0 ? NC : ncomp;
     const long long total = (long long)n * nc;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -131,42 +167,27 @@ k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
         const int k = idx[j];
         const int p = idx_is_src ? j : k;
         const int row = idx_is_src ? k : j;
+        if (p < 0 || p >= seg.start[P]) continue;
         int d = 0;
 #pragma unroll
         for (int t = 1; t < 8; ++t) d += (t < P && p >= seg.start[t]) ? 1 : 0;
         if (d == skip_seg) continue;
+        const int off = p - seg.start[d];
+        if (seg.cnt && off >= seg.cnt[d]) continue;
+        double v;
+        if (row >= 0) v = src[(long long)row * nc + c];
+        else if (seg.fill) v = seg.sentinel[c < 3 ? c : 2];
+        else continue;
         double* out = reinterpret_cast<double*>(dst.p[d]);
-        out[(seg.base[d] + (p - seg.start[d])) * nc + c] = src[(long long)row * nc + c];
+        out[(seg.base[d] + off) * nc + c] = v;
     }
     peer_publish(P, sy);
 }
 
-// raise flag[slot] = epoch on every peer (after the stores of earlier kernels on this stream)
-__global__ void k_peer_signal(int P, int slot, PeerPtrs flags, long long epoch) {
-    __threadfence_system();
-    const int d = threadIdx.x;
-    if (d < P) {
-        volatile long long* f = reinterpret_cast<volatile long long*>(flags.p[d]);
-        f[slot] = epoch;
-    }
-    __threadfence_system();
-}
-
-// spin until every one of my P flags has reached `epoch`; traps instead of hanging forever
-__global__ void k_peer_wait(int P, const long long* my_flags, long long epoch) {
-    const int d = threadIdx.x;
-    if (d < P) {
-        const volatile long long* f = my_flags;
-        unsigned long long spins = 0;
-        while (f[d] < epoch) {
-            if (++spins > (1ull << 31)) {
-                printf("vmadpm: peer wait timed out (flag %d = %lld, want %lld)\n", d, f[d], epoch);
-                __trap();
-            }
-            __nanosleep(100);
-        }
-    }
-    __threadfence_system();
+// the counts the peers posted with transfer (buffer b) -> out[0 .. P): rows received from rank s
+__global__ void k_peer_read_mail(int P, const long long* mine, int buf, int* __restrict__ out) {
+    const int s = threadIdx.x;
+    if (s < P) out[s] = (int)reinterpret_cast<const volatile long long*>(mine)[W_MAIL + 4 * (8 * buf + s)];
 }
 
 }  // namespace vpm
@@ -183,16 +204,15 @@ static PeerSync make_sync(int P, const vpm_peer_sync* h) {
     PeerSync sy;
     memset(&sy, 0, sizeof(sy));
     if (h && h->mode) {
-        VPM_REQUIRE(h->peer_flags && h->my_flags, "peer sync: flag arrays missing");
-        VPM_REQUIRE(!(h->mode & VPM_PEER_SIGNAL) || h->counter, "peer sync: signalling needs a counter word");
+        VPM_REQUIRE(h->peer_flags && h->my_flags, "peer sync: flag blocks missing");
         VPM_REQUIRE(!(h->mode & VPM_PEER_WAIT_DATA) || (h->mode & VPM_PEER_SIGNAL),
                     "peer sync: waiting for data implies signalling");
+        VPM_REQUIRE(h->buf == 0 || h->buf == 1, "peer sync: buffer must be 0 or 1");
         sy.flags = make_ptrs(P, h->peer_flags);
-        sy.my_flags = reinterpret_cast<const long long*>(h->my_flags);
+        sy.mine = reinterpret_cast<long long*>(h->my_flags);
         sy.rank = h->rank;
         sy.mode = h->mode;
-        sy.epoch = h->epoch;
-        sy.counter = h->counter;
+        sy.buf = h->buf;
     }
     return sy;
 }
@@ -274,18 +294,24 @@ static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, 
 
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
                       const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
-                      const int64_t* dst_base, const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
+                      const int64_t* dst_base, const int32_t* seg_count, const int32_t* mail,
+                      const double* sentinel3, const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("peer_put_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx && seg_start && dst_base && peer_bufs && nranks >= 1 && nranks <= 8,
                 "bad argument");
     VPM_REQUIRE(n >= 0 && n < (1LL << 31) && ncomp >= 1, "row count / columns out of range");
+    VPM_REQUIRE(!mail || sync, "posting counts needs the flag protocol");
     if (n > 0 || sync) {
         VPM_REQUIRE(n == 0 || (src && idx), "bad argument");
         const PeerSync sy = make_sync(nranks, sync);
         PeerSegs seg;
         for (int i = 0; i < 9; ++i) seg.start[i] = i <= nranks ? seg_start[i] : 0x7fffffff;
         for (int i = 0; i < 8; ++i) seg.base[i] = i < nranks ? dst_base[i] : 0;
+        seg.cnt = seg_count;
+        seg.mail = mail;
+        seg.fill = sentinel3 ? 1 : 0;
+        for (int i = 0; i < 3; ++i) seg.sentinel[i] = sentinel3 ? sentinel3[i] : 0.0;
         const PeerPtrs dst = make_ptrs(nranks, peer_bufs);
         const long long total = (long long)n * ncomp;
         unsigned grid = (unsigned)std::max<long long>(
@@ -303,19 +329,18 @@ int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const doub
     VPM_API_END
 }
 
-int vpm_peer_signal(vpm_ctx* ctx, int nranks, int slot, const uint64_t* peer_flags, int64_t epoch) {
+int vpm_peer_read_mail(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int buf, int32_t* counts) {
     VPM_API_BEGIN
-    VPM_REQUIRE(ctx && peer_flags && nranks >= 1 && nranks <= 8, "bad argument");
-    VPM_LAUNCH(k_peer_signal, 1, 32, 0, ctx->stream, nranks, slot, make_ptrs(nranks, peer_flags),
-               (long long)epoch);
+    VPM_REQUIRE(ctx && my_flags && counts && nranks >= 1 && nranks <= 8 && (buf == 0 || buf == 1), "bad argument");
+    VPM_LAUNCH(k_peer_read_mail, 1, 32, 0, ctx->stream, nranks, reinterpret_cast<const long long*>(my_flags), buf, counts);
     VPM_API_END
 }
 
-int vpm_peer_wait(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int64_t epoch) {
+int vpm_peer_set_spin_limit(vpm_ctx* ctx, uint64_t spins) {
     VPM_API_BEGIN
-    VPM_REQUIRE(ctx && my_flags && nranks >= 1 && nranks <= 8, "bad argument");
-    VPM_LAUNCH(k_peer_wait, 1, 32, 0, ctx->stream, nranks,
-               reinterpret_cast<const long long*>(my_flags), (long long)epoch);
+    VPM_REQUIRE(ctx && spins > 0, "bad argument");
+    unsigned long long v = spins;
+    VPM_CUDA(cudaMemcpyToSymbol(g_peer_spin_limit, &v, sizeof(v)));
     VPM_API_END
 }
 

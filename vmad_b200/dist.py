@@ -196,17 +196,19 @@ class TorchComm(object):
 
 
 class PeerExchange(object):
-    """Double-buffered receive areas + flag arrays of every rank, mapped into this process
+    """Double-buffered receive areas + flag blocks of every rank, mapped into this process
     through CUDA IPC, for the peer-memory transposes of the slab FFT and the particle exchange
     (vmad_b200/csrc/peer.cu).  One per communicator; ``nbytes`` is the capacity of one
     receive area.
 
-    Protocol for transfer number e (buffer e % 2), all inside the put kernel(s): acknowledge
-    transfer e - 1 to every peer (its consumer precedes this launch on the stream) -> wait until
-    every peer acknowledged transfer e - 2 (it has finished reading the area about to be
-    overwritten) -> store blocks into the peers' areas -> last thread block raises data[me] = e
-    everywhere and waits for all data flags here: when the kernel completes my receive area is
-    complete and the consumer (next kernel on the stream) reads it in place.
+    Protocol of a transfer on receive buffer b, all inside the put kernel(s): acknowledge my
+    previous transfer to every peer (its consumer precedes this launch on the stream) -> wait
+    until every peer acknowledged the previous transfer that used buffer b (it has finished
+    reading the area about to be overwritten) -> store blocks into the peers' areas -> last
+    thread block raises my data flag everywhere and waits for all data flags here: when the
+    kernel completes my receive area is complete and the consumer (next kernel on the stream)
+    reads it in place.  The transfer numbers live in the flag block ON THE DEVICE; the host only
+    alternates the buffer, so captured CUDA graphs containing transfers can be replayed.
     """
 
     def __init__(self, comm, nbytes):
@@ -219,17 +221,18 @@ class PeerExchange(object):
         if self.P > 8:
             raise ValueError("peer exchange supports up to 8 ranks")
         self._own, self._opened = [], []
+        self.seq = 0
         self._allocate(nbytes)
 
     def _allocate(self, nbytes):
-        """collective: (re)create the receive areas and flag arrays, exchange the IPC handles"""
+        """collective: (re)create the receive areas and flag blocks, exchange the IPC handles"""
         import ctypes
         C, comm = self.C, self.comm
         self.nbytes = int(nbytes)
         ctx = self._ctx()
         self._own, self._opened = [], []
         mine = []
-        for size in (self.nbytes, self.nbytes, 8 * (2 * self.P + 1)):
+        for size in (self.nbytes, self.nbytes, 8 * C.PEER_FLAG_WORDS):
             ptr = ctypes.c_void_p()
             handle = ctypes.create_string_buffer(64)
             C.check(C.lib.vpm_peer_alloc(ctx, size, ctypes.byref(ptr), handle))
@@ -254,7 +257,6 @@ class PeerExchange(object):
         self.data_flag_ptrs = pad(ptrs[2])
         self.my_bufs = [self._own[0], self._own[1]]
         self.my_flags = self._own[2]
-        self.epoch = 0
         comm.barrier()
 
     def close(self):
@@ -277,50 +279,59 @@ class PeerExchange(object):
         return rt.ctx
 
     def begin(self):
-        self.epoch += 1
-        return self.epoch, self.epoch % 2
+        """next transfer: (sequence number, receive buffer)"""
+        self.seq += 1
+        return self.seq, self.seq % 2
 
-    def _sync(self, e, first, last):
+    def _sync(self, b, first, last):
         """flag protocol riding on a put launch (include/vmadpm.h: vpm_peer_sync)"""
         C, ct = self.C, self.ctypes
         sy = C.vpm_peer_sync()
         sy.peer_flags = ct.cast(self.data_flag_ptrs, ct.POINTER(ct.c_uint64))
         sy.my_flags = self.my_flags
         sy.rank = self.rank
-        mode = 0
-        if first and e > 1:
+        mode = C.PEER_WAIT_ACK
+        if first:
             mode |= C.PEER_RAISE_ACK
-        if e > 2:
-            mode |= C.PEER_WAIT_ACK
         if last:
             mode |= C.PEER_SIGNAL | C.PEER_WAIT_DATA
         sy.mode = mode
-        sy.epoch = e
-        sy.counter = self.my_flags + 8 * 2 * self.P
+        sy.buf = b
         return ct.byref(sy)
 
-    def put(self, e, src, rows, inner, s_row, s_dst, dst_off, first=True, last=True):
+    def put(self, b, src, rows, inner, s_row, s_dst, dst_off, first=True, last=True):
         C, ct = self.C, self.ctypes
         C.check(C.lib.vpm_peer_put(self._ctx(), self.P, int(rows), int(inner), int(s_row), int(s_dst),
-                                   ct.c_void_p(src.data_ptr()), self.buf_ptrs[e % 2], int(dst_off),
-                                   self._sync(e, first, last)))
+                                   ct.c_void_p(src.data_ptr()), self.buf_ptrs[b], int(dst_off),
+                                   self._sync(b, first, last)))
 
-    def put_to(self, e, src_ptr, count, mask, dst_off, first, last):
+    def put_to(self, b, src_ptr, count, mask, dst_off, first, last):
         """``count`` contiguous complex128 elements at device address ``src_ptr`` to the ranks in
         ``mask`` (halo planes for the real-space stencils)"""
         C, ct = self.C, self.ctypes
         C.check(C.lib.vpm_peer_put_to(self._ctx(), self.P, int(mask), int(count), ct.c_void_p(int(src_ptr)),
-                                      self.buf_ptrs[e % 2], int(dst_off), self._sync(e, first, last)))
+                                      self.buf_ptrs[b], int(dst_off), self._sync(b, first, last)))
 
-    def put_rows(self, e, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1):
-        """particle rows to their destination ranks (vpm_peer_put_rows)"""
+    def put_rows(self, b, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1, seg_count=None,
+                 mail=None, sentinel=None):
+        """particle rows to their destination ranks (vpm_peer_put_rows); ``seg_count`` / ``mail``
+        (device int32 tensors) and ``sentinel`` (3 floats) belong to the fixed-capacity routing"""
         C, ct = self.C, self.ctypes
         P = self.P
         seg = (ct.c_int32 * (P + 1))(*[int(v) for v in seg_start])
         base = (ct.c_int64 * P)(*[int(v) for v in dst_base])
+        sent = (ct.c_double * 3)(*sentinel) if sentinel is not None else None
         C.check(C.lib.vpm_peer_put_rows(self._ctx(), P, int(n), int(ncomp), ct.c_void_p(src.data_ptr()),
                                         ct.c_void_p(idx.data_ptr()), int(idx_is_src), int(skip), seg, base,
-                                        self.buf_ptrs[e % 2], self._sync(e, True, True)))
+                                        ct.c_void_p(seg_count.data_ptr()) if seg_count is not None else None,
+                                        ct.c_void_p(mail.data_ptr()) if mail is not None else None, sent,
+                                        self.buf_ptrs[b], self._sync(b, True, True)))
+
+    def read_mail(self, b, out):
+        """what the peers posted with the last transfer on buffer b -> ``out`` (device int32 [P])"""
+        C, ct = self.C, self.ctypes
+        C.check(C.lib.vpm_peer_read_mail(self._ctx(), self.P, ct.c_void_p(self.my_flags), int(b),
+                                         ct.c_void_p(out.data_ptr())))
 
     def ensure(self, nbytes):
         """collective: grow the receive areas (every rank must call with the same value)"""
@@ -328,12 +339,6 @@ class PeerExchange(object):
             self.close()
             self._allocate(int(1.25 * nbytes))
 
-    def commit(self, e):
-        """nothing to launch: the last put of a transfer returns when my receive area is complete"""
-
     def recv_ptr(self, b, offset_elems=0):
         """device pointer (as c_void_p) to complex element ``offset_elems`` of my receive area b"""
         return self.ctypes.c_void_p(self.my_bufs[b] + 16 * int(offset_elems))
-
-    def release(self, e):
-        """nothing to launch: the first put of the next transfer acknowledges this one"""

@@ -513,8 +513,10 @@ def lpt(rhok, q, pm):
     one, src = lpt1, lpt2src
     if _fusable(pm) and USE_FUSED_STAGE:
         from .. import pm as dev
-        if dev._use_stencil(pm) and getattr(pm, 'P', 1) == 1:
-            one, src = lpt1_at_constant_q, lpt2src_real_space
+        if dev._use_stencil(pm):
+            one = lpt1_at_constant_q           # across ranks: halo planes over peer memory
+            if getattr(pm, 'P', 1) == 1:
+                src = lpt2src_real_space       # (two stencils deep: one rank only)
     dx1 = one(rhok, q, pm)
     rhok2 = r2c(src(rhok, pm))
     dx2 = one(rhok2, q, pm)

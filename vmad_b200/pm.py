@@ -752,6 +752,7 @@ class DistLayout(object):
         # counts[s][d] = rows rank s sends to rank d: every rank sees the whole matrix, so the
         # row offsets inside every peer's receive area are known without a second exchange
         counts = comm.allgather_counts(self.send_counts)
+        pm._note_route_counts(counts)
         me = pm.rank
         self.recv_counts = [int(c) for c in counts[:, me]]
         self.nrecv = int(sum(self.recv_counts))
@@ -795,8 +796,7 @@ class DistLayout(object):
         px = self.px
         px.ensure(8 * self._max_rows * ncomp)
         e, b = px.begin()
-        px.put_rows(e, t, self.send_idx, self.nsend, ncomp, 1, self.send_start, self._fwd_base, skip)
-        px.commit(e)
+        px.put_rows(b, t, self.send_idx, self.nsend, ncomp, 1, self.send_start, self._fwd_base, skip)
         return e, b
 
     def _forward(self, t):
@@ -808,7 +808,6 @@ class DistLayout(object):
             out = rt.empty((self.nrecv,) + tuple(t.shape[1:]))
             C.check(C.lib.vpm_axpby(rt.ctx, self.nrecv * ncomp, 1.0, self.px.recv_ptr(b), 0.0, None, 0.0,
                                     _ptr(out)))
-            self.px.release(e)
             return out
         send = rt.empty((self.nsend,) + tuple(t.shape[1:]))
         C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.send_idx), self.nsend, ncomp, _ptr(send)))
@@ -834,7 +833,6 @@ class DistLayout(object):
                 e, b = self._peer_forward(t, ncomp)
                 C.check(C.lib.vpm_take_rows(rt.ctx, self.px.recv_ptr(b), _ptr(self.indices), self.nrecv, ncomp,
                                             _ptr(out)))
-            self.px.release(e)
             return DeviceArray(out, cellindex=self)
         recv = self._forward(data.t)
         ncomp = _ncomp(recv)
@@ -857,25 +855,148 @@ class DistLayout(object):
             e, b = px.begin()
             out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
             if self.take_idx is None:
-                px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base)
+                px.put_rows(b, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base)
                 C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), self.nsend, ncomp,
                                                    _ptr(out)))
-                px.release(e)
                 return DeviceArray(out)
-            px.put_rows(e, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base,
+            px.put_rows(b, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base,
                         skip=self.pm.rank)
             # rows that never left go straight into their home rows
             C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(t), _ptr(self.take_idx), self.nrecv, ncomp, _ptr(out)))
-            px.commit(e)
             C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_remote), self.nsend, ncomp,
                                                _ptr(out)))
-            px.release(e)
             return DeviceArray(out)
         unsorted = rt.empty(tuple(t.shape))
         C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), self.nrecv, ncomp, _ptr(unsorted)))
         back = self.pm.comm.alltoallv_rows(unsorted, self.recv_counts, self.send_counts)
         out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
         C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(back), _ptr(self.send_idx), self.nsend, ncomp, _ptr(out)))
+        return DeviceArray(out)
+
+
+class RoutingOverflow(C.VpmError):
+    """a fixed-capacity segment of the static particle routing was too small"""
+
+
+class RoutingPlan(object):
+    """Fixed capacities ``cap[s][d]`` (rows rank s may send to rank d) of the particle exchange.
+    With them every array of a cross-rank layout has a shape the host knows without reading the
+    per-peer counts back from the device: send order and receive order are divided into
+    segments of fixed capacity (by destination / by source), the rows actually used are counted
+    on the device, the rest are inert padding.  That removes the one host synchronisation of
+    ``decompose`` and makes a multi-rank step capturable in a CUDA graph."""
+
+    def __init__(self, cap, rank):
+        cap = numpy.asarray(cap, dtype='i8')
+        P = len(cap)
+        self.cap = cap
+        self.P = P
+        self.sbase = [0] + [int(v) for v in numpy.cumsum(cap[rank, :])]      # my send segments
+        self.rbase = [0] + [int(v) for v in numpy.cumsum(cap[:, rank])]      # my receive segments
+        self.cap_send, self.cap_recv = self.sbase[-1], self.rbase[-1]
+        # exchange: my rows start at row sum_{s < me} cap[s][d] of rank d's receive order
+        self.fwd_base = [int(cap[:rank, d].sum()) for d in range(P)]
+        # gather: my rows start at row sum_{d < me} cap[s][d] of rank s's send order
+        self.back_base = [int(cap[s, :rank].sum()) for s in range(P)]
+        self.max_rows = int(max(cap.sum(axis=0).max(), cap.sum(axis=1).max()))
+
+
+class StaticDistLayout(object):
+    """``pm.decompose`` over several ranks with the fixed-capacity routing of a ``RoutingPlan``:
+    the same routing rule, per-destination order and results as ``DistLayout`` -- but no value
+    ever travels to the host.  Positions without a particle (the unused tail of a segment) are
+    stored as a sentinel position that lies on no plane this rank holds: the cell sort files
+    them last, paint and readout skip them (no plane of theirs is local), gather masks them."""
+
+    def __init__(self, pm, pos, plan, keep_index=None):
+        rt = pm.rt
+        rt.sync_stream()
+        self.pm = pm
+        self.plan = plan
+        P, me = pm.P, pm.rank
+        _, x3 = pm._pos3(pos)
+        n = x3.shape[0]
+        self.oldlength = n
+        self.px = px = pm._peer()
+        self.send_idx = rt.empty((max(plan.cap_send, 1),), torch.int32)
+        self.scnt = torch.zeros((P + 1,), dtype=torch.int32, device=rt.device)   # rows per destination + overflow flag
+        seg = (ctypes.c_int32 * (P + 1))(*plan.sbase)
+        C.check(C.lib.vpm_route_build_static(rt.ctx, ctypes.byref(pm._mesh), P, _ptr(x3), n, seg,
+                                             _ptr(self.send_idx), _ptr(self.scnt)))
+        pm._overflow |= self.scnt[P:]
+        # positions travel once here, with the per-destination counts in the mailboxes
+        _, b = px.begin()
+        px.put_rows(b, x3, self.send_idx, plan.cap_send, 3, 1, plan.sbase, plan.fwd_base, skip=-1,
+                    mail=self.scnt, sentinel=pm._sentinel())
+        self.rcnt = rt.empty((P,), torch.int32)
+        px.read_mail(b, self.rcnt)
+        # the local cell sort reads the receive area in place (padding rows carry the sentinel)
+        local = pm._decompose_local(None, keep_index, ptr=px.recv_ptr(b), n=plan.cap_recv)
+        self.indices = local.indices
+        self.cell_start = local.cell_start
+        self.keys = local.keys
+        self.newlength = plan.cap_recv
+        xs = rt.empty((plan.cap_recv, 3))
+        C.check(C.lib.vpm_take_rows(rt.ctx, px.recv_ptr(b), _ptr(self.indices), plan.cap_recv, 3, _ptr(xs)))
+        pos = asdevice(pos)
+        self._src = weakref.ref(pos) if isinstance(pos, DeviceArray) and pm.ndim == 3 else None
+        self._xs = xs
+        self.take_idx = self.send_remote = None
+        if not getattr(pm, 'force_recompute', False):
+            # rows that stay on this rank (nearly all) bypass the receive area (see DistLayout)
+            self.take_idx = rt.empty((max(plan.cap_recv, 1),), torch.int32)
+            self.send_remote = rt.empty((max(plan.cap_send, 1),), torch.int32)
+            C.check(C.lib.vpm_route_compose(rt.ctx, _ptr(self.indices), plan.cap_recv, _ptr(self.send_idx),
+                                            plan.cap_send, plan.rbase[me], plan.rbase[me + 1], plan.sbase[me],
+                                            _ptr(self.take_idx), _ptr(self.send_remote)))
+
+    def _area(self, ncomp):
+        if 8 * self.plan.max_rows * ncomp > self.px.nbytes:
+            self.px.ensure(8 * self.plan.max_rows * ncomp)      # collective; not during a capture
+
+    def exchange(self, data):
+        """fastpm.py:289,301,308"""
+        data = asdevice(data)
+        if self._xs is not None and self._src is not None and self._src() is data:
+            return DeviceArray(self._xs, cellindex=self)
+        pm, plan, px = self.pm, self.plan, self.px
+        rt = pm.rt
+        rt.sync_stream()
+        t = data.t
+        ncomp = _ncomp(t)
+        self._area(ncomp)
+        out = rt.empty((plan.cap_recv,) + tuple(t.shape[1:]))
+        _, b = px.begin()
+        if self.take_idx is not None:
+            px.put_rows(b, t, self.send_idx, plan.cap_send, ncomp, 1, plan.sbase, plan.fwd_base, skip=pm.rank)
+            C.check(C.lib.vpm_take_rows2(rt.ctx, _ptr(t), px.recv_ptr(b), _ptr(self.take_idx), plan.cap_recv,
+                                         ncomp, _ptr(out)))
+        else:
+            px.put_rows(b, t, self.send_idx, plan.cap_send, ncomp, 1, plan.sbase, plan.fwd_base)
+            C.check(C.lib.vpm_take_rows(rt.ctx, px.recv_ptr(b), _ptr(self.indices), plan.cap_recv, ncomp, _ptr(out)))
+        return DeviceArray(out, cellindex=self)
+
+    def gather(self, data, mode='sum'):
+        """fastpm.py:286,293,304: back to the home rank and order, copies summed"""
+        data = asdevice(data)
+        pm, plan, px = self.pm, self.plan, self.px
+        rt = pm.rt
+        rt.sync_stream()
+        t = data.t
+        ncomp = _ncomp(t)
+        self._area(ncomp)
+        out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
+        _, b = px.begin()
+        if self.take_idx is None:
+            px.put_rows(b, t, self.indices, plan.cap_recv, ncomp, 0, plan.rbase, plan.back_base, seg_count=self.rcnt)
+            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), plan.cap_send, ncomp,
+                                               _ptr(out)))
+            return DeviceArray(out)
+        px.put_rows(b, t, self.indices, plan.cap_recv, ncomp, 0, plan.rbase, plan.back_base, skip=pm.rank,
+                    seg_count=self.rcnt)
+        C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(t), _ptr(self.take_idx), plan.cap_recv, ncomp, _ptr(out)))
+        C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_remote), plan.cap_send, ncomp,
+                                           _ptr(out)))
         return DeviceArray(out)
 
 
@@ -945,6 +1066,9 @@ class ParticleMesh(object):
         self._tables = {}
         self._frozen_layouts = {}     # id(constant position array) -> (weakref, layout)
         self._tf_cache = {}
+        self._route_stats = None      # element-wise max of the count matrices seen by decompose
+        self._route_plan = None       # RoutingPlan: decompose never talks to the host
+        self._overflow = None
 
     def __vmad_hyper_key__(self):
         """memo key as a hyper-argument of an autooperator: the mesh is immutable configuration;
@@ -1091,6 +1215,65 @@ class ParticleMesh(object):
             return g3[:, 1:].contiguous()
         return g3
 
+    # -- fixed-capacity routing across ranks ------------------------------------------------------
+    def _note_route_counts(self, counts):
+        counts = numpy.asarray(counts, dtype='i8')
+        self._route_stats = counts.copy() if self._route_stats is None else numpy.maximum(self._route_stats, counts)
+
+    def plan_static_routing(self, slack=2.0, floor=4096, cap=None):
+        """Switch ``decompose`` to the fixed-capacity routing (``StaticDistLayout``).  The
+        capacities come from the per-peer counts observed so far (every decompose of at least one
+        representative step in the default mode): rows that stay on their rank are bounded by the
+        rank's particle count; for the others ``slack`` x the largest count seen + ``floor``.
+        Collective (identical on all ranks: the count matrices were all-gathered).  Returns the
+        plan; ``check_routing()`` reports whether a later decompose outgrew it."""
+        if self.P == 1:
+            return None
+        if self._peer() is None:
+            raise C.VpmError("the fixed-capacity routing needs the peer-memory exchange")
+        n0, n0l = int(self.Nmesh[0]), self.rshape[0]
+        if n0 - n0l < 3:
+            raise C.VpmError("the fixed-capacity routing needs at least 3 mesh planes outside the local slab")
+        if cap is None:
+            if self._route_stats is None:
+                raise C.VpmError("plan_static_routing: no decompose has been observed yet")
+            st = self._route_stats
+            cap = numpy.ceil(st * slack).astype('i8') + floor
+            for r in range(self.P):
+                cap[r, r] = max(int(st[r].sum()), int(st[r, r]))     # <= the rank's own particle count
+        plan = RoutingPlan(cap, self.rank)
+        self._peer().ensure(24 * plan.max_rows)
+        self._route_plan = plan
+        self._frozen_layouts.clear()
+        if self._overflow is None:
+            self._overflow = torch.zeros((1,), dtype=torch.int32, device=self.rt.device)
+        return plan
+
+    def check_routing(self):
+        """synchronises; raises RoutingOverflow if a decompose since the last check did not fit
+        the plan (rows were dropped: results are wrong -- re-plan with more slack and repeat)"""
+        if self._overflow is None:
+            return
+        bad = self.comm.allreduce(int(self._overflow.item()))     # collective: all ranks raise together
+        if bad:
+            self._overflow.zero_()
+            raise RoutingOverflow("a segment of the fixed-capacity particle routing overflowed on %d rank(s)" % bad)
+
+    def _global_count(self, n):
+        """sum over ranks of a particle count; the answer for a given local count is cached (the
+        home arrays of a simulation never change length), so a step has no host-side collective"""
+        hit = self._tables.get(('count', n))
+        if hit is None:
+            hit = self._tables[('count', n)] = int(self.comm.allreduce(int(n)))
+        return hit
+
+    def _sentinel(self):
+        """a position on a mesh plane that this rank neither holds nor keys as its lower ghost"""
+        n0, n0l = int(self.Nmesh[0]), self.rshape[0]
+        cell = self.BoxSize / self.Nmesh
+        i0 = (self.rstart0 + n0l + 1) % n0
+        return ((i0 + 0.5) * cell[0], 0.25 * cell[1], 0.25 * cell[2])
+
     # -- decompose (fastpm.py:272) ------------------------------------------------------------
     def cell_keys(self, pos):
         rt = self.rt
@@ -1109,24 +1292,31 @@ class ParticleMesh(object):
             hit = self._frozen_layouts.get(id(pos))
             if hit is not None and hit[0]() is pos:
                 return hit[1]
-        layout = DistLayout(self, pos, keep_index) if self.P > 1 else self._decompose_local(pos, keep_index)
+        if self.P > 1:
+            layout = StaticDistLayout(self, pos, self._route_plan, keep_index) if self._route_plan is not None \
+                else DistLayout(self, pos, keep_index)
+        else:
+            layout = self._decompose_local(pos, keep_index)
         if frozen:
             cache, key = self._frozen_layouts, id(pos)
             cache[key] = (weakref.ref(pos, lambda r, cache=cache, key=key: cache.pop(key, None)), layout)
         return layout
 
-    def _decompose_local(self, pos, keep_index=None):
+    def _decompose_local(self, pos, keep_index=None, ptr=None, n=None):
         """``keep_index``: also keep the cell keys and cell offsets on the layout (the sorted
         permutation alone is what exchange / gather and the default paint need; the layout sits
-        on the tape of every force evaluation, so the extra 8 B/particle + 4 B/cell matter)"""
+        on the tape of every force evaluation, so the extra 8 B/particle + 4 B/cell matter).
+        ``ptr, n``: positions given as a raw device pointer to ``[n, 3]`` doubles (a receive area)"""
         rt = self.rt
         rt.sync_stream()
-        _, x3 = self._pos3(pos)
-        n = x3.shape[0]
+        if ptr is None:
+            _, x3 = self._pos3(pos)
+            n = x3.shape[0]
+            ptr = _ptr(x3)
         keys = rt.empty((n,), torch.int32)
         perm = rt.empty((n,), torch.int32)
         cell_start = rt.empty((self._ncell + 1,), torch.int32)
-        C.check(C.lib.vpm_layout_build(rt.ctx, ctypes.byref(self._mesh), _ptr(x3), n, _ptr(keys),
+        C.check(C.lib.vpm_layout_build(rt.ctx, ctypes.byref(self._mesh), ptr, n, _ptr(keys),
                                        _ptr(perm), _ptr(cell_start)))
         if keep_index is None:
             keep_index = _KEEP_CELL_INDEX
@@ -1478,12 +1668,10 @@ class ParticleMesh(object):
             # pack + transfer in one kernel: block d is stored straight into rank d's buffer
             inner = n1l * Nh
             e, b = px.begin()
-            px.put(e, a, n0l, inner, P * inner, inner, self.rank * n0l * inner)
-            px.commit(e)
+            px.put(b, a, n0l, inner, P * inner, inner, self.rank * n0l * inner)
             o = rt.empty(self.cshape, _C16)
             C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, px.recv_ptr(b),
                                                 _ptr(o), 0, float(scale)))
-            px.release(e)
             return ComplexField(self, o)
         # [n0l, P, n1l*Nh] -> [P, n0l, n1l*Nh]: block d goes to rank d
         send = rt.empty((P, n0l, n1l, Nh), _C16)
@@ -1507,15 +1695,13 @@ class ParticleMesh(object):
             for k, real in enumerate(reals):
                 a = rt.empty((n0l, N1, Nh), _C16)
                 C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
-                px.put(e, a, n0l, inner, P * inner, inner, k * slab + self.rank * n0l * inner, first=(k == 0), last=(k == K - 1))
-            px.commit(e)
+                px.put(b, a, n0l, inner, P * inner, inner, k * slab + self.rank * n0l * inner, first=(k == 0), last=(k == K - 1))
             out = []
             for k in range(K):
                 o = rt.empty(self.cshape, _C16)
                 C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, px.recv_ptr(b, k * slab),
                                                     _ptr(o), 0, float(scale)))
                 out.append(ComplexField(self, o))
-            px.release(e)
             return out
         send = rt.empty((P, K, n0l, n1l, Nh), _C16)
         a = rt.empty((n0l, N1, Nh), _C16)
@@ -1547,8 +1733,7 @@ class ParticleMesh(object):
             e, b = px.begin()
             for k, c in enumerate(cplxs):
                 C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, inner, _ptr(c.t), 1, 1.0))
-                px.put(e, c.t, 1, blk, 0, blk, k * slab + self.rank * blk, first=(k == 0), last=(k == K - 1))
-            px.commit(e)
+                px.put(b, c.t, 1, blk, 0, blk, k * slab + self.rank * blk, first=(k == 0), last=(k == K - 1))
             out = []
             for k in range(K):
                 a = rt.empty((n0l, N1, Nh), _C16)
@@ -1557,7 +1742,6 @@ class ParticleMesh(object):
                 o = rt.empty(self.rshape)
                 C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
                 out.append(RealField(self, o))
-            px.release(e)
             return out
         send = rt.empty((P, K, n0l, n1l, Nh), _C16)
         for k, c in enumerate(cplxs):
@@ -1588,11 +1772,9 @@ class ParticleMesh(object):
             work = rt.empty(self.cshape, _C16)
             C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, _ptr(cplx.t), _ptr(work), 1, 1.0))
             e, b = px.begin()
-            px.put(e, work, 1, blk, 0, blk, self.rank * blk)
-            px.commit(e)
+            px.put(b, work, 1, blk, 0, blk, self.rank * blk)
             a = rt.empty((n0l, N1, Nh), _C16)
             C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner, px.recv_ptr(b), _ptr(a)))
-            px.release(e)
             o = rt.empty(self.rshape) if out is None else out
             C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
             return RealField(self, o)
@@ -1618,14 +1800,13 @@ class ParticleMesh(object):
         base = padded.data_ptr()
         px.ensure(32 * cnt)
         e, b = px.begin()
-        px.put_to(e, base + 2 * plane, cnt, 1 << prev, cnt, True, False)            # -> prev's HI slot
-        px.put_to(e, base + n0l * plane, cnt, 1 << nxt, 0, False, True)             # -> next's LO slot
+        px.put_to(b, base + 2 * plane, cnt, 1 << prev, cnt, True, False)            # -> prev's HI slot
+        px.put_to(b, base + n0l * plane, cnt, 1 << nxt, 0, False, True)             # -> next's LO slot
         rt.sync_stream()
         lo = ctypes.c_void_p(base)
         hi = ctypes.c_void_p(base + (n0l + 2) * plane)
         C.check(C.lib.vpm_axpby(rt.ctx, 2 * cnt, 1.0, px.recv_ptr(b, 0), 0.0, None, 0.0, lo))
         C.check(C.lib.vpm_axpby(rt.ctx, 2 * cnt, 1.0, px.recv_ptr(b, cnt), 0.0, None, 0.0, hi))
-        px.release(e)
 
     # -- k-space (fastpm.py:79,83,87) ---------------------------------------------------------------
     def _transfer(self, cplx, scale=1.0, laplace=False, tables=(None, None, None), conj=False):
@@ -1842,7 +2023,7 @@ def force_apl(pm, dx, q, x=None, kick=None, want_f=True):
     xl = layout.exchange(x)
     rho = pm.paint(xl, 1.0)
     rhok = pm._r2c(rho, 1.0)                                   # un-normalised cuFFT output
-    npart = pm.comm.allreduce(len(q))
+    npart = pm._global_count(len(q))
     scale = 1.0 / npart                                        # (Nc / Np) * (1 / Nc)
     tabs = _force_tables(pm)
     if _use_stencil(pm):
@@ -1972,34 +2153,47 @@ def lpt1_apl(pm, rhok, q):
     """Zel'dovich displacement (fastpm.py:336-351) read out at the constant positions ``q``:
     ONE inverse FFT of the potential + the 4-point stencil (the Fourier symbol of
     fourier_space_neg_gradient(order=1), as in force_apl) + the three-mesh readout; the layout
-    and the sorted copy of ``q`` are cached with ``q``.  Returns ``(dx1, state)``."""
+    and the sorted copy of ``q`` are cached with ``q``.  Across ranks the stencil reads the
+    neighbours' boundary planes (halo exchange, as the force does).  Returns ``(dx1, state)``."""
     q = asdevice(q)
     layout = pm.decompose(q)
     xl = layout.exchange(q)
-    phi = pm._c2r(pm._transfer(pm._as_field(rhok, True), scale=1.0, laplace=True), 1.0, consume=True)
+    phi = _potential(pm, pm._transfer(pm._as_field(rhok, True), scale=1.0, laplace=True), consume=True)
     F = _fd4(pm, phi)
     return pm.readout3(F[0], F[1], F[2], xl, gather=layout), (layout, xl)
 
 
+def _fd4_adjoint(pm, Fbar):
+    """phibar = adjoint of F_d = -D_d phi applied to the three cotangent meshes; across ranks
+    ``Fbar`` is the padded [3, n0l + 4, N1, N2] array of ``paint_cols3(pad=2)``"""
+    rt = pm.rt
+    phibar = rt.empty(pm.rshape)
+    if pm.P > 1:
+        pm._halo_fill(Fbar[0])
+        C.check(C.lib.vpm_fd4_neg_gradient_adjoint_slab(rt.ctx, C.i3(pm.rshape), _h3(pm), 2, _ptr(Fbar[0]),
+                                                        _ptr(Fbar[1]), _ptr(Fbar[2]), _ptr(phibar)))
+    else:
+        C.check(C.lib.vpm_fd4_neg_gradient_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(Fbar[0].t),
+                                                   _ptr(Fbar[1].t), _ptr(Fbar[2].t), _ptr(phibar)))
+    return RealField(pm, phibar)
+
+
 def lpt1_vjp(pm, state, _dx1):
     """cotangent of dx1 -> cotangent of rhok (``q`` is a constant here)"""
-    rt = pm.rt
     layout, xl = state
     _fl = layout.exchange(asdevice(_dx1))
-    Fbar = pm.paint_cols3(xl, _fl)
-    phibar = rt.empty(pm.rshape)
-    C.check(C.lib.vpm_fd4_neg_gradient_adjoint(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(Fbar[0].t),
-                                               _ptr(Fbar[1].t), _ptr(Fbar[2].t), _ptr(phibar)))
+    Fbar = pm.paint_cols3(xl, _fl, pad=2 if pm.P > 1 else 0)
+    phibar = _fd4_adjoint(pm, Fbar)
     del Fbar
     # c2r.vjp of the un-normalised inverse is the un-normalised forward transform
-    return pm._transfer(pm._r2c(RealField(pm, phibar), 1.0), scale=1.0, laplace=True)
+    return pm._transfer(pm._r2c(phibar, 1.0), scale=1.0, laplace=True)
 
 
 def lpt1_jvp(pm, state, rhok_):
     if _is_zero_literal(rhok_):
         return 0
     layout, xl = state
-    phi_ = pm._c2r(pm._transfer(pm._as_field(rhok_, True), scale=1.0, laplace=True), 1.0, consume=True)
+    phi_ = _potential(pm, pm._transfer(pm._as_field(rhok_, True), scale=1.0, laplace=True), consume=True)
     F_ = _fd4(pm, phi_)
     return pm.readout3(F_[0], F_[1], F_[2], xl, gather=layout)
 
