@@ -585,7 +585,7 @@ def run_main_problem(env, args, dims, label, steps, warmup, want_profile=True, w
                                   "stay on the device: no host synchronisation inside a step" % plan.cap.tolist())
                 del dx_s, g_s
             except Exception as e:
-                env.log("%s: static routing unavailable (%s)" % (label, str(e).splitlines()[0][:200]))
+                env.log("%s: static routing unavailable (%s)" % (label, str(e).splitlines()[0][:800]))
                 prob.pm._route_plan = None
         del dx_x, g_x
     l0 = C.launch_count()

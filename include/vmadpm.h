@@ -84,6 +84,16 @@ int64_t vpm_layout_ncell(const vpm_mesh* mesh);
  * cell; cell_start[ncell] = np). */
 int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_t np,
                      int32_t* keys, int32_t* perm, int32_t* cell_start);
+/* An index equal to VPM_ROW_PADDING marks a slot that holds no particle (the unused tail of a
+ * fixed-capacity segment, vpm_route_build_static): the take functions write the context's fill
+ * row there when the array has three columns (0 otherwise; vpm_ctx_set_fill_row, default 0), the
+ * scatter / put functions skip it like any negative index. */
+#define VPM_ROW_PADDING (-2147483647 - 1)
+int vpm_ctx_set_fill_row(vpm_ctx* ctx, const double* row3_host);
+/* sorted_to_recv[t] = VPM_ROW_PADDING for every slot t >= sum(recv_counts[0 .. nranks)) (device
+ * counts): the padding rows of a fixed-capacity receive order sort last */
+int vpm_route_mark_padding(vpm_ctx* ctx, int32_t* sorted_to_recv, int64_t n, const int32_t* recv_counts,
+                           int nranks);
 /* dst[i, :] = src[perm[i], :]            (Layout.exchange on one rank) */
 int vpm_take_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64_t n,
                   int ncomp, double* dst);
@@ -298,12 +308,13 @@ int vpm_peer_put_to(vpm_ctx* ctx, int nranks, uint32_t dest_mask, int64_t count,
  *              of segment d hold particles;
  *   mail       (device, nranks ints or NULL) posted to the peers' mailboxes with this transfer
  *              (the per-destination row counts of the routing; vpm_peer_read_mail);
- *   sentinel3  (host, 3 doubles or NULL) exchange direction: a row without a particle
- *              (idx[j] < 0) is stored as this position instead of being skipped. */
+ *   sentinel_rows (host, nranks x 3 doubles or NULL) exchange direction: a position without a
+ *              particle (idx[j] < 0) in the segment of rank d is stored as row d of this array
+ *              -- a position that lies on no plane rank d holds -- instead of being skipped. */
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
                       const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
                       const int64_t* dst_base, const int32_t* seg_count, const int32_t* mail,
-                      const double* sentinel3, const uint64_t* peer_bufs, const vpm_peer_sync* sync);
+                      const double* sentinel_rows, const uint64_t* peer_bufs, const vpm_peer_sync* sync);
 /* counts[s] = what rank s posted with the last transfer on receive buffer `buf` */
 int vpm_peer_read_mail(vpm_ctx* ctx, int nranks, const int64_t* my_flags, int buf, int32_t* counts);
 int vpm_peer_set_spin_limit(vpm_ctx* ctx, uint64_t spins);
@@ -375,6 +386,20 @@ int vpm_lpt2_source_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3],
                             const double* f1, const double* f2, const double* sbar, double* work6,
                             double* fb0, double* fb1, double* fb2);
 
+/* Binned transfer functions (fastpm.py:97-213 apply_digitized; pmesh ComplexField.apply with a
+ * digitizer).  ind[m] = bin of stored mode m (int32, evaluated once on the host by the user's
+ * digitizer), conj_mask[m] != 0: use the conjugate of the bin's entry (NULL: never).
+ *   y[m] = x[m] * T(m),  T(m) = table[ind[m]] (conjugated per mask, and once more when conj_table)
+ *                               for 0 <= ind[m] < nbins, else dflt  (1: leave the mode alone) */
+int vpm_digitized_mul(vpm_ctx* ctx, int64_t n, const double* x, const int32_t* ind, const uint8_t* conj_mask,
+                      int nbins, const double* table, double dflt, int conj_table, double* y);
+/* vjp with respect to the per-bin table (fastpm.py:170-196): out[b] = sum over the modes of bin b
+ * of mult(m) Re(ybar[m] conj(v[m])), v = x (eit NULL: amplitude mode) or i x E(m), E the bin's
+ * phase factor eit[b] conjugated per mask (phase mode); mult = 2 for the stored modes that stand
+ * for two modes of the full spectrum (last-axis index not 0 and not n_last / 2).  out (nbins
+ * doubles, device) is overwritten; local modes only -- the caller all-reduces across ranks. */
+int vpm_digitized_bin(vpm_ctx* ctx, const int64_t nc[3], int64_t n_last, const double* x, const double* ybar,
+                      const int32_t* ind, const uint8_t* conj_mask, int nbins, const double* eit, double* out);
 /* ---- elementwise and reductions on flat fp64 arrays (the stdlib arithmetic that
  *      vmad applies to fields / particle arrays: vmad/core/stdlib/operators.py:14-152;
  *      kick / drift of fastpm.py:459-471) ------------------------------------- */

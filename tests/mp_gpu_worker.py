@@ -71,7 +71,17 @@ def main():
     orc = domain.decompose_ranks([x_all[slice(r, None, P)] for r in range(P)], [N] * 3, L)
 
     def check_routing(lay, tag):
-        bad = 0
+        class Bad(object):
+            n = 0
+            what = []
+
+            def __iadd__(self, failed):
+                import inspect
+                if failed:
+                    self.n += 1
+                    self.what.append(inspect.stack()[1].lineno)
+                return self
+        bad = Bad()
         if hasattr(lay, 'plan'):        # fixed-capacity segments: compare segment by segment
             plan = lay.plan
             sidx = lay.send_idx.cpu().numpy()
@@ -96,7 +106,18 @@ def main():
             bad += not numpy.array_equal(numpy.array(lay.send_start), orc['send_start'][rank])
             bad += not numpy.array_equal(numpy.array(lay.recv_counts), orc['counts'][:, rank])
             bad += not numpy.array_equal(lay.indices.cpu().numpy(), orc['perm'][rank])
-        errs['routing_bit_exact_' + tag] = float(bad)
+        errs['routing_bit_exact_' + tag] = float(bad.n)
+        if bad.n:
+            msg = "rank %d routing (%s): failed checks at lines %s" % (rank, tag, bad.what)
+            if hasattr(lay, 'plan'):
+                msg += "\nrank %d cap %s sbase %s rbase %s scnt %s rcnt %s oracle counts %s" % (
+                    rank, lay.plan.cap.tolist(), lay.plan.sbase, lay.plan.rbase, lay.scnt.cpu().tolist(),
+                    lay.rcnt.cpu().tolist(), orc['counts'].tolist())
+            print(msg, flush=True)
+            out = os.path.join(ROOT, 'gpurun_out')
+            if os.path.isdir(out):
+                with open(os.path.join(out, 'mp_worker_debug_rank%d.txt' % rank), 'a') as f:
+                    f.write(msg + "\n")
 
     check_routing(lay, 'exact')
     a = rng.standard_normal((20000, 3))

@@ -281,3 +281,54 @@ def test_lpt_real_space_operators_vs_graph(oracle_pm, device_pm):
         res[name] = [host(a) for a in (s, d, gx, s_, d_)]
     for a, b in zip(res['device'], res['oracle']):
         assert rel_l2(a, b) < 1e-12
+
+
+def test_neg_gradient_order0_vs_oracle(oracle_pm, device_pm):
+    """fourier_space_neg_gradient(order=0) (fastpm.py:316-319: -i k with the Nyquist mask):
+    apply_transfer forward, vjp (conjugate filter) and jvp on the device against the oracle"""
+    from vmad_b200 import Builder
+    from vmad_b200.lib import fastpm
+    N, L = 16, 37.0
+    rng = numpy.random.default_rng(17)
+    xh = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5
+    ch = rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1))
+    for d in range(3):
+        out = {}
+        for name, PM in [('oracle', oracle_pm), ('device', device_pm)]:
+            pm = PM([N] * 3, L)
+            with Builder() as m:
+                x = m.input('x')
+                m.output(y=fastpm.apply_transfer(x, fastpm.fourier_space_neg_gradient(d, pm, order=0)))
+            x0 = pm.create('complex', value=xh)
+            (y,), (g,) = m.compute_with_vjp(init=dict(x=x0), v=dict(_y=pm.create('complex', value=ch)))
+            _, (y_,) = m.compute_with_jvp(['y'], init=dict(x=x0), v=dict(x_=pm.create('complex', value=ch)))
+            out[name] = [host(y), host(g), host(y_)]
+        for a, b in zip(out['device'], out['oracle']):
+            assert rel_l2(a, b) < 1e-12
+        assert numpy.abs(out['oracle'][0]).max() > 0
+
+
+def test_lpt1_gradient_wrt_q_vs_oracle(oracle_pm, device_pm):
+    """lpt1's spec is 'rhok,q->dx1' (fastpm.py:336-351): the readout's position cotangent flows to
+    ``q``.  Forward, vjp w.r.t. BOTH inputs and jvp on the device against the oracle."""
+    from vmad_b200 import Builder
+    from vmad_b200.lib import fastpm
+    N, L = 16, 50.0
+    rng = numpy.random.default_rng(23)
+    rk = numpy.fft.rfftn(rng.standard_normal((N, N, N))) / N ** 1.5 * 20.0
+    qh = rng.uniform(0, L, size=(3000, 3))
+    cot = rng.standard_normal(qh.shape)
+    tq = rng.standard_normal(qh.shape)
+    out = {}
+    for name, PM, mv in [('oracle', oracle_pm, lambda a: a), ('device', device_pm, put)]:
+        pm = PM([N] * 3, L)
+        with Builder() as m:
+            r, q = m.input('r', 'q')
+            m.output(dx1=fastpm.lpt1(r, q, pm))
+        r0 = pm.create('complex', value=rk)
+        (dx1,), (gr, gq) = m.compute_with_vjp(init=dict(r=r0, q=mv(qh)), v=dict(_dx1=mv(cot)))
+        _, (dx1_,) = m.compute_with_jvp(['dx1'], init=dict(r=r0, q=mv(qh)), v=dict(r_=0, q_=mv(tq)))
+        out[name] = [host(dx1), host(gr), host(gq), host(dx1_)]
+    for what, a, b in zip(('dx1', '_rhok', '_q', 'jvp_q'), out['device'], out['oracle']):
+        assert rel_l2(a, b) < 1e-11, (what, rel_l2(a, b))
+    assert numpy.abs(out['oracle'][2]).max() > 0

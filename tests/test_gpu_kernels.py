@@ -426,3 +426,42 @@ def test_route_build_bit_exact_vs_p_rank_oracle(oracle_pm, device_pm, P, Nmesh, 
     got_start = numpy.array(list(start), dtype='i8')
     assert numpy.array_equal(got_start, want_start)
     assert numpy.array_equal(send_idx[:got_start[-1]].cpu().numpy(), want_idx)
+
+
+@pytest.mark.parametrize("npart", [60000, 1 << 21])
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_route_build_static_bit_exact(oracle_pm, device_pm, P, npart):
+    """the fixed-capacity variant of the routing (no host synchronisation): the same lists inside
+    fixed segments, -1 in the unused tails, device-side counts, overflow flag only when a segment
+    is too small"""
+    import ctypes
+    import torch
+    from pmesh import domain
+    from vmad_b200 import _capi as C
+    Nmesh, BoxSize = [32, 32, 32], 100.0
+    rng = numpy.random.default_rng(50 + P)
+    dpm = device_pm(Nmesh, BoxSize)
+    x = edge_positions(rng, Nmesh, BoxSize, npart)
+    want_idx, want_start = domain.route(x, Nmesh, BoxSize, P)
+    want_cnt = numpy.diff(want_start)
+    xd = torch.from_numpy(numpy.ascontiguousarray(x)).cuda()
+    rt = dpm.rt
+    rt.sync_stream()
+    for slack, expect_overflow in ((1.0, False), (1.5, False), (0.5, True)):
+        cap = numpy.maximum((want_cnt * slack).astype('i8') + (5 if slack > 1 else 0), 1)
+        seg = numpy.concatenate([[0], numpy.cumsum(cap)])
+        send_idx = torch.empty(int(seg[-1]), dtype=torch.int32, device='cuda')
+        counts = torch.zeros(P + 1, dtype=torch.int32, device='cuda')
+        cseg = (ctypes.c_int32 * (P + 1))(*[int(v) for v in seg])
+        C.check(C.lib.vpm_route_build_static(rt.ctx, ctypes.byref(dpm._mesh), P, ctypes.c_void_p(xd.data_ptr()),
+                                             len(x), cseg, ctypes.c_void_p(send_idx.data_ptr()),
+                                             ctypes.c_void_p(counts.data_ptr())))
+        got = send_idx.cpu().numpy()
+        cnt = counts.cpu().numpy()
+        assert bool(cnt[P]) == expect_overflow
+        assert numpy.array_equal(cnt[:P], numpy.minimum(want_cnt, cap))
+        for d in range(P):
+            w = want_idx[want_start[d]:want_start[d + 1]][:cap[d]]
+            s = got[seg[d]:seg[d + 1]]
+            assert numpy.array_equal(s[:len(w)], w)
+            assert (s[len(w):] == -1).all()

@@ -50,6 +50,7 @@ class vpm_peer_sync(Structure):
 
 PEER_RAISE_ACK, PEER_WAIT_ACK, PEER_SIGNAL, PEER_WAIT_DATA = 1, 2, 4, 8
 PEER_FLAG_WORDS = 128
+ROW_PADDING = -2147483648
 
 
 SIGNATURES = {
@@ -70,6 +71,8 @@ SIGNATURES = {
     'vpm_route_build': (c_int, [c_void_p, POINTER(vpm_mesh), c_int, _P, c_int64, _P, c_int64,
                                 POINTER(c_int32)]),
     'vpm_route_build_static': (c_int, [c_void_p, POINTER(vpm_mesh), c_int, _P, c_int64, POINTER(c_int32), _P, _P]),
+    'vpm_ctx_set_fill_row': (c_int, [c_void_p, POINTER(c_double)]),
+    'vpm_route_mark_padding': (c_int, [c_void_p, _P, c_int64, _P, c_int]),
     'vpm_take_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_take_rows_scaled': (c_int, [c_void_p, _P, _P, c_int64, c_int, c_double, _P]),
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
@@ -116,6 +119,8 @@ SIGNATURES = {
                              _P, _P, _P, c_int]),
     'vpm_transfer_table': (c_int, [c_void_p, POINTER(c_int64), _P, _P, _P, POINTER(c_int64),
                                    c_int, c_int]),
+    'vpm_digitized_mul': (c_int, [c_void_p, c_int64, _P, _P, _P, c_int, _P, c_double, c_int, _P]),
+    'vpm_digitized_bin': (c_int, [c_void_p, POINTER(c_int64), c_int64, _P, _P, _P, _P, c_int, _P, _P]),
     'vpm_force_kspace': (c_int, [c_void_p, POINTER(c_int64), _P, c_double, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P]),
     'vpm_force_kspace_vjp': (c_int, [c_void_p, POINTER(c_int64), _P, _P, _P, _P, c_double, _P, _P, _P,

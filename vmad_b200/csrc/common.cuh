@@ -100,6 +100,8 @@ struct vpm_ctx {
     // pinned host landing zone for reduction results
     double* host_scalars = nullptr;
     double* dev_scalars = nullptr;
+    // row written by the take kernels where an index is VPM_ROW_PADDING (vpm_ctx_set_fill_row)
+    double fill_row[3] = {0.0, 0.0, 0.0};
     // cuFFT plans keyed by (n0, n1, n2, direction)
     std::map<std::tuple<int64_t, int64_t, int64_t, int>, cufftHandle> plans;
 

@@ -204,6 +204,59 @@ k_final2(int nparts, const double* __restrict__ partial, double* __restrict__ ou
     }
 }
 
+// ---- binned transfer functions (apply_digitized, vmad/lib/fastpm.py:97-213) -----------------
+// mode m belongs to bin ind[m] (evaluated once on the host by the user's digitizer, like any
+// tf(k)); the per-bin table t has nb complex entries.
+//   y[m] = x[m] * T(m),  T(m) = (cj[m] ? conj(t[ind[m]]) : t[ind[m]]) inside [0, nb), else dflt
+__global__ void __launch_bounds__(KS_THREADS)
+k_digitized_mul(long long n, const double2* __restrict__ x, const int* __restrict__ ind,
+                const unsigned char* __restrict__ cj, int nb, const double2* __restrict__ t,
+                double dflt, bool conj_all, double2* __restrict__ y) {
+    long long e = blockIdx.x * (long long)KS_THREADS + threadIdx.x;
+    if (e >= n) return;
+    const int b = ind[e];
+    double2 T = make_double2(dflt, 0.0);
+    if (b >= 0 && b < nb) {
+        T = t[b];
+        if ((cj && cj[e]) != conj_all) T.y = -T.y;
+    }
+    y[e] = cmul(x[e], T);
+}
+
+// the vjp with respect to the per-bin table: out[b] += mult(m) Re(ybar[m] conj(pre x[m] E(m))) over
+// the modes of bin b, mult = 2 for modes that stand for two modes of the full spectrum
+// (fastpm.py:174,188); E = 1 (amplitude mode) or the bin's phase factor and pre = i (phase mode).
+// Block-level bins in shared memory, one global reduction per bin and block.
+constexpr int DIG_MAXBINS = 4096;
+__global__ void __launch_bounds__(KS_THREADS)
+k_digitized_bin(long long n, long long nh, long long n_last, const double2* __restrict__ x,
+                const double2* __restrict__ ybar, const int* __restrict__ ind,
+                const unsigned char* __restrict__ cj, int nb, const double2* __restrict__ eit,
+                double* __restrict__ out) {
+    extern __shared__ double bins[];
+    for (int b = threadIdx.x; b < nb; b += KS_THREADS) bins[b] = 0.0;
+    __syncthreads();
+    for (long long e = blockIdx.x * (long long)KS_THREADS + threadIdx.x; e < n;
+         e += (long long)gridDim.x * KS_THREADS) {
+        const int b = ind[e];
+        if (b < 0 || b >= nb) continue;
+        const long long k = e % nh;
+        const double mult = (k == 0 || k == n_last / 2) ? 1.0 : 2.0;
+        double2 v = x[e];
+        if (eit) {                       // y = x E, then i y
+            double2 E = eit[b];
+            if (cj && cj[e]) E.y = -E.y;
+            v = cmul(v, E);
+            v = make_double2(-v.y, v.x);
+        }
+        const double2 g = ybar[e];
+        atomicAdd(bins + b, mult * (g.x * v.x + g.y * v.y));     // Re(g conj(v))
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += KS_THREADS)
+        if (bins[b] != 0.0) atomicAdd(out + b, bins[b]);
+}
+
 static CShape make_cshape(const int64_t nc[3]) {
     VPM_REQUIRE(nc && nc[0] >= 1 && nc[1] >= 1 && nc[2] >= 1, "bad complex shape");
     CShape s;
@@ -278,6 +331,35 @@ int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, co
                reinterpret_cast<const double2*>(g0), reinterpret_cast<const double2*>(g1),
                reinterpret_cast<const double2*>(g2), reinterpret_cast<const double2*>(p_bar), scale,
                kk0, kk1, kk2, a0, a1, a2, reinterpret_cast<double2*>(rhok_bar));
+    VPM_API_END
+}
+
+int vpm_digitized_mul(vpm_ctx* ctx, int64_t n, const double* x, const int32_t* ind, const uint8_t* conj_mask,
+                      int nbins, const double* table, double dflt, int conj_table, double* y) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("digitized_mul", 37.0 * n);
+    VPM_REQUIRE(ctx && nbins >= 0, "bad argument");
+    if (n > 0) {
+        VPM_REQUIRE(x && ind && y && (nbins == 0 || table), "NULL argument");
+        VPM_LAUNCH(k_digitized_mul, (unsigned)ceil_div(n, KS_THREADS), KS_THREADS, 0, ctx->stream, (long long)n,
+                   reinterpret_cast<const double2*>(x), ind, conj_mask, nbins,
+                   reinterpret_cast<const double2*>(table), dflt, conj_table != 0, reinterpret_cast<double2*>(y));
+    }
+    VPM_API_END
+}
+
+int vpm_digitized_bin(vpm_ctx* ctx, const int64_t nc[3], int64_t n_last, const double* x, const double* ybar,
+                      const int32_t* ind, const uint8_t* conj_mask, int nbins, const double* eit, double* out) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && out && nbins >= 1 && nbins <= DIG_MAXBINS, "bad argument (up to 4096 bins)");
+    CShape s = make_cshape(nc);
+    VPM_PROF_GROUP("digitized_bin", 37.0 * s.total);
+    VPM_CUDA(cudaMemsetAsync(out, 0, (size_t)nbins * sizeof(double), ctx->stream));
+    VPM_REQUIRE(x && ybar && ind, "NULL argument");
+    const int grid = (int)std::min<long long>(ceil_div(s.total, KS_THREADS), 8LL * ctx->sm_count);
+    VPM_LAUNCH(k_digitized_bin, grid, KS_THREADS, (size_t)nbins * sizeof(double), ctx->stream, s.total, s.nh,
+               (long long)n_last, reinterpret_cast<const double2*>(x), reinterpret_cast<const double2*>(ybar), ind,
+               conj_mask, nbins, reinterpret_cast<const double2*>(eit), out);
     VPM_API_END
 }
 

@@ -34,8 +34,21 @@ __global__ void k_keys_count(Geo g, const double* __restrict__ x, long long np,
                              int* __restrict__ keys, int* __restrict__ rank,
                              int* __restrict__ count) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p < np) {
-        int k = key_of(g, x, p);
+    const int overflow = g.nsp * g.n1 * g.n2;
+    int k = -1;
+    if (p < np) k = key_of(g, x, p);
+    // rows that are not on this slab (the padding of a fixed-capacity receive order: long runs of
+    // them) would all hit one counter: one atomic per warp for those
+    const unsigned off = __ballot_sync(0xffffffffu, k == overflow);
+    if (k == overflow) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(off) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(count + k, __popc(off));
+        base = __shfl_sync(off, base, leader);
+        keys[p] = k;
+        rank[p] = base + __popc(off & ((1u << lane) - 1));
+    } else if (p < np) {
         keys[p] = k;
         rank[p] = atomicAdd(count + k, 1);
     }
@@ -139,11 +152,11 @@ __global__ void k_scatter_ids(const int* __restrict__ keys, const int* __restric
 // warp, in place; larger (pathological): rank sort spread over the whole grid via a copy.
 constexpr int FIX_SMALL = 16;
 constexpr int FIX_MEDIUM = 1024;
-__global__ void k_fix_small(const int* __restrict__ cell_start, long long ncell,
+__global__ void k_fix_small(const int* __restrict__ cell_start, long long ncell, long long nrepair,
                             int* __restrict__ perm, int* __restrict__ lists,
                             int* __restrict__ counts) {
     long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (c >= ncell) return;
+    if (c >= nrepair) return;
     int b = cell_start[c], e = cell_start[c + 1];
     int cnt = e - b;
     if (cnt < 2) return;
@@ -246,15 +259,34 @@ __global__ void k_copy_big(const int* __restrict__ cell_start, const int* __rest
 __global__ void k_set_last(int* cell_start, long long ncell, int np) { cell_start[ncell] = np; }
 
 // ---- row permutes -------------------------------------------------------------------
+// an index equal to VPM_ROW_PADDING marks a slot without a particle (fixed-capacity routing):
+// takes write the context's fill row there (three-column arrays; 0 otherwise), scatters skip it
+struct Fill3 {
+    double v[3];
+};
+
 template <int NC>
 __global__ void k_take_rows(const double* __restrict__ src, const int* __restrict__ perm,
-                            long long n, int ncomp, double scale, double* __restrict__ dst) {
+                            long long n, int ncomp, double scale, Fill3 fill, double* __restrict__ dst) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int nc = NC > 0 ? NC : ncomp;
     if (e >= n * nc) return;
     long long i = e / nc;
     int c = (int)(e - i * nc);
-    dst[e] = scale * __ldg(src + (long long)perm[i] * nc + c);   // scale = 1 is exact
+    const int p = perm[i];
+    if (p == VPM_ROW_PADDING) {
+        dst[e] = (NC == 3) ? fill.v[c] : 0.0;
+        return;
+    }
+    dst[e] = scale * __ldg(src + (long long)p * nc + c);   // scale = 1 is exact
+}
+
+// slots of the sorted order at or beyond the number of rows that really arrived hold padding
+__global__ void k_mark_padding(int* __restrict__ sorted_to_recv, int n, const int* __restrict__ rcnt, int P) {
+    int nvalid = 0;
+    for (int s = 0; s < P; ++s) nvalid += rcnt[s];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && t >= nvalid) sorted_to_recv[t] = VPM_ROW_PADDING;
 }
 
 template <int NC, bool ADD>
@@ -276,7 +308,7 @@ __global__ void k_scatter_rows(const double* __restrict__ src, const int* __rest
 // out[k] = idx[k] >= 0 ? a[idx[k]] : b[-1 - idx[k]]   (rows of NC doubles)
 template <int NC>
 __global__ void k_take_rows2(const double* __restrict__ a, const double* __restrict__ b,
-                             const int* __restrict__ idx, long long n, int ncomp,
+                             const int* __restrict__ idx, long long n, int ncomp, Fill3 fill,
                              double* __restrict__ dst) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int nc = NC > 0 ? NC : ncomp;
@@ -284,6 +316,10 @@ __global__ void k_take_rows2(const double* __restrict__ a, const double* __restr
     long long i = e / nc;
     int c = (int)(e - i * nc);
     const int p = idx[i];
+    if (p == VPM_ROW_PADDING) {
+        dst[e] = (NC == 3) ? fill.v[c] : 0.0;
+        return;
+    }
     dst[e] = p >= 0 ? a[(long long)p * nc + c] : b[(long long)(-1 - p) * nc + c];
 }
 
@@ -297,7 +333,14 @@ __global__ void k_route_compose(const int* __restrict__ sorted_to_recv, int nrec
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nrecv) {
         const int r = sorted_to_recv[t];
-        take[t] = (r >= recv_lo && r < recv_hi) ? send_idx[send_lo + (r - recv_lo)] : -1 - r;
+        if (r == VPM_ROW_PADDING) {
+            take[t] = VPM_ROW_PADDING;
+        } else if (r >= recv_lo && r < recv_hi) {
+            const int h = send_idx[send_lo + (r - recv_lo)];
+            take[t] = h >= 0 ? h : VPM_ROW_PADDING;
+        } else {
+            take[t] = -1 - r;
+        }
     }
     if (t < nsend) {
         const int send_hi = send_lo + (recv_hi - recv_lo);
@@ -558,7 +601,9 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
     if (np > 0) {
         VPM_LAUNCH(k_scatter_ids, (unsigned)ceil_div(np, 256), 256, 0, st, keys, rank, cell_start,
                    (long long)np, perm);
-        VPM_LAUNCH(k_fix_small, (unsigned)ceil_div(ncell, 256), 256, 0, st, cell_start, ncell, perm,
+        // the last bucket collects what is not on this slab (only the inert padding rows of the
+        // fixed-capacity routing end up there, possibly very many): their order is irrelevant
+        VPM_LAUNCH(k_fix_small, (unsigned)ceil_div(ncell, 256), 256, 0, st, cell_start, ncell, ncell - 1, perm,
                    big_list, big_count);
         int nblk = 4 * ctx->sm_count;
         VPM_LAUNCH(k_fix_medium, nblk, 256, 0, st, cell_start, big_list, big_count, perm);
@@ -578,9 +623,11 @@ static void launch_take_rows(vpm_ctx* ctx, const double* src, const int32_t* per
     if (n > 0) {
         VPM_REQUIRE(src && perm && dst, "NULL array");
         unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
-        if (ncomp == 1) VPM_LAUNCH(k_take_rows<1>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, dst);
-        else if (ncomp == 3) VPM_LAUNCH(k_take_rows<3>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, dst);
-        else VPM_LAUNCH(k_take_rows<0>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, dst);
+        Fill3 fill;
+        for (int c = 0; c < 3; ++c) fill.v[c] = ctx->fill_row[c];
+        if (ncomp == 1) VPM_LAUNCH(k_take_rows<1>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, fill, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows<3>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, fill, dst);
+        else VPM_LAUNCH(k_take_rows<0>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, fill, dst);
     }
 }
 
@@ -625,9 +672,11 @@ int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t
     if (n > 0) {
         VPM_REQUIRE(a && b && idx && dst, "NULL array");
         unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
-        if (ncomp == 1) VPM_LAUNCH(k_take_rows2<1>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, dst);
-        else if (ncomp == 3) VPM_LAUNCH(k_take_rows2<3>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, dst);
-        else VPM_LAUNCH(k_take_rows2<0>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, dst);
+        Fill3 fill;
+        for (int c = 0; c < 3; ++c) fill.v[c] = ctx->fill_row[c];
+        if (ncomp == 1) VPM_LAUNCH(k_take_rows2<1>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, fill, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows2<3>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, fill, dst);
+        else VPM_LAUNCH(k_take_rows2<0>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, fill, dst);
     }
     VPM_API_END
 }
@@ -647,6 +696,25 @@ int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv
                    (int)nrecv, send_idx, (int)nsend, (int)recv_lo, (int)recv_hi, (int)send_lo, take,
                    remote);
     }
+    VPM_API_END
+}
+
+int vpm_route_mark_padding(vpm_ctx* ctx, int32_t* sorted_to_recv, int64_t n, const int32_t* recv_counts,
+                           int nranks) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && recv_counts && nranks >= 1 && nranks <= ROUTE_MAXP && n >= 0 && n < (1LL << 31), "bad argument");
+    if (n > 0) {
+        VPM_REQUIRE(sorted_to_recv, "NULL array");
+        VPM_LAUNCH(k_mark_padding, (unsigned)ceil_div(n, 256), 256, 0, ctx->stream, sorted_to_recv, (int)n,
+                   recv_counts, nranks);
+    }
+    VPM_API_END
+}
+
+int vpm_ctx_set_fill_row(vpm_ctx* ctx, const double* row3_host) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx && row3_host, "NULL argument");
+    for (int c = 0; c < 3; ++c) ctx->fill_row[c] = row3_host[c];
     VPM_API_END
 }
 

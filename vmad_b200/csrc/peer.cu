@@ -139,7 +139,7 @@ struct PeerSegs {
                              // cnt[d]) of segment d hold particles (NULL: every row does)
     const int* mail;         // my per-destination row counts, posted to peer d's mailbox (NULL: none)
     int fill;                // exchange direction: positions without a particle (idx < 0) are stored as
-    double sentinel[3];      // this row (a position no rank's slab covers); else they are skipped
+    double sentinel[8][3];   // the destination's row (a position off ITS slab); else they are skipped
 };
 
 // Particle rows to their destination ranks, pack and transfer fused.  Routing order position p
@@ -176,7 +176,7 @@ k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
         if (seg.cnt && off >= seg.cnt[d]) continue;
         double v;
         if (row >= 0) v = src[(long long)row * nc + c];
-        else if (seg.fill) v = seg.sentinel[c < 3 ? c : 2];
+        else if (seg.fill) v = seg.sentinel[d][c < 3 ? c : 2];
         else continue;
         double* out = reinterpret_cast<double*>(dst.p[d]);
         out[(seg.base[d] + off) * nc + c] = v;
@@ -295,7 +295,7 @@ static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, 
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
                       const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
                       const int64_t* dst_base, const int32_t* seg_count, const int32_t* mail,
-                      const double* sentinel3, const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
+                      const double* sentinel_rows, const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("peer_put_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx && seg_start && dst_base && peer_bufs && nranks >= 1 && nranks <= 8,
@@ -310,8 +310,9 @@ int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const doub
         for (int i = 0; i < 8; ++i) seg.base[i] = i < nranks ? dst_base[i] : 0;
         seg.cnt = seg_count;
         seg.mail = mail;
-        seg.fill = sentinel3 ? 1 : 0;
-        for (int i = 0; i < 3; ++i) seg.sentinel[i] = sentinel3 ? sentinel3[i] : 0.0;
+        seg.fill = sentinel_rows ? 1 : 0;
+        for (int d = 0; d < 8; ++d)
+            for (int i = 0; i < 3; ++i) seg.sentinel[d][i] = (sentinel_rows && d < nranks) ? sentinel_rows[3 * d + i] : 0.0;
         const PeerPtrs dst = make_ptrs(nranks, peer_bufs);
         const long long total = (long long)n * ncomp;
         unsigned grid = (unsigned)std::max<long long>(

@@ -315,12 +315,13 @@ class PeerExchange(object):
     def put_rows(self, b, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1, seg_count=None,
                  mail=None, sentinel=None):
         """particle rows to their destination ranks (vpm_peer_put_rows); ``seg_count`` / ``mail``
-        (device int32 tensors) and ``sentinel`` (3 floats) belong to the fixed-capacity routing"""
+        (device int32 tensors) and ``sentinel`` (one inert position per destination rank) belong to
+        the fixed-capacity routing"""
         C, ct = self.C, self.ctypes
         P = self.P
         seg = (ct.c_int32 * (P + 1))(*[int(v) for v in seg_start])
         base = (ct.c_int64 * P)(*[int(v) for v in dst_base])
-        sent = (ct.c_double * 3)(*sentinel) if sentinel is not None else None
+        sent = (ct.c_double * (3 * P))(*[float(v) for row in sentinel for v in row]) if sentinel is not None else None
         C.check(C.lib.vpm_peer_put_rows(self._ctx(), P, int(n), int(ncomp), ct.c_void_p(src.data_ptr()),
                                         ct.c_void_p(idx.data_ptr()), int(idx_is_src), int(skip), seg, base,
                                         ct.c_void_p(seg_count.data_ptr()) if seg_count is not None else None,

@@ -239,8 +239,9 @@ def _times_table(x, table):
 class apply_digitized:
     """fastpm.py:97-213 -- transfer function given per bin: ``y = x * tf[bin(k)]`` (mode
     'amplitude') or ``y = x * exp(i tf[bin(k)])`` (mode 'phase'); modes whose bin falls outside
-    ``tf`` are left alone.  ``digitizer(k) -> (ind, conj)``.  The binned reductions of the vjp
-    run on the host (this operator is used by no autooperator of the library)."""
+    ``tf`` are left alone.  ``digitizer(k) -> (ind, conj)`` is user code and is evaluated on the
+    host (like any ``tf(k)``); on the device backend the per-mode multiply and the binned
+    reduction of the vjp are kernels, the per-bin table ``tf`` stays a (small) host array."""
     ain = 'x', 'tf'
     aout = 'y'
 
@@ -259,20 +260,29 @@ class apply_digitized:
         ind = numpy.broadcast_to(numpy.asarray(ind, dtype='intp'), shape)
         conj = numpy.broadcast_to(numpy.asarray(conj, dtype='?'), shape)
         tf = numpy.asarray(tf)
-        if mode == 'amplitude':
-            eit = None
-            y = _times_table(x, _take_default(tf, ind, conj, 1))
-        else:
-            eit = numpy.exp(1j * tf)
-            y = _times_table(x, _take_default(eit, ind, conj, 1))
+        eit = None if mode == 'amplitude' else numpy.exp(1j * tf)
+        dev = getattr(x.pm, 'digitized', None)
+        if dev is not None:
+            # device backend: the bins (like any tf(k), evaluated once by the user's digitizer on
+            # the host) become device index arrays; the multiply and, in the vjp, the binned
+            # reduction are kernels (vpm_digitized_mul / vpm_digitized_bin)
+            ind, conj = dev.bins(ind, conj)
+            y = dev.mul(x, ind, conj, tf if eit is None else eit, 1.0)
+            return dict(y=y, ind=ind, conj=conj, eit=eit)
+        y = _times_table(x, _take_default(tf if eit is None else eit, ind, conj, 1))
         return dict(y=y, ind=ind, conj=conj, eit=eit)
 
     def vjp(node, _y, x, tf, ind, conj, eit, mode):
         tf = numpy.asarray(tf)
-        ind1 = ind.clip(0, len(tf) - 1)
-        mask = ind1 != ind
         pm = x.pm
         _y = pm.create(type='complex', value=_y)
+        dev = getattr(pm, 'digitized', None)
+        if dev is not None:
+            _x = dev.mul(_y, ind, conj, tf if eit is None else eit, 1.0, conj_table=eit is not None)
+            _tf = pm.comm.allreduce(dev.bin(x, _y, ind, conj, len(tf), eit))
+            return dict(_tf=_tf, _x=_x)
+        ind1 = ind.clip(0, len(tf) - 1)
+        mask = ind1 != ind
         # every stored mode stands for 1 or 2 modes of the full spectrum (fastpm.py:174,188)
         i_last = x._coords('index')[-1]
         mult = 1 + ((i_last != 0) & (numpy.abs(i_last) != int(pm.Nmesh[-1]) // 2))
@@ -293,16 +303,21 @@ class apply_digitized:
     def jvp(node, tf_, x_, x, tf, ind, conj, eit, mode):
         y_ = 0
         tf = numpy.asarray(tf)
+        dev = getattr(x.pm, 'digitized', None)
+        if dev is not None:
+            times = lambda f, table, dflt: dev.mul(f, ind, conj, table, dflt)
+        else:
+            times = lambda f, table, dflt: _times_table(f, _take_default(table, ind, conj, dflt))
         if mode == 'amplitude':
             if not _is_zero(tf_):
-                y_ = y_ + _times_table(x, _take_default(numpy.asarray(tf_), ind, conj, 0))
+                y_ = y_ + times(x, numpy.asarray(tf_), 0)
             if not _is_zero(x_):
-                y_ = y_ + _times_table(x.pm.create(type='complex', value=x_), _take_default(tf, ind, conj, 1))
+                y_ = y_ + times(x.pm.create(type='complex', value=x_), tf, 1)
         else:
             if not _is_zero(tf_):
-                y_ = y_ + _times_table(x, _take_default(eit * 1j * numpy.asarray(tf_), ind, conj, 0))
+                y_ = y_ + times(x, eit * 1j * numpy.asarray(tf_), 0)
             if not _is_zero(x_):
-                y_ = y_ + _times_table(x.pm.create(type='complex', value=x_), _take_default(eit, ind, conj, 1))
+                y_ = y_ + times(x.pm.create(type='complex', value=x_), eit, 1)
         return dict(y_=y_)
 
 

@@ -924,10 +924,11 @@ class StaticDistLayout(object):
         C.check(C.lib.vpm_route_build_static(rt.ctx, ctypes.byref(pm._mesh), P, _ptr(x3), n, seg,
                                              _ptr(self.send_idx), _ptr(self.scnt)))
         pm._overflow |= self.scnt[P:]
+        pm._last_static = weakref.ref(self)
         # positions travel once here, with the per-destination counts in the mailboxes
         _, b = px.begin()
         px.put_rows(b, x3, self.send_idx, plan.cap_send, 3, 1, plan.sbase, plan.fwd_base, skip=-1,
-                    mail=self.scnt, sentinel=pm._sentinel())
+                    mail=self.scnt, sentinel=[pm._sentinel(d) for d in range(P)])
         self.rcnt = rt.empty((P,), torch.int32)
         px.read_mail(b, self.rcnt)
         # the local cell sort reads the receive area in place (padding rows carry the sentinel)
@@ -936,6 +937,11 @@ class StaticDistLayout(object):
         self.cell_start = local.cell_start
         self.keys = local.keys
         self.newlength = plan.cap_recv
+        # padding sorted last (its key is the overflow bucket): mark those slots, so that every
+        # later take writes the sentinel position / 0 there and every scatter or put skips them
+        C.check(C.lib.vpm_route_mark_padding(rt.ctx, _ptr(self.indices), plan.cap_recv, _ptr(self.rcnt), P))
+        self._fill = (ctypes.c_double * 3)(*pm._sentinel())
+        C.check(C.lib.vpm_ctx_set_fill_row(rt.ctx, self._fill))
         xs = rt.empty((plan.cap_recv, 3))
         C.check(C.lib.vpm_take_rows(rt.ctx, px.recv_ptr(b), _ptr(self.indices), plan.cap_recv, 3, _ptr(xs)))
         pos = asdevice(pos)
@@ -966,6 +972,7 @@ class StaticDistLayout(object):
         ncomp = _ncomp(t)
         self._area(ncomp)
         out = rt.empty((plan.cap_recv,) + tuple(t.shape[1:]))
+        C.check(C.lib.vpm_ctx_set_fill_row(rt.ctx, self._fill))
         _, b = px.begin()
         if self.take_idx is not None:
             px.put_rows(b, t, self.send_idx, plan.cap_send, ncomp, 1, plan.sbase, plan.fwd_base, skip=pm.rank)
@@ -1257,7 +1264,11 @@ class ParticleMesh(object):
         bad = self.comm.allreduce(int(self._overflow.item()))     # collective: all ranks raise together
         if bad:
             self._overflow.zero_()
-            raise RoutingOverflow("a segment of the fixed-capacity particle routing overflowed on %d rank(s)" % bad)
+            last = getattr(self, '_last_static', lambda: None)()
+            info = "" if last is None else (" (rank %d: capacities %s, last layout sent %s)" % (
+                self.rank, last.plan.cap[self.rank].tolist(), last.scnt.cpu().tolist()))
+            raise RoutingOverflow("a segment of the fixed-capacity particle routing overflowed on %d rank(s)%s"
+                                  % (bad, info))
 
     def _global_count(self, n):
         """sum over ranks of a particle count; the answer for a given local count is cached (the
@@ -1267,11 +1278,13 @@ class ParticleMesh(object):
             hit = self._tables[('count', n)] = int(self.comm.allreduce(int(n)))
         return hit
 
-    def _sentinel(self):
-        """a position on a mesh plane that this rank neither holds nor keys as its lower ghost"""
+    def _sentinel(self, rank=None):
+        """a position on a mesh plane that ``rank`` (default: this rank) neither holds nor keys as
+        its lower ghost: inert padding for that rank's cell sort, paint and readout"""
         n0, n0l = int(self.Nmesh[0]), self.rshape[0]
         cell = self.BoxSize / self.Nmesh
-        i0 = (self.rstart0 + n0l + 1) % n0
+        rank = self.rank if rank is None else rank
+        i0 = (rank * n0l + n0l + 1) % n0
         return ((i0 + 0.5) * cell[0], 0.25 * cell[1], 0.25 * cell[2])
 
     # -- decompose (fastpm.py:272) ------------------------------------------------------------
@@ -1877,6 +1890,11 @@ class ParticleMesh(object):
             self._tf_cache[key] = hit
         return self._transfer_table(cplx, None, conj, prepared=hit[1])
 
+    @property
+    def digitized(self):
+        """device side of ``apply_digitized`` (fastpm.py:97-213)"""
+        return _Digitized(self)
+
     def force_kspace(self, rhok, scale, grad_tables, want_p=True):
         """fused ``gravity`` k-space pass (fastpm.py:424-431); 3-D only"""
         rt = self.rt
@@ -1890,6 +1908,45 @@ class ParticleMesh(object):
                                        _ptr(grad_tables[1]), _ptr(grad_tables[2]), _ptr(p),
                                        _ptr(g[0]), _ptr(g[1]), _ptr(g[2])))
         return (ComplexField(self, p) if want_p else None), [ComplexField(self, t) for t in g]
+
+
+class _Digitized(object):
+    """binned transfer functions on the device: index arrays from the user's digitizer, the
+    per-mode multiply ``x * table[bin]`` and the binned reduction of the vjp w.r.t. the table"""
+
+    def __init__(self, pm):
+        self.pm = pm
+
+    def bins(self, ind, conj):
+        """host (ind, conj) of the local complex shape -> (int32 device tensor, uint8 tensor or None)"""
+        pm = self.pm
+        ind = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(ind), pm.cshape))
+        ind = numpy.clip(ind, -1, 2 ** 31 - 2).astype('i4')        # anything below 0 is "no bin"
+        conj = numpy.broadcast_to(numpy.asarray(conj, dtype='?'), pm.cshape)
+        ind_d = torch.from_numpy(ind).to(pm.rt.device)
+        conj_d = torch.from_numpy(numpy.ascontiguousarray(conj).astype('u1')).to(pm.rt.device) if conj.any() else None
+        return ind_d, conj_d
+
+    def mul(self, x, ind, conj, table, dflt, conj_table=False):
+        pm, rt = self.pm, self.pm.rt
+        x = pm._as_field(x, True)
+        t = _upload(numpy.asarray(table).ravel(), numpy.complex128)
+        rt.sync_stream()
+        o = rt.empty(pm.cshape, _C16)
+        C.check(C.lib.vpm_digitized_mul(rt.ctx, x.t.numel(), _ptr(x.t), _ptr(ind), _ptr(conj), t.numel(), _ptr(t),
+                                        float(dflt), 1 if conj_table else 0, _ptr(o)))
+        return ComplexField(pm, o)
+
+    def bin(self, x, ybar, ind, conj, nbins, eit):
+        """local part of the cotangent of the table: a host array of ``nbins`` doubles"""
+        pm, rt = self.pm, self.pm.rt
+        x, ybar = pm._as_field(x, True), pm._as_field(ybar, True)
+        e = _upload(numpy.asarray(eit).ravel(), numpy.complex128) if eit is not None else None
+        rt.sync_stream()
+        out = rt.empty((nbins,))
+        C.check(C.lib.vpm_digitized_bin(rt.ctx, C.i3(pm._cshape3), int(pm.Nmesh[-1]), _ptr(x.t), _ptr(ybar.t),
+                                        _ptr(ind), _ptr(conj), int(nbins), _ptr(e), _ptr(out)))
+        return out.cpu().numpy()
 
 
 # ---------------------------------------------------------------------------------------------
