@@ -497,7 +497,7 @@ def profile_step(env, prob, ms_per_step):
         if gb > 0:
             e['calls'] += 1
             e['bytes'] += gb
-        kk = kernels.setdefault(k, dict(launches=0, ms=0.0, group=g))
+        kk = kernels.setdefault((g, k), dict(launches=0, ms=0.0, group=g))
         kk['launches'] += 1
         kk['ms'] += ms
     out = []
@@ -508,7 +508,7 @@ def profile_step(env, prob, ms_per_step):
         if e['bytes'] > 0 and e['ms'] > 0:
             ach = e['bytes'] / (e['ms'] * 1e-3) / 1e9
             rec.update(algorithmic_bytes_per_call=e['bytes'] / max(e['calls'], 1), achieved=ach, frac=ach / peak)
-        rec['kernels'] = {k: dict(launches=v['launches'], ms=v['ms']) for k, v in kernels.items() if v['group'] == g}
+        rec['kernels'] = {k[1]: dict(launches=v['launches'], ms=v['ms']) for k, v in kernels.items() if k[0] == g}
         out.append(rec)
     return dict(step_ms_profiled=total, step_ms_timed=ms_per_step, launches=len(p.records),
                 entry_points=out, peak=peak, peak_source=peak_src)

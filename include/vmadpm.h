@@ -108,18 +108,28 @@ int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64
  * negative index are skipped (vpm_scatter_rows too). */
 int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n,
                          int ncomp, double* dst);
+/* dst[idx[i], :] += scale * src[i, :]  (gather across ranks fused with a kick / drift update: dst
+ * starts as a copy of the array being updated) */
+int vpm_scatter_add_rows_scaled(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n,
+                                int ncomp, double scale, double* dst);
 /* dst[i, :] = idx[i] >= 0 ? a[idx[i], :] : b[-1 - idx[i], :]   (Layout.exchange across ranks: rows
  * that stay on this rank are read from the home array a, the rest from the receive area b) */
 int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
                    int ncomp, double* dst);
+/* ... times a constant (the kick factor riding on the exchange of a momentum cotangent) */
+int vpm_take_rows2_scaled(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
+                          int ncomp, double scale, double* dst);
 /* Index composition for a cross-rank layout.  sorted_to_recv = the local sort permutation over the
  * receive order; the self segment is rows [recv_lo, recv_hi) of the receive order and rows
  * [send_lo, send_lo + recv_hi - recv_lo) of the send order.
  *   take[k]   = send_idx[send_lo + r - recv_lo] if r = sorted_to_recv[k] is a self row, else -1 - r
- *   remote[j] = send_idx[j] outside the self segment, -1 inside */
+ *   remote[j] = send_idx[j] outside the self segment, -1 inside
+ *   inv_remote[r'] (optional, nrecv - (recv_hi - recv_lo) ints) = the sorted slot k of receive
+ *               row r outside the self segment (r' = r below the segment, r - its length above),
+ *               -1 for rows no slot refers to */
 int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv,
                       const int32_t* send_idx, int64_t nsend, int64_t recv_lo, int64_t recv_hi,
-                      int64_t send_lo, int32_t* take, int32_t* remote);
+                      int64_t send_lo, int32_t* take, int32_t* remote, int32_t* inv_remote);
 
 /* Routing for the slab decomposition over `nranks` ranks (rank r owns planes
  * [r n0/nranks, (r+1) n0/nranks)): a particle is sent to the owner of its floor plane and, when
@@ -296,13 +306,23 @@ int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t 
  * stencils: the two boundary planes of a slab go to the neighbouring rank only); sync as above. */
 int vpm_peer_put_to(vpm_ctx* ctx, int nranks, uint32_t dest_mask, int64_t count, const double* src,
                     const uint64_t* peer_bufs, int64_t dst_off, const vpm_peer_sync* sync);
+/* nblocks (<= 8) contiguous blocks of `count` complex128 elements in ONE launch: block k goes from
+ * src + src_off[k] (elements) to element dst_off[k] of rank dest[k]'s receive area (host arrays).
+ * The two boundary-plane pairs of a slab travel to the previous and the next rank this way. */
+int vpm_peer_put_blocks(vpm_ctx* ctx, int nranks, int nblocks, int64_t count, const double* src,
+                        const int32_t* dest, const int64_t* src_off, const int64_t* dst_off,
+                        const uint64_t* peer_bufs, const vpm_peer_sync* sync);
+/* out_a[0 .. count) = a, out_b[0 .. count) = b (complex128 elements) in one launch */
+int vpm_copy2(vpm_ctx* ctx, int64_t count, const double* a, double* out_a, const double* b, double* out_b);
 /* Particle rows (Layout.exchange / Layout.gather across ranks; replaces pmesh's MPI_Alltoallv):
  * pack and transfer in one kernel.  Position p of the routing order lies in segment d when
  * seg_start[d] <= p < seg_start[d+1] (host array, nranks+1) and is stored to row
  * dst_base[d] + p - seg_start[d] of peer d's receive area (ncomp doubles per row).
- * idx_is_src=1: p = j, source row idx[j] (exchange); idx_is_src=0: p = idx[j], source row j
- * (gather, idx = the local sort permutation).  Rows of segment skip_seg (-1: none) are not
- * transferred: rows staying on this rank bypass the receive area (vpm_route_compose).
+ * idx_is_src=1: position p, source row idx[p] (exchange); idx_is_src=0: p = idx[j], source row j
+ * (gather, idx = the local sort permutation); idx_is_src=2: position p, source row idx[t] with
+ * idx = the inverse permutation over the positions outside skip_seg (gather; vpm_route_compose's
+ * inv_remote).  Rows of segment skip_seg (-1: none) are not transferred -- rows staying on this
+ * rank bypass the receive area (vpm_route_compose) -- and in modes 1 and 2 not even visited.
  * Fixed-capacity segments (vpm_route_build_static; the counts stay on the device):
  *   seg_count  (device, nranks ints or NULL) gather direction: only the first seg_count[d] rows
  *              of segment d hold particles;
@@ -385,6 +405,18 @@ int vpm_lpt2_source(vpm_ctx* ctx, const int64_t n[3], const double h[3], const d
 int vpm_lpt2_source_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* f0,
                             const double* f1, const double* f2, const double* sbar, double* work6,
                             double* fb0, double* fb1, double* fb2);
+/* Slab forms (several ranks): every mesh argument except out / sbar has `pad` (>= 2) halo planes on
+ * each side of axis 0 which the caller fills from the neighbouring slabs; n = the local cells
+ * written; the adjoint comes in two halves because W_00 and W_01 need their halo planes filled in
+ * between (the axis-0 difference of the second half).  w6_padded: [6][n0 + 2 pad][n1][n2]; fb0..2
+ * padded alike (interiors written). */
+int vpm_lpt2_source_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad, const double* f0,
+                         const double* f1, const double* f2, const double* g0, const double* g1,
+                         const double* g2, double scale, double* out);
+int vpm_lpt2_adjoint_w_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad, const double* f0,
+                            const double* f1, const double* f2, const double* sbar, double* w6_padded);
+int vpm_lpt2_adjoint_f_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
+                            const double* w6_padded, double* fb0, double* fb1, double* fb2);
 
 /* Binned transfer functions (fastpm.py:97-213 apply_digitized; pmesh ComplexField.apply with a
  * digitizer).  ind[m] = bin of stored mode m (int32, evaluated once on the host by the user's

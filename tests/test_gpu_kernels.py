@@ -356,8 +356,13 @@ def test_routing_helpers_bit_exact(device_pm):
     take = torch.empty(nrecv, dtype=torch.int32, device='cuda')
     remote = torch.empty(nsend, dtype=torch.int32, device='cuda')
     d_perm, d_send = dev(perm), dev(send_idx)
+    inv = torch.empty(nrecv - nself, dtype=torch.int32, device='cuda')
     C.check(C.lib.vpm_route_compose(rt.ctx, P(d_perm), nrecv, P(d_send), nsend, recv_lo, recv_lo + nself,
-                                    send_lo, P(take), P(remote)))
+                                    send_lo, P(take), P(remote), P(inv)))
+    want_inv = numpy.empty(nrecv, dtype='i4')
+    want_inv[perm] = numpy.arange(nrecv, dtype='i4')
+    want_inv = numpy.concatenate([want_inv[:recv_lo], want_inv[recv_lo + nself:]])
+    assert numpy.array_equal(inv.cpu().numpy(), want_inv)
     self_row = (perm >= recv_lo) & (perm < recv_lo + nself)
     want_take = numpy.where(self_row, send_idx[numpy.clip(send_lo + perm - recv_lo, 0, nsend - 1)], -1 - perm)
     want_remote = send_idx.copy()

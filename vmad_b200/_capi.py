@@ -78,7 +78,9 @@ SIGNATURES = {
     'vpm_scatter_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_scatter_add_rows': (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     'vpm_take_rows2': (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, _P]),
-    'vpm_route_compose': (c_int, [c_void_p, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
+    'vpm_take_rows2_scaled': (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, c_double, _P]),
+    'vpm_scatter_add_rows_scaled': (c_int, [c_void_p, _P, _P, c_int64, c_int, c_double, _P]),
+    'vpm_route_compose': (c_int, [c_void_p, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
     'vpm_paint_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
     'vpm_paint_sorted_cols3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int, c_int64, _P, _P, c_int64]),
     'vpm_paint_sorted_col': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int, c_int, c_int64, _P, _P]),
@@ -109,6 +111,9 @@ SIGNATURES = {
                              POINTER(vpm_peer_sync)]),
     'vpm_peer_put_to': (c_int, [c_void_p, c_int, ctypes.c_uint32, c_int64, _P, POINTER(c_uint64), c_int64,
                                 POINTER(vpm_peer_sync)]),
+    'vpm_peer_put_blocks': (c_int, [c_void_p, c_int, c_int, c_int64, _P, POINTER(c_int32), POINTER(c_int64),
+                                    POINTER(c_int64), POINTER(c_uint64), POINTER(vpm_peer_sync)]),
+    'vpm_copy2': (c_int, [c_void_p, c_int64, _P, _P, _P, _P]),
     'vpm_peer_put_rows': (c_int, [c_void_p, c_int, c_int64, c_int, _P, _P, c_int, c_int, POINTER(c_int32),
                                   POINTER(c_int64), _P, _P, POINTER(c_double), POINTER(c_uint64),
                                   POINTER(vpm_peer_sync)]),
@@ -131,6 +136,9 @@ SIGNATURES = {
     'vpm_fd4_neg_gradient_adjoint_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P]),
     'vpm_lpt2_source': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, c_double, _P]),
     'vpm_lpt2_source_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, _P, _P]),
+    'vpm_lpt2_source_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P, _P, _P, c_double, _P]),
+    'vpm_lpt2_adjoint_w_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P, _P]),
+    'vpm_lpt2_adjoint_f_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P]),
     'vpm_axpby': (c_int, [c_void_p, c_int64, c_double, _P, c_double, _P, c_double, _P]),
     'vpm_drift_pos': (c_int, [c_void_p, c_int64, _P, _P, c_double, _P, _P, _P]),
     'vpm_mul': (c_int, [c_void_p, c_int64, _P, _P, _P]),

@@ -291,7 +291,7 @@ __global__ void k_mark_padding(int* __restrict__ sorted_to_recv, int n, const in
 
 template <int NC, bool ADD>
 __global__ void k_scatter_rows(const double* __restrict__ src, const int* __restrict__ perm,
-                               long long n, int ncomp, double* __restrict__ dst) {
+                               long long n, int ncomp, double scale, double* __restrict__ dst) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int nc = NC > 0 ? NC : ncomp;
     if (e >= n * nc) return;
@@ -299,7 +299,7 @@ __global__ void k_scatter_rows(const double* __restrict__ src, const int* __rest
     int c = (int)(e - i * nc);
     const int p = perm[i];
     if (p < 0) return;              // masked row (lives on another rank / arrives separately)
-    double v = src[e];
+    double v = scale * src[e];       // scale = 1 is exact
     double* d = dst + (long long)p * nc + c;
     if (ADD) atomicAdd(d, v);
     else *d = v;
@@ -308,7 +308,7 @@ __global__ void k_scatter_rows(const double* __restrict__ src, const int* __rest
 // out[k] = idx[k] >= 0 ? a[idx[k]] : b[-1 - idx[k]]   (rows of NC doubles)
 template <int NC>
 __global__ void k_take_rows2(const double* __restrict__ a, const double* __restrict__ b,
-                             const int* __restrict__ idx, long long n, int ncomp, Fill3 fill,
+                             const int* __restrict__ idx, long long n, int ncomp, double scale, Fill3 fill,
                              double* __restrict__ dst) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int nc = NC > 0 ? NC : ncomp;
@@ -320,7 +320,7 @@ __global__ void k_take_rows2(const double* __restrict__ a, const double* __restr
         dst[e] = (NC == 3) ? fill.v[c] : 0.0;
         return;
     }
-    dst[e] = p >= 0 ? a[(long long)p * nc + c] : b[(long long)(-1 - p) * nc + c];
+    dst[e] = scale * (p >= 0 ? a[(long long)p * nc + c] : b[(long long)(-1 - p) * nc + c]);
 }
 
 // Index composition for a cross-rank layout: rows that stay on this rank skip the receive area.
@@ -329,7 +329,7 @@ __global__ void k_take_rows2(const double* __restrict__ a, const double* __restr
 __global__ void k_route_compose(const int* __restrict__ sorted_to_recv, int nrecv,
                                 const int* __restrict__ send_idx, int nsend, int recv_lo,
                                 int recv_hi, int send_lo, int* __restrict__ take,
-                                int* __restrict__ remote) {
+                                int* __restrict__ remote, int* __restrict__ inv_remote) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nrecv) {
         const int r = sorted_to_recv[t];
@@ -340,6 +340,7 @@ __global__ void k_route_compose(const int* __restrict__ sorted_to_recv, int nrec
             take[t] = h >= 0 ? h : VPM_ROW_PADDING;
         } else {
             take[t] = -1 - r;
+            if (inv_remote) inv_remote[r < recv_lo ? r : r - (recv_hi - recv_lo)] = t;
         }
     }
     if (t < nsend) {
@@ -353,6 +354,8 @@ __global__ void k_route_compose(const int* __restrict__ sorted_to_recv, int nrec
 // that owns plane i0 + 1 (the two planes a CIC particle touches).  Within a destination the
 // original particle order is kept (stable), so the routing is deterministic.
 constexpr int ROUTE_THREADS = 256;
+constexpr int ROUTE_ROUNDS = 8;                          // a block routes ROUTE_ROUNDS x 256 consecutive particles
+constexpr int ROUTE_TILE = ROUTE_THREADS * ROUTE_ROUNDS;
 constexpr int ROUTE_MAXP = 64;
 
 __device__ __forceinline__ void route_of(const Geo& g, int planes_per_rank, const double* x,
@@ -371,39 +374,68 @@ k_route_count(Geo g, int planes_per_rank, int P, const double* __restrict__ x, l
     __shared__ int c[ROUTE_MAXP];
     for (int d = threadIdx.x; d < P; d += blockDim.x) c[d] = 0;
     __syncthreads();
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p < np) {
-        int r0, r1;
-        route_of(g, planes_per_rank, x, p, r0, r1);
-        atomicAdd(&c[r0], 1);
-        if (r1 >= 0) atomicAdd(&c[r1], 1);
+    for (int r = 0; r < ROUTE_ROUNDS; ++r) {
+        long long p = blockIdx.x * (long long)ROUTE_TILE + r * ROUTE_THREADS + threadIdx.x;
+        if (p < np) {
+            int r0, r1;
+            route_of(g, planes_per_rank, x, p, r0, r1);
+            atomicAdd(&c[r0], 1);
+            if (r1 >= 0) atomicAdd(&c[r1], 1);
+        }
     }
     __syncthreads();
     for (int d = threadIdx.x; d < P; d += blockDim.x) counts[d * nblocks + blockIdx.x] = c[d];
+}
+
+// in-block stable ranks: rounds in order, within a round warps in order, within a warp lanes in
+// order (ballot); `run[d]` carries the rows bound for d seen in the earlier rounds of this block
+template <bool STATIC>
+__device__ __forceinline__ void route_scatter_block(const Geo& g, int planes_per_rank, int P,
+                                                    const double* __restrict__ x, long long np,
+                                                    long long nblocks, const int* __restrict__ offsets,
+                                                    const int* seg_start, int* __restrict__ send_idx) {
+    __shared__ int warp_cnt[ROUTE_THREADS / 32];
+    __shared__ int run[ROUTE_MAXP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < P; d += blockDim.x) run[d] = 0;
+    __syncthreads();
+    for (int r = 0; r < ROUTE_ROUNDS; ++r) {
+        const long long p = blockIdx.x * (long long)ROUTE_TILE + r * ROUTE_THREADS + threadIdx.x;
+        int r0 = -1, r1 = -1;
+        if (p < np) route_of(g, planes_per_rank, x, p, r0, r1);
+        for (int d = 0; d < P; ++d) {
+            const bool mine = (r0 == d) || (r1 == d);
+            const unsigned b = __ballot_sync(0xffffffffu, mine);
+            if (lane == 0) warp_cnt[w] = __popc(b);
+            __syncthreads();
+            int base = run[d];
+            for (int k = 0; k < w; ++k) base += warp_cnt[k];
+            if (mine) {
+                const int rank = base + __popc(b & ((1u << lane) - 1));
+                if (STATIC) {
+                    // rank among the rows bound for d (input order): rows of earlier blocks + this one
+                    const int pos = offsets[d * nblocks + blockIdx.x] - offsets[d * nblocks] + rank;
+                    if (pos < seg_start[d + 1] - seg_start[d]) send_idx[seg_start[d] + pos] = (int)p;
+                } else {
+                    send_idx[offsets[d * nblocks + blockIdx.x] + rank] = (int)p;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int k = 0; k < ROUTE_THREADS / 32; ++k) tot += warp_cnt[k];
+                run[d] += tot;
+            }
+            __syncthreads();
+        }
+    }
 }
 
 __global__ void __launch_bounds__(ROUTE_THREADS)
 k_route_scatter(Geo g, int planes_per_rank, int P, const double* __restrict__ x, long long np,
                 long long nblocks, const int* __restrict__ offsets /* [P][nblocks] */,
                 int* __restrict__ send_idx) {
-    __shared__ int warp_cnt[ROUTE_THREADS / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int r0 = -1, r1 = -1;
-    if (p < np) route_of(g, planes_per_rank, x, p, r0, r1);
-    for (int d = 0; d < P; ++d) {
-        const bool mine = (r0 == d) || (r1 == d);
-        const unsigned b = __ballot_sync(0xffffffffu, mine);
-        if (lane == 0) warp_cnt[w] = __popc(b);
-        __syncthreads();
-        int base = 0;
-        for (int k = 0; k < w; ++k) base += warp_cnt[k];
-        if (mine) {
-            const int rank = base + __popc(b & ((1u << lane) - 1));
-            send_idx[offsets[d * nblocks + blockIdx.x] + rank] = (int)p;
-        }
-        __syncthreads();
-    }
+    route_scatter_block<false>(g, planes_per_rank, P, x, np, nblocks, offsets, nullptr, send_idx);
 }
 
 // fixed-capacity variant: destination d owns positions [seg[d], seg[d + 1]) of the send order
@@ -415,27 +447,7 @@ __global__ void __launch_bounds__(ROUTE_THREADS)
 k_route_scatter_static(Geo g, int planes_per_rank, int P, const double* __restrict__ x, long long np,
                        long long nblocks, const int* __restrict__ offsets /* [P][nblocks] */,
                        RouteSegs seg, int* __restrict__ send_idx) {
-    __shared__ int warp_cnt[ROUTE_THREADS / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int r0 = -1, r1 = -1;
-    if (p < np) route_of(g, planes_per_rank, x, p, r0, r1);
-    for (int d = 0; d < P; ++d) {
-        const bool mine = (r0 == d) || (r1 == d);
-        const unsigned b = __ballot_sync(0xffffffffu, mine);
-        if (lane == 0) warp_cnt[w] = __popc(b);
-        __syncthreads();
-        int base = 0;
-        for (int k = 0; k < w; ++k) base += warp_cnt[k];
-        if (mine) {
-            // rank of this row among the rows bound for d (input order): rows before this block +
-            // rows of this block before this thread
-            const int rank = offsets[d * nblocks + blockIdx.x] - offsets[d * nblocks] + base +
-                             __popc(b & ((1u << lane) - 1));
-            if (rank < seg.start[d + 1] - seg.start[d]) send_idx[seg.start[d] + rank] = (int)p;
-        }
-        __syncthreads();
-    }
+    route_scatter_block<true>(g, planes_per_rank, P, x, np, nblocks, offsets, seg.start, send_idx);
 }
 
 // counts[d] = rows bound for d (clipped to the capacity), counts[P] = 1 when a segment overflowed
@@ -486,7 +498,7 @@ int vpm_route_build(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const double
     Geo g = make_geo(&m);
     const int ppr = (int)(mesh->n[0] / nranks);
     cudaStream_t st = ctx->stream;
-    const long long nblocks = std::max<long long>(1, ceil_div(np, ROUTE_THREADS));
+    const long long nblocks = std::max<long long>(1, ceil_div(np, ROUTE_TILE));
     const long long ncount = (long long)nranks * nblocks;
     const long long ntmp = scan_tmp_ints(ncount);
     int* ws = (int*)ctx->workspace((size_t)(2 * ncount + ntmp + nranks + 8) * sizeof(int));
@@ -532,7 +544,7 @@ int vpm_route_build_static(vpm_ctx* ctx, const vpm_mesh* mesh, int nranks, const
     // positions without a particle keep -1
     VPM_PROF_CALL("memset(send_idx)", st,
                   VPM_CUDA(cudaMemsetAsync(send_idx, 0xff, (size_t)seg.start[nranks] * sizeof(int), st)));
-    const long long nblocks = std::max<long long>(1, ceil_div(np, ROUTE_THREADS));
+    const long long nblocks = std::max<long long>(1, ceil_div(np, ROUTE_TILE));
     const long long ncount = (long long)nranks * nblocks;
     const long long ntmp = scan_tmp_ints(ncount);
     int* ws = (int*)ctx->workspace((size_t)(2 * ncount + ntmp + 8) * sizeof(int));
@@ -656,15 +668,20 @@ int vpm_scatter_rows(vpm_ctx* ctx, const double* src, const int32_t* perm, int64
     if (n > 0) {
         VPM_REQUIRE(src && perm && dst, "NULL array");
         unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
-        if (ncomp == 1) VPM_LAUNCH((k_scatter_rows<1, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
-        else if (ncomp == 3) VPM_LAUNCH((k_scatter_rows<3, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
-        else VPM_LAUNCH((k_scatter_rows<0, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, dst);
+        if (ncomp == 1) VPM_LAUNCH((k_scatter_rows<1, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, 1.0, dst);
+        else if (ncomp == 3) VPM_LAUNCH((k_scatter_rows<3, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, 1.0, dst);
+        else VPM_LAUNCH((k_scatter_rows<0, false>), grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, 1.0, dst);
     }
     VPM_API_END
 }
 
 int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
                    int ncomp, double* dst) {
+    return vpm_take_rows2_scaled(ctx, a, b, idx, n, ncomp, 1.0, dst);
+}
+
+int vpm_take_rows2_scaled(vpm_ctx* ctx, const double* a, const double* b, const int32_t* idx, int64_t n,
+                          int ncomp, double scale, double* dst) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("take_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
@@ -674,16 +691,16 @@ int vpm_take_rows2(vpm_ctx* ctx, const double* a, const double* b, const int32_t
         unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
         Fill3 fill;
         for (int c = 0; c < 3; ++c) fill.v[c] = ctx->fill_row[c];
-        if (ncomp == 1) VPM_LAUNCH(k_take_rows2<1>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, fill, dst);
-        else if (ncomp == 3) VPM_LAUNCH(k_take_rows2<3>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, fill, dst);
-        else VPM_LAUNCH(k_take_rows2<0>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, fill, dst);
+        if (ncomp == 1) VPM_LAUNCH(k_take_rows2<1>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, scale, fill, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows2<3>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, scale, fill, dst);
+        else VPM_LAUNCH(k_take_rows2<0>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, scale, fill, dst);
     }
     VPM_API_END
 }
 
 int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv,
                       const int32_t* send_idx, int64_t nsend, int64_t recv_lo, int64_t recv_hi,
-                      int64_t send_lo, int32_t* take, int32_t* remote) {
+                      int64_t send_lo, int32_t* take, int32_t* remote, int32_t* inv_remote) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("route_compose", 8.0 * nrecv + 8.0 * nsend);
     VPM_REQUIRE(ctx, "ctx is NULL");
@@ -692,9 +709,11 @@ int vpm_route_compose(vpm_ctx* ctx, const int32_t* sorted_to_recv, int64_t nrecv
     if (n > 0) {
         VPM_REQUIRE((nrecv == 0 || (sorted_to_recv && take)) && (nsend == 0 || (send_idx && remote)),
                     "NULL array");
+        if (inv_remote && nrecv - (recv_hi - recv_lo) > 0)
+            VPM_CUDA(cudaMemsetAsync(inv_remote, 0xff, (size_t)(nrecv - (recv_hi - recv_lo)) * sizeof(int), ctx->stream));
         VPM_LAUNCH(k_route_compose, (unsigned)ceil_div(n, 256), 256, 0, ctx->stream, sorted_to_recv,
                    (int)nrecv, send_idx, (int)nsend, (int)recv_lo, (int)recv_hi, (int)send_lo, take,
-                   remote);
+                   remote, inv_remote);
     }
     VPM_API_END
 }
@@ -720,6 +739,11 @@ int vpm_ctx_set_fill_row(vpm_ctx* ctx, const double* row3_host) {
 
 int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n, int ncomp,
                          double* dst) {
+    return vpm_scatter_add_rows_scaled(ctx, src, idx, n, ncomp, 1.0, dst);
+}
+
+int vpm_scatter_add_rows_scaled(vpm_ctx* ctx, const double* src, const int32_t* idx, int64_t n, int ncomp,
+                                double scale, double* dst) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("scatter_add_rows", (16.0 * ncomp + 4.0) * n);
     VPM_REQUIRE(ctx, "ctx is NULL");
@@ -727,9 +751,9 @@ int vpm_scatter_add_rows(vpm_ctx* ctx, const double* src, const int32_t* idx, in
     if (n > 0) {
         VPM_REQUIRE(src && idx && dst, "NULL array");
         unsigned grid = (unsigned)ceil_div(n * ncomp, 256);
-        if (ncomp == 1) VPM_LAUNCH((k_scatter_rows<1, true>), grid, 256, 0, ctx->stream, src, idx, (long long)n, ncomp, dst);
-        else if (ncomp == 3) VPM_LAUNCH((k_scatter_rows<3, true>), grid, 256, 0, ctx->stream, src, idx, (long long)n, ncomp, dst);
-        else VPM_LAUNCH((k_scatter_rows<0, true>), grid, 256, 0, ctx->stream, src, idx, (long long)n, ncomp, dst);
+        if (ncomp == 1) VPM_LAUNCH((k_scatter_rows<1, true>), grid, 256, 0, ctx->stream, src, idx, (long long)n, ncomp, scale, dst);
+        else if (ncomp == 3) VPM_LAUNCH((k_scatter_rows<3, true>), grid, 256, 0, ctx->stream, src, idx, (long long)n, ncomp, scale, dst);
+        else VPM_LAUNCH((k_scatter_rows<0, true>), grid, 256, 0, ctx->stream, src, idx, (long long)n, ncomp, scale, dst);
     }
     VPM_API_END
 }

@@ -132,6 +132,40 @@ k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_
     peer_publish(P, sy);
 }
 
+// up to 8 contiguous blocks of `count` complex elements, block k going from src + src_off[k] to
+// element dst_off[k] of rank dest[k]'s receive area: the halo planes of a slab travel to both
+// neighbours in ONE launch (and one pass of the flag protocol)
+struct PeerBlocks {
+    int dest[8];
+    long long src_off[8], dst_off[8];
+};
+
+__global__ void __launch_bounds__(256)
+k_peer_put_blocks(int P, int nblocks, long long count, const double2* __restrict__ src, PeerBlocks blk,
+                  PeerPtrs dst, PeerSync sy) {
+    peer_acquire(P, sy);
+    const int k = blockIdx.y;
+    if (k < nblocks) {
+        const double2* __restrict__ in = src + blk.src_off[k];
+        double2* __restrict__ out = reinterpret_cast<double2*>(dst.p[blk.dest[k]]) + blk.dst_off[k];
+        for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < count;
+             c += (long long)gridDim.x * blockDim.x)
+            out[c] = in[c];
+    }
+    peer_publish(P, sy);
+}
+
+// two copies of `count` complex elements in one launch (the received halo planes into the padded array)
+__global__ void __launch_bounds__(256)
+k_copy2(long long count, const double2* __restrict__ a, double2* __restrict__ oa,
+        const double2* __restrict__ b, double2* __restrict__ ob) {
+    const double2* __restrict__ in = blockIdx.y ? b : a;
+    double2* __restrict__ out = blockIdx.y ? ob : oa;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < count;
+         c += (long long)gridDim.x * blockDim.x)
+        out[c] = in[c];
+}
+
 struct PeerSegs {
     int start[9];            // segment boundaries in the routing order (P + 1 used)
     long long base[8];       // first destination row of my segment in peer d's receive area
@@ -145,12 +179,16 @@ struct PeerSegs {
 // Particle rows to their destination ranks, pack and transfer fused.  Routing order position p
 // (a row of the send order / of the receive order) belongs to segment d when
 // start[d] <= p < start[d + 1] and lands in row base[d] + p - start[d] of peer d.
-//   idx_is_src = 1 (exchange): position p = j,       source row = idx[j]
-//   idx_is_src = 0 (gather):   position p = idx[j],  source row = j
+//   mode 1 (exchange):            position p,            source row = idx[p]
+//   mode 0 (gather):              position p = idx[j],   source row = j        (j over all rows)
+//   mode 2 (gather, by position): position p,            source row = idx[t]   (idx = the inverse
+//                                 of the sort permutation over the positions that are not skipped)
+// In modes 1 and 2 the loop runs over the positions OUTSIDE the skipped segment only (t -> p jumps
+// over it): rows that stay on their rank cost nothing here.
 template <int NC>
 __global__ void __launch_bounds__(256)
 k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
-                const int* __restrict__ idx, int idx_is_src, int skip_seg, PeerSegs seg,
+                const int* __restrict__ idx, int mode, int skip_seg, PeerSegs seg,
                 PeerPtrs dst, PeerSync sy) {
     peer_acquire(P, sy);
     if (seg.mail && blockIdx.x == 0 && (int)threadIdx.x < P) {
@@ -159,18 +197,26 @@ k_peer_put_rows(int P, int n, int ncomp, const double* __restrict__ src,
         f[W_MAIL + 4 * (8 * sy.buf + sy.rank)] = seg.mail[threadIdx.x];
     }
     const int nc = NC > 0 ? NC : ncomp;
-    const long long total = (long long)n * nc;
+    const bool jump = mode != 0 && skip_seg >= 0;
+    const int skip_lo = jump ? seg.start[skip_seg] : 0;
+    const int skip_len = jump ? seg.start[skip_seg + 1] - seg.start[skip_seg] : 0;
+    const long long total = (long long)(n - skip_len) * nc;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(e / nc);
-        const int c = (int)(e - (long long)j * nc);
-        const int k = idx[j];
-        const int p = idx_is_src ? j : k;
-        const int row = idx_is_src ? k : j;
+        const int t = (int)(e / nc);
+        const int c = (int)(e - (long long)t * nc);
+        int p, row;
+        if (mode == 0) {
+            p = idx[t];
+            row = t;
+        } else {
+            p = t < skip_lo ? t : t + skip_len;
+            row = mode == 1 ? idx[p] : idx[t];
+        }
         if (p < 0 || p >= seg.start[P]) continue;
         int d = 0;
 #pragma unroll
-        for (int t = 1; t < 8; ++t) d += (t < P && p >= seg.start[t]) ? 1 : 0;
+        for (int u = 1; u < 8; ++u) d += (u < P && p >= seg.start[u]) ? 1 : 0;
         if (d == skip_seg) continue;
         const int off = p - seg.start[d];
         if (seg.cnt && off >= seg.cnt[d]) continue;
@@ -292,6 +338,43 @@ static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, 
     VPM_API_END
 }
 
+int vpm_peer_put_blocks(vpm_ctx* ctx, int nranks, int nblocks, int64_t count, const double* src,
+                        const int32_t* dest, const int64_t* src_off, const int64_t* dst_off,
+                        const uint64_t* peer_bufs, const vpm_peer_sync* sync) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("peer_put", 32.0 * count * nblocks);
+    VPM_REQUIRE(ctx && src && dest && src_off && dst_off && peer_bufs, "NULL argument");
+    VPM_REQUIRE(nranks >= 1 && nranks <= 8 && nblocks >= 1 && nblocks <= 8 && count >= 0, "bad argument");
+    VPM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, "source must be 16-byte aligned");
+    PeerBlocks blk;
+    for (int k = 0; k < 8; ++k) {
+        blk.dest[k] = k < nblocks ? dest[k] : 0;
+        blk.src_off[k] = k < nblocks ? src_off[k] : 0;
+        blk.dst_off[k] = k < nblocks ? dst_off[k] : 0;
+        VPM_REQUIRE(blk.dest[k] >= 0 && blk.dest[k] < nranks, "bad destination rank");
+    }
+    const long long gx = std::max<long long>(1, std::min<long long>(ceil_div(count, 256), 4LL * ctx->sm_count / nblocks));
+    dim3 grid((unsigned)gx, (unsigned)nblocks);
+    VPM_LAUNCH(k_peer_put_blocks, grid, 256, 0, ctx->stream, nranks, nblocks, (long long)count,
+               reinterpret_cast<const double2*>(src), blk, make_ptrs(nranks, peer_bufs), make_sync(nranks, sync));
+    VPM_API_END
+}
+
+int vpm_copy2(vpm_ctx* ctx, int64_t count, const double* a, double* out_a, const double* b, double* out_b) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("copy2", 64.0 * count);
+    VPM_REQUIRE(ctx && count >= 0, "bad argument");
+    if (count > 0) {
+        VPM_REQUIRE(a && out_a && b && out_b, "NULL array");
+        const long long gx = std::max<long long>(1, std::min<long long>(ceil_div(count, 256), 2LL * ctx->sm_count));
+        dim3 grid((unsigned)gx, 2);
+        VPM_LAUNCH(k_copy2, grid, 256, 0, ctx->stream, (long long)count, reinterpret_cast<const double2*>(a),
+                   reinterpret_cast<double2*>(out_a), reinterpret_cast<const double2*>(b),
+                   reinterpret_cast<double2*>(out_b));
+    }
+    VPM_API_END
+}
+
 int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const double* src,
                       const int32_t* idx, int idx_is_src, int skip_seg, const int32_t* seg_start,
                       const int64_t* dst_base, const int32_t* seg_count, const int32_t* mail,
@@ -314,7 +397,11 @@ int vpm_peer_put_rows(vpm_ctx* ctx, int nranks, int64_t n, int ncomp, const doub
         for (int d = 0; d < 8; ++d)
             for (int i = 0; i < 3; ++i) seg.sentinel[d][i] = (sentinel_rows && d < nranks) ? sentinel_rows[3 * d + i] : 0.0;
         const PeerPtrs dst = make_ptrs(nranks, peer_bufs);
-        const long long total = (long long)n * ncomp;
+        VPM_REQUIRE(idx_is_src >= 0 && idx_is_src <= 2, "mode must be 0, 1 or 2");
+        VPM_REQUIRE(skip_seg < nranks, "bad skip segment");
+        long long rows = n;
+        if (idx_is_src != 0 && skip_seg >= 0) rows -= seg.start[skip_seg + 1] - seg.start[skip_seg];
+        const long long total = std::max<long long>(rows, 0) * ncomp;
         unsigned grid = (unsigned)std::max<long long>(
             1, std::min<long long>(ceil_div(total, 256), 16LL * ctx->sm_count));
         if (ncomp == 1)

@@ -107,12 +107,13 @@ struct Cell3 {
     int x, y, z;
 };
 
+// cell e of the n0 x n1 x n2 cells written; x counts planes of the (padded) INPUT arrays
 __device__ __forceinline__ Cell3 cell_of(const Grid3& g, long long e) {
     Cell3 c;
     c.z = (int)(e % g.n2);
     const long long r = e / g.n2;
     c.y = (int)(r % g.n1);
-    c.x = (int)(r / g.n1);
+    c.x = (int)(r / g.n1) + g.pad;
     return c;
 }
 
@@ -131,9 +132,11 @@ __device__ __forceinline__ double dax(const Grid3& g, const double* __restrict__
         const double b = __ldg(col + wrapi(c.y + 2, g.n1) * s1) - __ldg(col + wrapi(c.y - 2, g.n1) * s1);
         return (8.0 * a - b) * g.c1;
     } else {
+        // with pad > 0 the axis-0 neighbours are halo planes (no wrap happens), else periodic
+        const int nx = g.n0 + 2 * g.pad;
         const double* pil = f + (long long)c.y * s1 + c.z;
-        const double a = __ldg(pil + wrapi(c.x + 1, g.n0) * s0) - __ldg(pil + wrapi(c.x - 1, g.n0) * s0);
-        const double b = __ldg(pil + wrapi(c.x + 2, g.n0) * s0) - __ldg(pil + wrapi(c.x - 2, g.n0) * s0);
+        const double a = __ldg(pil + wrapi(c.x + 1, nx) * s0) - __ldg(pil + wrapi(c.x - 1, nx) * s0);
+        const double b = __ldg(pil + wrapi(c.x + 2, nx) * s0) - __ldg(pil + wrapi(c.x - 2, nx) * s0);
         return (8.0 * a - b) * g.c0;
     }
 }
@@ -186,12 +189,16 @@ k_lpt2_adjoint_w(Grid3 g, const double* __restrict__ F0, const double* __restric
     const Cell3 c = cell_of(g, e);
     const Hess p = hessian(g, F0, F1, F2, c);
     const double s = sbar[e];
-    W[e] = (3.0 / 7.0) * (p.p11 + p.p22) * s;
-    W[total + e] = (3.0 / 7.0) * (p.p22 + p.p00) * s;
-    W[2 * total + e] = (3.0 / 7.0) * (p.p00 + p.p11) * s;
-    W[3 * total + e] = -(6.0 / 7.0) * p.p12 * s;
-    W[4 * total + e] = -(6.0 / 7.0) * p.p20 * s;
-    W[5 * total + e] = -(6.0 / 7.0) * p.p01 * s;
+    // the six meshes carry the same halo planes as the inputs (filled by the caller across ranks)
+    const long long plane = (long long)g.n1 * g.n2;
+    const long long comp = (long long)(g.n0 + 2 * g.pad) * plane;
+    const long long o = e + g.pad * plane;
+    W[o] = (3.0 / 7.0) * (p.p11 + p.p22) * s;
+    W[comp + o] = (3.0 / 7.0) * (p.p22 + p.p00) * s;
+    W[2 * comp + o] = (3.0 / 7.0) * (p.p00 + p.p11) * s;
+    W[3 * comp + o] = -(6.0 / 7.0) * p.p12 * s;
+    W[4 * comp + o] = -(6.0 / 7.0) * p.p20 * s;
+    W[5 * comp + o] = -(6.0 / 7.0) * p.p01 * s;
 }
 
 // second half: P_ij = -D_i F_j  =>  Fbar_j = sum_i D_i W_ij
@@ -203,9 +210,12 @@ k_lpt2_adjoint_f(Grid3 g, const double* __restrict__ W, double* __restrict__ Fb0
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= total) return;
     const Cell3 c = cell_of(g, e);
-    Fb0[e] = dax<0>(g, W, c) + dax<2>(g, W + 4 * total, c);
-    Fb1[e] = dax<1>(g, W + total, c) + dax<0>(g, W + 5 * total, c);
-    Fb2[e] = dax<2>(g, W + 2 * total, c) + dax<1>(g, W + 3 * total, c);
+    const long long plane = (long long)g.n1 * g.n2;
+    const long long comp = (long long)(g.n0 + 2 * g.pad) * plane;
+    const long long o = e + g.pad * plane;      // outputs padded like the inputs
+    Fb0[o] = dax<0>(g, W, c) + dax<2>(g, W + 4 * comp, c);
+    Fb1[o] = dax<1>(g, W + comp, c) + dax<0>(g, W + 5 * comp, c);
+    Fb2[o] = dax<2>(g, W + 2 * comp, c) + dax<1>(g, W + 3 * comp, c);
 }
 
 static Grid3 make_grid(const int64_t n[3], const double h[3]) {
@@ -305,6 +315,62 @@ int vpm_lpt2_source_adjoint(vpm_ctx* ctx, const int64_t n[3], const double h[3],
     const unsigned grid = (unsigned)ceil_div(total, 256);
     VPM_LAUNCH(k_lpt2_adjoint_w, grid, 256, 0, ctx->stream, g, f0, f1, f2, sbar, work6);
     VPM_LAUNCH(k_lpt2_adjoint_f, grid, 256, 0, ctx->stream, g, work6, fb0, fb1, fb2);
+    VPM_API_END
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// slab forms of the 2LPT source and its adjoint: every mesh argument except `out` / `sbar` has
+// `pad` (>= 2) halo planes on each side of axis 0, filled by the caller from the neighbouring
+// slabs; n = the cells written (the local slab)
+int vpm_lpt2_source_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad, const double* f0,
+                         const double* f1, const double* f2, const double* g0, const double* g1,
+                         const double* g2, double scale, double* out) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("lpt2_source", 56.0 * ((double)n[0] * n[1] * n[2]));
+    VPM_REQUIRE(ctx && f0 && f1 && f2 && out, "NULL argument");
+    VPM_REQUIRE((g0 && g1 && g2) || (!g0 && !g1 && !g2), "pass all of g0, g1, g2 or none");
+    VPM_REQUIRE(pad >= 2, "the stencil needs two halo planes per side");
+    Grid3 g = make_grid(n, h);
+    g.pad = pad;
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    const unsigned grid = (unsigned)ceil_div(total, 256);
+    if (total > 0) {
+        if (g0)
+            VPM_LAUNCH(k_lpt2_bilinear<false>, grid, 256, 0, ctx->stream, g, f0, f1, f2, g0, g1, g2, scale, out);
+        else
+            VPM_LAUNCH(k_lpt2_bilinear<true>, grid, 256, 0, ctx->stream, g, f0, f1, f2, f0, f1, f2, scale, out);
+    }
+    VPM_API_END
+}
+
+int vpm_lpt2_adjoint_w_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad, const double* f0,
+                            const double* f1, const double* f2, const double* sbar, double* w6_padded) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("lpt2_source_adjoint", 80.0 * ((double)n[0] * n[1] * n[2]));
+    VPM_REQUIRE(ctx && f0 && f1 && f2 && sbar && w6_padded, "NULL argument");
+    VPM_REQUIRE(pad >= 2, "the stencil needs two halo planes per side");
+    Grid3 g = make_grid(n, h);
+    g.pad = pad;
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    if (total > 0)
+        VPM_LAUNCH(k_lpt2_adjoint_w, (unsigned)ceil_div(total, 256), 256, 0, ctx->stream, g, f0, f1, f2, sbar, w6_padded);
+    VPM_API_END
+}
+
+int vpm_lpt2_adjoint_f_slab(vpm_ctx* ctx, const int64_t n[3], const double h[3], int pad,
+                            const double* w6_padded, double* fb0, double* fb1, double* fb2) {
+    VPM_API_BEGIN
+    VPM_PROF_GROUP("lpt2_source_adjoint", 72.0 * ((double)n[0] * n[1] * n[2]));
+    VPM_REQUIRE(ctx && w6_padded && fb0 && fb1 && fb2, "NULL argument");
+    VPM_REQUIRE(pad >= 2, "the stencil needs two halo planes per side");
+    Grid3 g = make_grid(n, h);
+    g.pad = pad;
+    const long long total = (long long)g.n0 * g.n1 * g.n2;
+    if (total > 0)
+        VPM_LAUNCH(k_lpt2_adjoint_f, (unsigned)ceil_div(total, 256), 256, 0, ctx->stream, g, w6_padded, fb0, fb1, fb2);
     VPM_API_END
 }
 

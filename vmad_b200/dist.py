@@ -312,6 +312,17 @@ class PeerExchange(object):
         C.check(C.lib.vpm_peer_put_to(self._ctx(), self.P, int(mask), int(count), ct.c_void_p(int(src_ptr)),
                                       self.buf_ptrs[b], int(dst_off), self._sync(b, first, last)))
 
+    def put_blocks(self, b, src_ptr, count, blocks):
+        """``blocks`` = [(dest rank, source offset, destination offset)] in complex128 elements, each
+        ``count`` elements long, all in one launch and one pass of the flag protocol"""
+        C, ct = self.C, self.ctypes
+        nb = len(blocks)
+        dest = (ct.c_int32 * nb)(*[int(v[0]) for v in blocks])
+        so = (ct.c_int64 * nb)(*[int(v[1]) for v in blocks])
+        do = (ct.c_int64 * nb)(*[int(v[2]) for v in blocks])
+        C.check(C.lib.vpm_peer_put_blocks(self._ctx(), self.P, nb, int(count), ct.c_void_p(int(src_ptr)), dest, so, do,
+                                          self.buf_ptrs[b], self._sync(b, True, True)))
+
     def put_rows(self, b, src, idx, n, ncomp, idx_is_src, seg_start, dst_base, skip=-1, seg_count=None,
                  mail=None, sentinel=None):
         """particle rows to their destination ranks (vpm_peer_put_rows); ``seg_count`` / ``mail``

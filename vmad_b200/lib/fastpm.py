@@ -479,7 +479,8 @@ class lpt1_at_constant_q:
     constant of the graph -- as ONE operator: Green's function, ONE inverse FFT of the potential,
     the real-space 4-point stencil that ``fourier_space_neg_gradient(order=1)`` is the symbol of,
     and the three-mesh readout, instead of 4 transfers + 3 inverse FFTs + 3 readouts + stack
-    (13 nodes).  One-GPU device backend; ``lpt1`` is the portable graph."""
+    (13 nodes).  Device backend (across ranks the stencil reads the neighbours' boundary planes);
+    ``lpt1`` is the portable graph."""
     ain = {'rhok': 'ComplexField'}
     aout = {'dx1': 'ndarray'}
 
@@ -503,7 +504,8 @@ class lpt2src_real_space:
     gradient stencil, and a second stencil pass that forms the six second derivatives and their
     3/7 (sum P_ii P_jj - P_ij^2) combination -- instead of 13 transfers, 6 inverse FFTs and 9
     elementwise nodes; the reverse sweep is two stencil kernels, the gradient-stencil adjoint and
-    ONE forward FFT.  One-GPU device backend; ``lpt2src`` is the portable graph."""
+    ONE forward FFT.  Device backend (across ranks: four halo planes of the potential, then halo
+    planes of two of the six adjoint meshes); ``lpt2src`` is the portable graph."""
     ain = {'rhok': 'ComplexField'}
     aout = {'rho_lpt2': 'RealField'}
 
@@ -530,8 +532,8 @@ def lpt(rhok, q, pm):
         from .. import pm as dev
         if dev._use_stencil(pm):
             one = lpt1_at_constant_q           # across ranks: halo planes over peer memory
-            if getattr(pm, 'P', 1) == 1:
-                src = lpt2src_real_space       # (two stencils deep: one rank only)
+            if getattr(pm, 'P', 1) == 1 or pm.rshape[0] >= 4:
+                src = lpt2src_real_space       # two stencils deep: four halo planes across ranks
     dx1 = one(rhok, q, pm)
     rhok2 = r2c(src(rhok, pm))
     dx2 = one(rhok2, q, pm)

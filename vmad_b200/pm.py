@@ -686,12 +686,12 @@ class Layout(object):
         self.newlength = int(perm.shape[0])
         self._const = None          # (weakref to a constant input array, its sorted rows)
 
-    def exchange(self, data):
-        """fastpm.py:289,301,308."""
+    def exchange(self, data, scale=1.0):
+        """fastpm.py:289,301,308.  ``scale``: the rows arrive multiplied by this constant."""
         data = asdevice(data)
         if not isinstance(data, DeviceArray):
             raise TypeError("exchange needs an array")
-        frozen = getattr(data, '_frozen', False)
+        frozen = getattr(data, '_frozen', False) and scale == 1.0
         if frozen and self._const is not None and self._const[0]() is data:
             return DeviceArray(self._const[1], cellindex=self)
         rt = runtime()
@@ -700,13 +700,13 @@ class Layout(object):
         n = self.newlength
         ncomp = _ncomp(t)
         out = rt.empty((n,) + tuple(t.shape[1:]))
-        C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, _ptr(out)))
+        C.check(C.lib.vpm_take_rows_scaled(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, float(scale), _ptr(out)))
         if frozen:      # a constant of the graph (q): its sorted copy is a constant too
             self._const = (weakref.ref(data), out)
         return DeviceArray(out, cellindex=self)
 
-    def gather(self, data, mode='sum'):
-        """fastpm.py:286,293,304."""
+    def gather(self, data, mode='sum', init=None, scale=1.0):
+        """fastpm.py:286,293,304.  ``init`` / ``scale``: returns ``init + scale * gathered``."""
         data = asdevice(data)
         if not isinstance(data, DeviceArray):
             raise TypeError("gather needs an array")
@@ -718,7 +718,10 @@ class Layout(object):
         # single rank: the permutation is a bijection, every output row is written once
         out = rt.empty((self.oldlength,) + tuple(t.shape[1:]))
         C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), n, ncomp, _ptr(out)))
-        return DeviceArray(out)
+        r = DeviceArray(out)
+        if init is not None or scale != 1.0:
+            r = r * float(scale) if init is None else asdevice(init)._axpby(1.0, float(scale), out)
+        return r
 
 
 class DistLayout(object):
@@ -786,9 +789,12 @@ class DistLayout(object):
             # the tape per layout -- skipped in the memory-lean mode of the largest runs)
             self.take_idx = rt.empty((max(self.nrecv, 1),), torch.int32)
             self.send_remote = rt.empty((max(self.nsend, 1),), torch.int32)
+            nself = self.recv_start[me + 1] - self.recv_start[me]
+            self.inv_remote = rt.empty((max(self.nrecv - nself, 1),), torch.int32)
             C.check(C.lib.vpm_route_compose(rt.ctx, _ptr(self.indices), self.nrecv, _ptr(self.send_idx),
                                             self.nsend, self.recv_start[me], self.recv_start[me + 1],
-                                            self.send_start[me], _ptr(self.take_idx), _ptr(self.send_remote)))
+                                            self.send_start[me], _ptr(self.take_idx), _ptr(self.send_remote),
+                                            _ptr(self.inv_remote)))
 
     def _peer_forward(self, t, ncomp, skip=-1):
         """rows -> the peers' receive areas (pack fused with the NVLink stores); returns the
@@ -813,13 +819,14 @@ class DistLayout(object):
         C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(t), _ptr(self.send_idx), self.nsend, ncomp, _ptr(send)))
         return self.pm.comm.alltoallv_rows(send, self.send_counts, self.recv_counts)
 
-    def exchange(self, data):
-        """fastpm.py:289,301,308"""
+    def exchange(self, data, scale=1.0):
+        """fastpm.py:289,301,308.  ``scale``: the rows arrive multiplied by this constant."""
         data = asdevice(data)
-        if self._xs is not None and self._src is not None and self._src() is data:
+        if scale == 1.0 and self._xs is not None and self._src is not None and self._src() is data:
             return DeviceArray(self._xs, cellindex=self)
         rt = self.pm.rt
         rt.sync_stream()
+        scale = float(scale)
         if self.px is not None:
             # put -> (flags) -> the local sort gathers straight out of the receive area
             t = data.t
@@ -827,51 +834,66 @@ class DistLayout(object):
             out = rt.empty((self.nrecv,) + tuple(t.shape[1:]))
             if self.take_idx is not None:
                 e, b = self._peer_forward(t, ncomp, skip=self.pm.rank)
-                C.check(C.lib.vpm_take_rows2(rt.ctx, _ptr(t), self.px.recv_ptr(b), _ptr(self.take_idx),
-                                             self.nrecv, ncomp, _ptr(out)))
+                C.check(C.lib.vpm_take_rows2_scaled(rt.ctx, _ptr(t), self.px.recv_ptr(b), _ptr(self.take_idx),
+                                                    self.nrecv, ncomp, scale, _ptr(out)))
             else:
                 e, b = self._peer_forward(t, ncomp)
-                C.check(C.lib.vpm_take_rows(rt.ctx, self.px.recv_ptr(b), _ptr(self.indices), self.nrecv, ncomp,
-                                            _ptr(out)))
+                C.check(C.lib.vpm_take_rows_scaled(rt.ctx, self.px.recv_ptr(b), _ptr(self.indices), self.nrecv,
+                                                   ncomp, scale, _ptr(out)))
             return DeviceArray(out, cellindex=self)
         recv = self._forward(data.t)
         ncomp = _ncomp(recv)
         out = rt.empty(tuple(recv.shape))
-        C.check(C.lib.vpm_take_rows(rt.ctx, _ptr(recv), _ptr(self.indices), self.nrecv, ncomp, _ptr(out)))
+        C.check(C.lib.vpm_take_rows_scaled(rt.ctx, _ptr(recv), _ptr(self.indices), self.nrecv, ncomp, scale, _ptr(out)))
         return DeviceArray(out, cellindex=self)
 
-    def gather(self, data, mode='sum'):
-        """fastpm.py:286,293,304: back to the home rank and order, copies summed"""
+    def gather(self, data, mode='sum', init=None, scale=1.0):
+        """fastpm.py:286,293,304: back to the home rank and order, copies summed.
+        ``init`` / ``scale``: returns ``init + scale * gathered`` (the sum starts from a copy of
+        ``init`` instead of zeros and the factor rides on the scatter)"""
         data = asdevice(data)
         rt = self.pm.rt
         rt.sync_stream()
         t = data.t
         ncomp = _ncomp(t)
+        scale = float(scale)
+        shape = (self.oldlength,) + tuple(t.shape[1:])
+        out = asdevice(init).t.clone() if init is not None else torch.zeros(shape, dtype=_F8, device=rt.device)
         if self.px is not None:
             # sorted row k sits at receive position indices[k]; it goes back to its source rank,
             # into the row it had in that rank's send order, and is summed into its home row there
             px = self.px
             px.ensure(8 * self._max_rows * ncomp)
             e, b = px.begin()
-            out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
             if self.take_idx is None:
                 px.put_rows(b, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base)
-                C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), self.nsend, ncomp,
-                                                   _ptr(out)))
+                C.check(C.lib.vpm_scatter_add_rows_scaled(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), self.nsend,
+                                                          ncomp, scale, _ptr(out)))
                 return DeviceArray(out)
-            px.put_rows(b, t, self.indices, self.nrecv, ncomp, 0, self.recv_start, self._back_base,
+            # only the rows that came from other ranks are visited (through the inverse of the sort)
+            px.put_rows(b, t, self.inv_remote, self.nrecv, ncomp, 2, self.recv_start, self._back_base,
                         skip=self.pm.rank)
             # rows that never left go straight into their home rows
-            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(t), _ptr(self.take_idx), self.nrecv, ncomp, _ptr(out)))
-            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_remote), self.nsend, ncomp,
-                                               _ptr(out)))
+            C.check(C.lib.vpm_scatter_add_rows_scaled(rt.ctx, _ptr(t), _ptr(self.take_idx), self.nrecv, ncomp, scale,
+                                                      _ptr(out)))
+            _scatter_add_remote(rt, px, b, self.send_remote, self.send_start, self.pm.rank, ncomp, out, scale)
             return DeviceArray(out)
         unsorted = rt.empty(tuple(t.shape))
         C.check(C.lib.vpm_scatter_rows(rt.ctx, _ptr(t), _ptr(self.indices), self.nrecv, ncomp, _ptr(unsorted)))
         back = self.pm.comm.alltoallv_rows(unsorted, self.recv_counts, self.send_counts)
-        out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
-        C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(back), _ptr(self.send_idx), self.nsend, ncomp, _ptr(out)))
+        C.check(C.lib.vpm_scatter_add_rows_scaled(rt.ctx, _ptr(back), _ptr(self.send_idx), self.nsend, ncomp, scale,
+                                                  _ptr(out)))
         return DeviceArray(out)
+
+
+def _scatter_add_remote(rt, px, b, send_remote, send_start, me, ncomp, out, scale=1.0):
+    """what came back from the other ranks (receive area b, in send order) is summed into the home
+    rows; the positions of the self segment hold nothing, so only the ranges around it are visited"""
+    for lo, hi in ((0, send_start[me]), (send_start[me + 1], send_start[-1])):
+        if hi > lo:
+            src = ctypes.c_void_p(px.my_bufs[b] + 8 * ncomp * lo)
+            C.check(C.lib.vpm_scatter_add_rows_scaled(rt.ctx, src, _ptr(send_remote[lo:hi]), hi - lo, ncomp,
+                                                      float(scale), _ptr(out)))
 
 
 class RoutingOverflow(C.VpmError):
@@ -952,19 +974,21 @@ class StaticDistLayout(object):
             # rows that stay on this rank (nearly all) bypass the receive area (see DistLayout)
             self.take_idx = rt.empty((max(plan.cap_recv, 1),), torch.int32)
             self.send_remote = rt.empty((max(plan.cap_send, 1),), torch.int32)
+            self.inv_remote = rt.empty((max(plan.cap_recv - int(plan.cap[me, me]), 1),), torch.int32)
             C.check(C.lib.vpm_route_compose(rt.ctx, _ptr(self.indices), plan.cap_recv, _ptr(self.send_idx),
                                             plan.cap_send, plan.rbase[me], plan.rbase[me + 1], plan.sbase[me],
-                                            _ptr(self.take_idx), _ptr(self.send_remote)))
+                                            _ptr(self.take_idx), _ptr(self.send_remote), _ptr(self.inv_remote)))
 
     def _area(self, ncomp):
         if 8 * self.plan.max_rows * ncomp > self.px.nbytes:
             self.px.ensure(8 * self.plan.max_rows * ncomp)      # collective; not during a capture
 
-    def exchange(self, data):
-        """fastpm.py:289,301,308"""
+    def exchange(self, data, scale=1.0):
+        """fastpm.py:289,301,308.  ``scale``: the rows arrive multiplied by this constant."""
         data = asdevice(data)
-        if self._xs is not None and self._src is not None and self._src() is data:
+        if scale == 1.0 and self._xs is not None and self._src is not None and self._src() is data:
             return DeviceArray(self._xs, cellindex=self)
+        scale = float(scale)
         pm, plan, px = self.pm, self.plan, self.px
         rt = pm.rt
         rt.sync_stream()
@@ -976,34 +1000,39 @@ class StaticDistLayout(object):
         _, b = px.begin()
         if self.take_idx is not None:
             px.put_rows(b, t, self.send_idx, plan.cap_send, ncomp, 1, plan.sbase, plan.fwd_base, skip=pm.rank)
-            C.check(C.lib.vpm_take_rows2(rt.ctx, _ptr(t), px.recv_ptr(b), _ptr(self.take_idx), plan.cap_recv,
-                                         ncomp, _ptr(out)))
+            C.check(C.lib.vpm_take_rows2_scaled(rt.ctx, _ptr(t), px.recv_ptr(b), _ptr(self.take_idx), plan.cap_recv,
+                                                ncomp, scale, _ptr(out)))
         else:
             px.put_rows(b, t, self.send_idx, plan.cap_send, ncomp, 1, plan.sbase, plan.fwd_base)
-            C.check(C.lib.vpm_take_rows(rt.ctx, px.recv_ptr(b), _ptr(self.indices), plan.cap_recv, ncomp, _ptr(out)))
+            C.check(C.lib.vpm_take_rows_scaled(rt.ctx, px.recv_ptr(b), _ptr(self.indices), plan.cap_recv, ncomp,
+                                               scale, _ptr(out)))
         return DeviceArray(out, cellindex=self)
 
-    def gather(self, data, mode='sum'):
-        """fastpm.py:286,293,304: back to the home rank and order, copies summed"""
+    def gather(self, data, mode='sum', init=None, scale=1.0):
+        """fastpm.py:286,293,304: back to the home rank and order, copies summed.
+        ``init`` / ``scale``: returns ``init + scale * gathered``"""
         data = asdevice(data)
         pm, plan, px = self.pm, self.plan, self.px
         rt = pm.rt
         rt.sync_stream()
         t = data.t
         ncomp = _ncomp(t)
+        scale = float(scale)
         self._area(ncomp)
-        out = torch.zeros((self.oldlength,) + tuple(t.shape[1:]), dtype=_F8, device=rt.device)
+        shape = (self.oldlength,) + tuple(t.shape[1:])
+        out = asdevice(init).t.clone() if init is not None else torch.zeros(shape, dtype=_F8, device=rt.device)
         _, b = px.begin()
         if self.take_idx is None:
             px.put_rows(b, t, self.indices, plan.cap_recv, ncomp, 0, plan.rbase, plan.back_base, seg_count=self.rcnt)
-            C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), plan.cap_send, ncomp,
-                                               _ptr(out)))
+            C.check(C.lib.vpm_scatter_add_rows_scaled(rt.ctx, px.recv_ptr(b), _ptr(self.send_idx), plan.cap_send,
+                                                      ncomp, scale, _ptr(out)))
             return DeviceArray(out)
-        px.put_rows(b, t, self.indices, plan.cap_recv, ncomp, 0, plan.rbase, plan.back_base, skip=pm.rank,
-                    seg_count=self.rcnt)
-        C.check(C.lib.vpm_scatter_add_rows(rt.ctx, _ptr(t), _ptr(self.take_idx), plan.cap_recv, ncomp, _ptr(out)))
-        C.check(C.lib.vpm_scatter_add_rows(rt.ctx, px.recv_ptr(b), _ptr(self.send_remote), plan.cap_send, ncomp,
-                                           _ptr(out)))
+        # only the rows that came from other ranks are visited (through the inverse of the sort;
+        # receive positions no sorted slot refers to -- the padding -- carry -1 there)
+        px.put_rows(b, t, self.inv_remote, plan.cap_recv, ncomp, 2, plan.rbase, plan.back_base, skip=pm.rank)
+        C.check(C.lib.vpm_scatter_add_rows_scaled(rt.ctx, _ptr(t), _ptr(self.take_idx), plan.cap_recv, ncomp, scale,
+                                                  _ptr(out)))
+        _scatter_add_remote(rt, px, b, self.send_remote, plan.sbase, pm.rank, ncomp, out, scale)
         return DeviceArray(out)
 
 
@@ -1569,6 +1598,9 @@ class ParticleMesh(object):
         else:
             r = DeviceArray(val, cellindex=pos._cellindex)
             if gather is not None:
+                if kick is not None and not want_value:
+                    # the kick rides on the gather: the sum starts from a copy of y, factor on the scatter
+                    return None, gather.gather(r, init=kick[0], scale=kick[1])
                 r = gather.gather(r)
         if kick is not None:
             return r, asdevice(kick[0])._axpby(1.0, float(kick[1]), r.t)
@@ -1800,26 +1832,26 @@ class ParticleMesh(object):
         C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
         return RealField(self, o)
 
-    def _halo_fill(self, padded):
-        """fill the two halo planes on each side of a [n0l + 4, N1, N2] slab array from the
-        neighbouring ranks' boundary planes: two masked peer puts (my lower planes -> previous
-        rank's upper halo, my upper planes -> next rank's lower halo) + two small copies"""
+    def _halo_fill(self, padded, width=2):
+        """fill the ``width`` halo planes on each side of a [n0l + 2 width, N1, N2] slab array from
+        the neighbouring ranks' boundary planes: ONE peer put (my lower planes -> previous rank's
+        upper halo, my upper planes -> next rank's lower halo) + one copy kernel"""
         rt = self.rt
         px = self._peer()
         n0l, N1, N2 = self.rshape
-        cnt = N1 * N2                       # two planes of doubles = N1 * N2 complex elements
+        cnt = width * N1 * N2 // 2          # `width` planes of doubles, in complex elements
         plane = N1 * N2 * 8
         prev, nxt = (self.rank - 1) % self.P, (self.rank + 1) % self.P
         base = padded.data_ptr()
         px.ensure(32 * cnt)
-        e, b = px.begin()
-        px.put_to(b, base + 2 * plane, cnt, 1 << prev, cnt, True, False)            # -> prev's HI slot
-        px.put_to(b, base + n0l * plane, cnt, 1 << nxt, 0, False, True)             # -> next's LO slot
+        _, b = px.begin()
+        # interior = planes [width, width + n0l): its first `width` planes go to the previous rank's
+        # HI slot, its last `width` planes to the next rank's LO slot -- one launch
+        px.put_blocks(b, base, cnt, [(prev, cnt, cnt), (nxt, n0l * N1 * N2 // 2, 0)])
         rt.sync_stream()
         lo = ctypes.c_void_p(base)
-        hi = ctypes.c_void_p(base + (n0l + 2) * plane)
-        C.check(C.lib.vpm_axpby(rt.ctx, 2 * cnt, 1.0, px.recv_ptr(b, 0), 0.0, None, 0.0, lo))
-        C.check(C.lib.vpm_axpby(rt.ctx, 2 * cnt, 1.0, px.recv_ptr(b, cnt), 0.0, None, 0.0, hi))
+        hi = ctypes.c_void_p(base + (n0l + width) * plane)
+        C.check(C.lib.vpm_copy2(rt.ctx, cnt, px.recv_ptr(b, 0), lo, px.recv_ptr(b, cnt), hi))
 
     # -- k-space (fastpm.py:79,83,87) ---------------------------------------------------------------
     def _transfer(self, cplx, scale=1.0, laplace=False, tables=(None, None, None), conj=False):
@@ -2135,7 +2167,7 @@ def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None, update=None):
         C.check(C.lib.vpm_take_rows_scaled(rt.ctx, _ptr(_f.t), _ptr(lay.indices), n, 3, float(f_scale), _ptr(t)))
         _fl = DeviceArray(t, cellindex=lay)
     else:
-        _fl = lay.exchange(asdevice(_f) * float(f_scale))
+        _fl = lay.exchange(asdevice(_f), scale=f_scale)
     # readout.vjp (mesh half) x3: three paints of the columns of the force cotangent
     halo = st.phi is not None and pm.P > 1
     Fbar = pm.paint_cols3(xl, _fl, pad=2 if halo else 0)
@@ -2198,9 +2230,7 @@ def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None, update=None):
     C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
                                     _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
                                     None, None, _ptr(g), None, 0.0, None))
-    out = lay.gather(DeviceArray(g))
-    if base is not None:
-        out = out + asdevice(base)
+    out = lay.gather(DeviceArray(g), init=base)
     if update is None:
         return out
     return out, (y._axpby(1.0, float(fac), out.t) if y is not None else out * float(fac))
@@ -2265,16 +2295,49 @@ def _lpt2_bilinear(pm, F, G, scale):
     rt = pm.rt
     rt.sync_stream()
     out = rt.empty(pm.rshape)
+    if pm.P > 1:        # F, G: tensors with two halo planes per side (_lpt2_gradients_slab)
+        g = [None, None, None] if G is None else [_ptr(t) for t in G]
+        C.check(C.lib.vpm_lpt2_source_slab(rt.ctx, C.i3(pm.rshape), _h3(pm), 2, _ptr(F[0]), _ptr(F[1]), _ptr(F[2]),
+                                           g[0], g[1], g[2], float(scale), _ptr(out)))
+        return RealField(pm, out)
     g = [None, None, None] if G is None else [_ptr(t.t) for t in G]
     C.check(C.lib.vpm_lpt2_source(rt.ctx, C.i3(pm._n3), _h3(pm), _ptr(F[0].t), _ptr(F[1].t), _ptr(F[2].t),
                                   g[0], g[1], g[2], float(scale), _ptr(out)))
     return RealField(pm, out)
 
 
+def _lpt2_potential_slab(pm, rhok):
+    """several ranks: the potential with FOUR halo planes per side (the source is two stencils
+    deep), as a [n0l + 8, N1, N2] tensor: one inverse FFT + one halo exchange"""
+    rt = pm.rt
+    n0l, N1, N2 = pm.rshape
+    phi4 = rt.empty((n0l + 8, N1, N2))
+    rt.sync_stream()
+    pm._c2r_slab(pm._transfer(pm._as_field(rhok, True), scale=1.0, laplace=True), 1.0, consume=True,
+                 out=phi4[4:4 + n0l])
+    pm._halo_fill(phi4, width=4)
+    return phi4
+
+
+def _lpt2_gradients_slab(pm, phi4):
+    """F_j = -D_j phi on the local planes AND two planes beyond on each side: three
+    [n0l + 4, N1, N2] tensors = the gradient meshes with their own halo planes (no exchange)"""
+    rt = pm.rt
+    n0l, N1, N2 = pm.rshape
+    rt.sync_stream()
+    F = [rt.empty((n0l + 4, N1, N2)) for _ in range(3)]
+    C.check(C.lib.vpm_fd4_neg_gradient_slab(rt.ctx, C.i3((n0l + 4, N1, N2)), _h3(pm), 2, _ptr(phi4), _ptr(F[0]),
+                                            _ptr(F[1]), _ptr(F[2])))
+    return F
+
+
 def lpt2src_apl(pm, rhok):
     """source of the second-order displacement (fastpm.py:353-387) from ONE inverse FFT: the six
     second derivatives are stencils of the gradient meshes (csrc/stencil.cu).  Returns
     ``(source, state)``; only the potential stays on the tape."""
+    if pm.P > 1:
+        phi4 = _lpt2_potential_slab(pm, rhok)
+        return _lpt2_bilinear(pm, _lpt2_gradients_slab(pm, phi4), None, 0.5), phi4
     phi, F = _lpt2_potential(pm, rhok)
     return _lpt2_bilinear(pm, F, None, 0.5), phi
 
@@ -2282,6 +2345,25 @@ def lpt2src_apl(pm, rhok):
 def lpt2src_vjp(pm, phi, _src):
     rt = pm.rt
     sbar = pm._as_field(_src, False)
+    if pm.P > 1:
+        n0l, N1, N2 = pm.rshape
+        F = _lpt2_gradients_slab(pm, phi)
+        rt.sync_stream()
+        W = rt.empty((6, n0l + 4, N1, N2))
+        C.check(C.lib.vpm_lpt2_adjoint_w_slab(rt.ctx, C.i3(pm.rshape), _h3(pm), 2, _ptr(F[0]), _ptr(F[1]),
+                                              _ptr(F[2]), _ptr(sbar.t), _ptr(W)))
+        del F
+        # the second half differentiates W_00 and W_01 along axis 0: their boundary planes travel
+        pm._halo_fill(W[0])
+        pm._halo_fill(W[5])
+        rt.sync_stream()
+        Fb = rt.empty((3, n0l + 4, N1, N2))
+        C.check(C.lib.vpm_lpt2_adjoint_f_slab(rt.ctx, C.i3(pm.rshape), _h3(pm), 2, _ptr(W), _ptr(Fb[0]), _ptr(Fb[1]),
+                                              _ptr(Fb[2])))
+        del W
+        phibar = _fd4_adjoint(pm, Fb)
+        del Fb
+        return pm._transfer(pm._r2c(phibar, 1.0), scale=1.0, laplace=True)
     F = _fd4(pm, phi)
     rt.sync_stream()
     work = rt.empty((6,) + tuple(pm.rshape))
@@ -2300,6 +2382,9 @@ def lpt2src_vjp(pm, phi, _src):
 def lpt2src_jvp(pm, phi, rhok_):
     if _is_zero_literal(rhok_):
         return 0
+    if pm.P > 1:
+        F_ = _lpt2_gradients_slab(pm, _lpt2_potential_slab(pm, rhok_))
+        return _lpt2_bilinear(pm, _lpt2_gradients_slab(pm, phi), F_, 1.0)
     _, F_ = _lpt2_potential(pm, rhok_)
     return _lpt2_bilinear(pm, _fd4(pm, phi), F_, 1.0)
 
