@@ -97,8 +97,9 @@ __global__ void k_scan_reduce(const int* __restrict__ in, long long n, int* __re
     if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
+// close != 0: also write the grand total to out[n] (the cell offsets array has n + 1 entries)
 __global__ void k_scan_down(const int* __restrict__ in, long long n,
-                            const int* __restrict__ block_offsets, int* __restrict__ out) {
+                            const int* __restrict__ block_offsets, int* __restrict__ out, int close = 0) {
     long long base = blockIdx.x * (long long)SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int s = 0;
@@ -115,62 +116,7 @@ __global__ void k_scan_down(const int* __restrict__ in, long long n,
         if (base + j < n) out[base + j] = off;
         off += v[j];
     }
-}
-
-// ---- single-pass exclusive scan (decoupled look-back) ---------------------------------------
-// One launch for the histogram -> cell offsets step of the cell sort.  Tiles are claimed in order
-// through an atomic ticket, so every tile a block waits for has already started (no deadlock
-// whatever the block scheduling); a tile publishes its aggregate, looks back over its
-// predecessors' (aggregate | inclusive prefix) words until it meets a prefix, publishes its own
-// inclusive prefix and writes its part.  status: one 64-bit word per tile, [63:62] = 0 empty,
-// 1 aggregate, 2 prefix; [31:0] the value.  status and the ticket must be zero on entry.
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_chained(const int* __restrict__ in, long long n, int* __restrict__ out /* n + 1 */,
-               unsigned long long* __restrict__ status, unsigned* __restrict__ ticket) {
-    __shared__ unsigned s_tile;
-    __shared__ int s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned tile = s_tile;
-    const long long base = tile * (long long)SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    int v[SCAN_ITEMS];
-    int sum = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        v[j] = (base + j < n) ? in[base + j] : 0;
-        sum += v[j];
-    }
-    int total;
-    const int ex = block_exclusive_scan(sum, total);
-    if (threadIdx.x == 0) {
-        volatile unsigned long long* st = status;
-        int prefix = 0;
-        if (tile == 0) {
-            st[0] = (2ull << 62) | (unsigned)total;
-        } else {
-            st[tile] = (1ull << 62) | (unsigned)total;
-            long long t = (long long)tile - 1;
-            while (true) {
-                unsigned long long w;
-                do { w = st[t]; } while ((w >> 62) == 0);
-                prefix += (int)(unsigned)(w & 0xffffffffull);
-                if ((w >> 62) == 2) break;
-                --t;
-            }
-            __threadfence();
-            st[tile] = (2ull << 62) | (unsigned)(prefix + total);
-        }
-        s_prefix = prefix;
-    }
-    __syncthreads();
-    int off = s_prefix + ex;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        if (base + j < n) out[base + j] = off;
-        off += v[j];
-    }
-    // the grand total closes the offsets array
-    if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = off;
+    if (close && base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = off;
 }
 
 // exclusive scan of in[0..n) into out[0..n); tmp must hold scan_tmp_ints(n) ints
@@ -183,17 +129,17 @@ static long long scan_tmp_ints(long long n) {
     return t + 1;
 }
 
-static void exclusive_scan(cudaStream_t st, const int* in, long long n, int* out, int* tmp) {
+static void exclusive_scan(cudaStream_t st, const int* in, long long n, int* out, int* tmp, int close = 0) {
     if (n <= 0) return;
     long long nb = ceil_div(n, SCAN_TILE);
     if (nb == 1) {
-        VPM_LAUNCH(k_scan_down, 1, SCAN_THREADS, 0, st, in, n, (const int*)nullptr, out);
+        VPM_LAUNCH(k_scan_down, 1, SCAN_THREADS, 0, st, in, n, (const int*)nullptr, out, close);
         return;
     }
     int* sums = tmp;
     VPM_LAUNCH(k_scan_reduce, (unsigned)nb, SCAN_THREADS, 0, st, in, n, sums);
     exclusive_scan(st, sums, nb, sums, tmp + nb);  // in-place on the block sums
-    VPM_LAUNCH(k_scan_down, (unsigned)nb, SCAN_THREADS, 0, st, in, n, (const int*)sums, out);
+    VPM_LAUNCH(k_scan_down, (unsigned)nb, SCAN_THREADS, 0, st, in, n, (const int*)sums, out, close);
 }
 
 __global__ void k_scatter_ids(const int* __restrict__ keys, const int* __restrict__ rank,
@@ -226,27 +172,24 @@ __global__ void k_fix_small(const int* __restrict__ cell_start, long long ncell,
         lists[which * ncell + slot] = (int)c;
         return;
     }
-    int v[FIX_SMALL];
+    // already ascending?  (contiguous entries: the loads of neighbouring threads share sectors)
+    int prev = perm[b];
     bool sorted = true;
-#pragma unroll
-    for (int i = 0; i < FIX_SMALL; ++i) v[i] = i < cnt ? perm[b + i] : 0x7fffffff;
-#pragma unroll
-    for (int i = 1; i < FIX_SMALL; ++i) sorted = sorted && (v[i - 1] <= v[i]);
-    if (sorted) return;
-    // odd-even transposition network on the padded array (padding = +inf stays at the end)
-#pragma unroll
-    for (int round = 0; round < FIX_SMALL; ++round) {
-#pragma unroll
-        for (int i = round & 1; i + 1 < FIX_SMALL; i += 2) {
-            const int lo = min(v[i], v[i + 1]), hi = max(v[i], v[i + 1]);
-            v[i] = lo;
-            v[i + 1] = hi;
-        }
-        if (round + 1 >= cnt) break;      // cnt rounds sort cnt elements
+    for (int i = b + 1; i < e; ++i) {
+        const int v = perm[i];
+        sorted = sorted && (prev <= v);
+        prev = v;
     }
-#pragma unroll
-    for (int i = 0; i < FIX_SMALL; ++i)
-        if (i < cnt) perm[b + i] = v[i];
+    if (sorted) return;
+    for (int i = b + 1; i < e; ++i) {  // insertion sort, segments are tiny
+        int v = perm[i];
+        int j = i - 1;
+        while (j >= b && perm[j] > v) {
+            perm[j + 1] = perm[j];
+            --j;
+        }
+        perm[j + 1] = v;
+    }
 }
 
 // medium cells: one warp per cell.  The ids are distinct, so the final slot of an id is the
@@ -333,7 +276,6 @@ __global__ void k_copy_big(const int* __restrict__ cell_start, const int* __rest
     }
 }
 
-__global__ void k_set_last(int* cell_start, long long ncell, int np) { cell_start[ncell] = np; }
 
 // ---- row permutes -------------------------------------------------------------------
 // an index equal to VPM_ROW_PADDING marks a slot without a particle (fixed-capacity routing):
@@ -668,29 +610,23 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
     long long ncell = vpm_layout_ncell(mesh);
     VPM_REQUIRE(cell_start, "cell_start is NULL");
     cudaStream_t st = ctx->stream;
-    // workspace: scan status[ntiles] (64-bit) | ticket, counts[4] | count[ncell] -- zeroed by ONE memset --
-    //            | rank[np] | lists[2][ncell] | perm2[np]
-    const long long ntiles = ceil_div(ncell, SCAN_TILE);
-    size_t ints = 2 * (size_t)ntiles + 8 + (size_t)ncell + (size_t)np + 2 * (size_t)ncell + (size_t)np;
+    // workspace: counts[8] | count[ncell] -- zeroed by ONE memset -- | rank[np] | scan tmp | lists[2][ncell] | perm2[np]
+    long long ntmp = scan_tmp_ints(ncell);
+    size_t ints = 8 + (size_t)ncell + (size_t)np + (size_t)ntmp + 2 * (size_t)ncell + (size_t)np;
     int* ws = (int*)ctx->workspace(ints * sizeof(int));
-    unsigned long long* scan_status = reinterpret_cast<unsigned long long*>(ws);
-    int* misc = ws + 2 * ntiles;
-    unsigned* scan_ticket = reinterpret_cast<unsigned*>(misc);
-    int* big_count = misc + 2;
-    int* count = misc + 8;
+    int* big_count = ws;
+    int* count = ws + 8;
     int* rank = count + ncell;
-    int* big_list = rank + np;           // [0]: medium cells, [1]: huge cells
+    int* tmp = rank + np;
+    int* big_list = tmp + ntmp;          // [0]: medium cells, [1]: huge cells
     int* perm2 = big_list + 2 * ncell;
-    VPM_PROF_CALL("memset(cell counts)", st,
-                  VPM_CUDA(cudaMemsetAsync(ws, 0, (size_t)(2 * ntiles + 8 + ncell) * sizeof(int), st)));
+    VPM_PROF_CALL("memset(cell counts)", st, VPM_CUDA(cudaMemsetAsync(ws, 0, (size_t)(8 + ncell) * sizeof(int), st)));
     if (np > 0) {
         VPM_REQUIRE(x && keys && perm, "NULL array");
         VPM_LAUNCH(k_keys_count, (unsigned)ceil_div(np, 256), 256, 0, st, g, x, (long long)np, keys,
                    rank, count);
     }
-    // histogram -> cell offsets in ONE launch (decoupled look-back; closes cell_start[ncell] = np)
-    VPM_LAUNCH(k_scan_chained, (unsigned)ceil_div(ncell, SCAN_TILE), SCAN_THREADS, 0, st, count, ncell, cell_start,
-               scan_status, scan_ticket);
+    exclusive_scan(st, count, ncell, cell_start, tmp, /*close: cell_start[ncell] = np*/ 1);
     if (np > 0) {
         VPM_LAUNCH(k_scatter_ids, (unsigned)ceil_div(np, 256), 256, 0, st, keys, rank, cell_start,
                    (long long)np, perm);
