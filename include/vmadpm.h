@@ -219,6 +219,11 @@ int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, cons
                       const double* f2, const double* r, const double* x, const double* w3,
                       int64_t np, const int32_t* out_row, const double* base, double* grad,
                       const double* y_in, double fac, double* y_out);
+/* Implementation variant of vpm_readout3 / vpm_readout_grad4 (same results bit for bit): bits
+ * 1 positions staged per CTA by a bulk asynchronous copy, 2 scattered rows requested before the
+ * mesh, 4 scattered rows as 16 + 8 byte accesses, 8 / 16 pair-load mode (csrc/readout.cu).  Used by
+ * the ablation in benchmarks/readout_variants.py; the default is the measured best. */
+int vpm_readout_set_variant(int variant);
 /* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);
  * either term may be absent (NULL). */
 int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,

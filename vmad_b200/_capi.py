@@ -85,6 +85,7 @@ SIGNATURES = {
     'vpm_paint_sorted_cols3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int, c_int64, _P, _P, c_int64]),
     'vpm_paint_sorted_col': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int, c_int, c_int64, _P, _P]),
     'vpm_paint_set_algorithm': (c_int, [c_int]),
+    'vpm_readout_set_variant': (c_int, [c_int]),
     'vpm_paint_set_tile': (c_int, [c_int, c_int, c_int]),
     'vpm_paint_sorted_rows': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P, _P]),
     'vpm_paint_jvp_sorted': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, _P, _P,

@@ -31,6 +31,7 @@ inline Geo make_geo(const vpm_mesh* m) {
     g.nsp = m->ghost ? g.nloc0 + 1 : g.n0;
     VPM_REQUIRE(g.stride1 >= g.n2 && g.stride0 >= g.stride1 * (long long)g.n1, "bad strides");
     VPM_REQUIRE((long long)g.nsp * g.n1 * g.n2 + 1 < (1LL << 31), "too many cells for int32 keys");
+    VPM_REQUIRE((long long)g.nloc0 * g.stride0 < (1LL << 31), "local mesh slab must have < 2^31 elements");
     return g;
 }
 
@@ -53,6 +54,35 @@ __device__ __forceinline__ void cell_axis(double x, double scale, int n, int& i,
         if (ll < 0) ll += n;
         i = (int)ll;
     }
+}
+
+// Periodic wrap of floor(u) given as a double.  The common case (inside the box or within one
+// box length outside) costs a compare, the general case is the exact 64-bit modulo of cell_axis,
+// so the two always agree.
+__device__ __forceinline__ int wrap_cell(double fl, int n) {
+    int i = __double2int_rn(fl);  // exact for |fl| < 2^31, saturates beyond
+    if ((unsigned)i >= (unsigned)n) {
+        if (i < 0 && i >= -n) {
+            i += n;
+        } else if (i >= n && i < 2 * n) {
+            i -= n;
+        } else {
+            long long ll = (fabs(fl) < 9.0e18) ? (long long)fl : 0LL;
+            ll %= (long long)n;
+            if (ll < 0) ll += n;
+            i = (int)ll;
+        }
+    }
+    return i;
+}
+
+// wrapped cell index, branch-free in the common case (inside the box or one box length out)
+__device__ __forceinline__ int wrap_fast(double fl, int n) {
+    int i = __double2int_rn(fl);  // exact for |fl| < 2^31, saturates beyond
+    i += (i < 0) ? n : 0;
+    i -= (i >= n) ? n : 0;
+    if (__builtin_expect((unsigned)i >= (unsigned)n, 0)) i = wrap_cell(fl, n);
+    return i;
 }
 
 __device__ __forceinline__ int wrap_inc(int i, int n) { return (i + 1 == n) ? 0 : i + 1; }

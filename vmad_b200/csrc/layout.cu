@@ -11,6 +11,7 @@
 // pairs of a radix sort, and FastPM particles arrive almost cell-sorted so the atomics
 // of (1) hit L2 lines that are already resident.
 #include "cic.cuh"
+#include "tile.cuh"
 
 namespace vpm {
 
@@ -298,6 +299,35 @@ __global__ void k_take_rows(const double* __restrict__ src, const int* __restric
         return;
     }
     dst[e] = scale * __ldg(src + (long long)p * nc + c);   // scale = 1 is exact
+}
+
+// [n, 3] rows, one thread per row: the scattered source row is fetched with one 16-byte and one
+// 8-byte access (tile.cuh), the destination tile of the CTA -- contiguous -- leaves as ONE bulk copy.
+// TWO = 1: rows come from two arrays (k_take_rows2 semantics).
+constexpr int TAKE_TILE = 256;
+template <int TWO>
+__global__ void __launch_bounds__(TAKE_TILE)
+k_take_rows3(const double* __restrict__ a, const double* __restrict__ b, const int* __restrict__ perm,
+             long long n, double scale, Fill3 fill, double* __restrict__ dst) {
+    __shared__ RowTile<TAKE_TILE, 1> tile;
+    const long long p0 = blockIdx.x * (long long)TAKE_TILE;
+    const long long i = p0 + threadIdx.x;
+    const bool live = i < n;
+    double v0 = fill.v[0], v1 = fill.v[1], v2 = fill.v[2];
+    if (live) {
+        const int p = __ldg(perm + i);
+        if (p != VPM_ROW_PADDING) {
+            if (TWO && p < 0) load_row3(b, (long long)(-1 - p), v0, v1, v2);
+            else load_row3(a, (long long)p, v0, v1, v2);
+            v0 *= scale; v1 *= scale; v2 *= scale;      // scale = 1 is exact
+        }
+    }
+    if (tile.can_flush(dst, p0, n)) {
+        tile.put(0, threadIdx.x, v0, v1, v2);
+        tile.flush(0, dst, p0);
+    } else if (live) {
+        dst[3 * i + 0] = v0; dst[3 * i + 1] = v1; dst[3 * i + 2] = v2;
+    }
 }
 
 // slots of the sorted order at or beyond the number of rows that really arrived hold padding
@@ -655,7 +685,7 @@ static void launch_take_rows(vpm_ctx* ctx, const double* src, const int32_t* per
         Fill3 fill;
         for (int c = 0; c < 3; ++c) fill.v[c] = ctx->fill_row[c];
         if (ncomp == 1) VPM_LAUNCH(k_take_rows<1>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, fill, dst);
-        else if (ncomp == 3) VPM_LAUNCH(k_take_rows<3>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, fill, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows3<0>, (unsigned)ceil_div(n, TAKE_TILE), TAKE_TILE, 0, ctx->stream, src, (const double*)nullptr, perm, (long long)n, scale, fill, dst);
         else VPM_LAUNCH(k_take_rows<0>, grid, 256, 0, ctx->stream, src, perm, (long long)n, ncomp, scale, fill, dst);
     }
 }
@@ -709,7 +739,7 @@ int vpm_take_rows2_scaled(vpm_ctx* ctx, const double* a, const double* b, const 
         Fill3 fill;
         for (int c = 0; c < 3; ++c) fill.v[c] = ctx->fill_row[c];
         if (ncomp == 1) VPM_LAUNCH(k_take_rows2<1>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, scale, fill, dst);
-        else if (ncomp == 3) VPM_LAUNCH(k_take_rows2<3>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, scale, fill, dst);
+        else if (ncomp == 3) VPM_LAUNCH(k_take_rows3<1>, (unsigned)ceil_div(n, TAKE_TILE), TAKE_TILE, 0, ctx->stream, a, b, idx, (long long)n, scale, fill, dst);
         else VPM_LAUNCH(k_take_rows2<0>, grid, 256, 0, ctx->stream, a, b, idx, (long long)n, ncomp, scale, fill, dst);
     }
     VPM_API_END

@@ -154,22 +154,7 @@ struct TileDims {
 // wrapped cell index along the contiguous axis; the common case (particle inside the box or
 // one box length outside) costs a compare, the general case is the exact 64-bit modulo that
 // the key kernel uses, so the two always agree.
-__device__ __forceinline__ int wrap_cell(double fl, int n) {
-    int i = __double2int_rn(fl);  // exact for |fl| < 2^31, saturates beyond
-    if ((unsigned)i >= (unsigned)n) {
-        if (i < 0 && i >= -n) {
-            i += n;
-        } else if (i >= n && i < 2 * n) {
-            i -= n;
-        } else {
-            long long ll = (fabs(fl) < 9.0e18) ? (long long)fl : 0LL;
-            ll %= (long long)n;
-            if (ll < 0) ll += n;
-            i = (int)ll;
-        }
-    }
-    return i;
-}
+// (wrap_cell / wrap_fast live in cic.cuh)
 
 // MASSKIND 0: mass == 1 (no multiply); 1: scalar mass0; 2: per-particle array
 template <int MODE, int MASSKIND, bool HAS_VMASS>
@@ -361,14 +346,6 @@ k_paint_tile(Geo g, TileDims td, const double* __restrict__ xs, const double* __
 // price is a zero fill of the mesh beforehand and a summation order that depends on the order
 // in which L2 receives the reductions (results agree to rounding, not bit for bit).
 // -------------------------------------------------------------------------------------------
-// wrapped cell index, branch-free in the common case (inside the box or one box length out)
-__device__ __forceinline__ int wrap_fast(double fl, int n) {
-    int i = __double2int_rn(fl);  // exact for |fl| < 2^31, saturates beyond
-    i += (i < 0) ? n : 0;
-    i -= (i >= n) ? n : 0;
-    if (__builtin_expect((unsigned)i >= (unsigned)n, 0)) i = wrap_cell(fl, n);
-    return i;
-}
 
 // V += tv on the lanes where pred != 0 (one predicated DADD, no select)
 #define VPM_ADD_IF(V, TV, PRED)                                                      \

@@ -88,10 +88,71 @@ struct RowTile {
         if (staged) mbar_wait(&bar, 0);
     }
 
-    // row p (global index) of array a: from the staged tile, else straight from global memory
-    __device__ __forceinline__ const double* row(int a, const double* global, long long p0, long long p) const {
-        return staged ? buf[a] + 3 * (p - p0) : global + 3 * p;
+    // row p (global index) of array a: from the staged tile (LDS), else straight from global memory
+    __device__ __forceinline__ void get(int a, const double* __restrict__ global, long long p0, long long p,
+                                        double& v0, double& v1, double& v2) const {
+        if (staged) {
+            const double* r = buf[a] + 3 * (int)(p - p0);
+            v0 = r[0]; v1 = r[1]; v2 = r[2];
+        } else {
+            const double* r = global + 3 * p;
+            v0 = __ldg(r); v1 = __ldg(r + 1); v2 = __ldg(r + 2);
+        }
+    }
+
+    // ---- the way back: rows written by their threads into buf[a], stored as ONE bulk copy -------
+    // put(): every thread with a row writes it (threads without a row do nothing);
+    // flush(): called by every thread of the CTA once, after all put()s of the arrays flushed.
+    // The tile must be whole and the destination 16-byte aligned (`can_flush`), else the caller
+    // stores its row itself.
+    __device__ __forceinline__ static bool can_flush(const double* dst, long long p0, long long np) {
+        return p0 + T <= np && (reinterpret_cast<uintptr_t>(dst + 3 * p0) & 15) == 0;
+    }
+    __device__ __forceinline__ void put(int a, int r, double v0, double v1, double v2) {
+        double* q = buf[a] + 3 * r;
+        q[0] = v0; q[1] = v1; q[2] = v2;
+    }
+    __device__ __forceinline__ void flush(int a, double* dst, long long p0) {
+        // generic-proxy writes to shared memory -> visible to the async proxy, then one thread issues
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + 3 * p0),
+                         "r"(smem_u32(buf[a])), "r"(3 * T * (uint32_t)sizeof(double))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the source may be released (CTA exit / re-use) once it has been read
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
     }
 };
+
+// ---- scattered rows of an [n, 3] array (home order reached through a permutation) -----------
+// A 24-byte row is 16-byte aligned at either its first or its second element: one 16-byte and
+// one 8-byte access instead of three 8-byte ones (a third fewer L1/L2 transactions; for stores,
+// which L1 does not merge, a third fewer partial-sector writes).
+__device__ __forceinline__ void load_row3(const double* __restrict__ base, long long o, double& a, double& b,
+                                          double& c) {
+    const double* r = base + 3 * o;
+    if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(r));
+        a = t.x; b = t.y; c = __ldg(r + 2);
+    } else {
+        a = __ldg(r);
+        const double2 t = __ldg(reinterpret_cast<const double2*>(r + 1));
+        b = t.x; c = t.y;
+    }
+}
+
+__device__ __forceinline__ void store_row3(double* __restrict__ base, long long o, double a, double b, double c) {
+    double* r = base + 3 * o;
+    if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+        *reinterpret_cast<double2*>(r) = make_double2(a, b);
+        r[2] = c;
+    } else {
+        r[0] = a;
+        *reinterpret_cast<double2*>(r + 1) = make_double2(b, c);
+    }
+}
 
 }  // namespace vpm
