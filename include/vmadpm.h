@@ -53,6 +53,11 @@ typedef struct vpm_mesh {
 int vpm_ctx_create(vpm_ctx** out, int device, void* stream);
 int vpm_ctx_destroy(vpm_ctx* ctx);
 int vpm_ctx_set_stream(vpm_ctx* ctx, void* stream);
+/* Launch the following calls on `stream` without draining the current stream or re-binding the FFT
+ * plans -- only for entry points that use neither cuFFT nor the context workspace (the peer puts
+ * of the pipelined slab transform); the caller orders the streams with events.  pop restores. */
+int vpm_ctx_push_stream(vpm_ctx* ctx, void* stream);
+int vpm_ctx_pop_stream(vpm_ctx* ctx);
 int vpm_sync(vpm_ctx* ctx);
 const char* vpm_last_error(void);
 int vpm_version(void);
@@ -204,6 +209,15 @@ int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const d
 int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
                  const double* f2, const double* x, int64_t np, const int32_t* out_row,
                  double* value3, const double* y_in, double fac, double* y_out);
+/* The same readout under a layout that spans several ranks (Layout.gather, fastpm.py:286-304, split
+ * into a local store and a cross-rank sum): value3_slots[p] = value where home_row[p] < 0 (slot
+ * order: the rows whose home is on another rank travel from there; other slots are not written)
+ * and, where home_row[p] >= 0 (the particle's home row
+ * is on this rank; negative = elsewhere or an empty slot), acc_out[home_row[p]] =
+ * acc_in[home_row[p]] (0 when acc_in is NULL) + scale * value. */
+int vpm_readout3_home(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                      const double* f2, const double* x, int64_t np, const int32_t* home_row,
+                      double* value3_slots, const double* acc_in, double scale, double* acc_out);
 /* value[p] (optional, may be NULL) and grad[p, d] = w_p * sum_c field[c] dW/dx_d,
  * w_p = weight[p] or weight0 when weight == NULL. */
 int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,
@@ -219,6 +233,13 @@ int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, cons
                       const double* f2, const double* r, const double* x, const double* w3,
                       int64_t np, const int32_t* out_row, const double* base, double* grad,
                       const double* y_in, double fac, double* y_out);
+/* vpm_readout_grad4 under a layout that spans several ranks: grad_slots[p] = the gradient (slot
+ * order, no base; only where home_row[p] < 0) and acc_out[home_row[p]] = acc_in[home_row[p]] (0 when NULL) + gradient where
+ * home_row[p] >= 0; see vpm_readout3_home. */
+int vpm_readout_grad4_home(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                           const double* f2, const double* r, const double* x, const double* w3,
+                           int64_t np, const int32_t* home_row, double* grad_slots,
+                           const double* acc_in, double* acc_out);
 /* Implementation variant of vpm_readout3 / vpm_readout_grad4 (same results bit for bit): bits
  * 1 positions staged per CTA by a bulk asynchronous copy, 2 scattered rows requested before the
  * mesh, 4 scattered rows as 16 + 8 byte accesses, 8 / 16 pair-load mode (csrc/readout.cu).  Used by
@@ -306,6 +327,12 @@ typedef struct vpm_peer_sync {
 int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
                  int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
                  const vpm_peer_sync* sync);
+/* the same with a destination row stride: peer_bufs[d][dst_off + i * d_row + c] = src[i * s_row +
+ * d * s_dst + c] -- the transpose of the inverse slab FFT lands in [planes, N1, N2/2+1] order in the
+ * receive area, so the batched 2-D Z2D reads it in place (no unpack pass). */
+int vpm_peer_put_strided(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
+                         int64_t s_dst, int64_t d_row, const double* src, const uint64_t* peer_bufs,
+                         int64_t dst_off, const vpm_peer_sync* sync);
 /* `count` contiguous complex128 elements (= 2 count doubles) to every rank whose bit is set in
  * dest_mask, stored at element dst_off of its receive area (halo planes for the real-space
  * stencils: the two boundary planes of a slab go to the neighbouring rank only); sync as above. */

@@ -470,3 +470,63 @@ def test_route_build_static_bit_exact(oracle_pm, device_pm, P, npart):
             s = got[seg[d]:seg[d + 1]]
             assert numpy.array_equal(s[:len(w)], w)
             assert (s[len(w):] == -1).all()
+
+
+@pytest.mark.parametrize("shape,pad", [((16, 12, 32), 0), ((8, 20, 36), 0), ((6, 8, 8), 2), ((5, 7, 10), 0),
+                                       ((64, 64, 64), 0), ((9, 16, 520), 2)])
+def test_fd4_stencil_and_adjoint(device_pm, shape, pad):
+    """4-point finite-difference gradient F_d = -D_d phi (the real-space form of
+    fastpm.py:316-323, order 1) and its adjoint against numpy rolls; the four-cells-per-thread
+    kernels (n2 % 4 == 0, aligned arrays) must agree bit for bit with the scalar ones"""
+    import ctypes
+    import torch
+    from vmad_b200 import _capi as C
+    from vmad_b200.pm import runtime, _ptr
+    rt = runtime()
+    rng = numpy.random.default_rng(11)
+    n0, n1, n2 = shape
+    h = numpy.array([0.7, 1.3, 0.9])
+    phi = rng.standard_normal((n0 + 2 * pad, n1, n2))
+    Fb = rng.standard_normal((3, n0 + 2 * pad, n1, n2))
+
+    def D(f, axis):
+        # periodic along axes 1, 2; along axis 0 periodic when pad == 0, else the halo planes are given
+        r = lambda k: numpy.roll(f, -k, axis=axis)
+        d = (8.0 * (r(1) - r(-1)) - (r(2) - r(-2))) * (1.0 / (12.0 * h[axis]))
+        return d[pad:pad + n0] if pad else d
+
+    want = [-D(phi, d) for d in range(3)]
+    want_adj = D(Fb[2], 2) + D(Fb[1], 1) + D(Fb[0], 0)
+    n3 = (ctypes.c_int64 * 3)(n0, n1, n2)
+    h3 = (ctypes.c_double * 3)(*h)
+
+    def run(misalign):
+        # one spare element in front: misalign = 1 shifts every array off 16-byte alignment -> scalar kernels
+        def dev(a):
+            t = torch.empty(a.size + 2, dtype=torch.float64, device=rt.device)
+            v = t[misalign:misalign + a.size].view(a.shape)
+            v.copy_(torch.from_numpy(numpy.ascontiguousarray(a)))
+            return t, v
+        keep = []
+        _, dphi = dev(phi); keep.append(_)
+        outs = []
+        for _ in range(3):
+            t, v = dev(numpy.zeros((n0, n1, n2))); keep.append(t); outs.append(v)
+        rt.sync_stream()
+        C.check(C.lib.vpm_fd4_neg_gradient_slab(rt.ctx, n3, h3, pad, _ptr(dphi), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])))
+        fb = []
+        for d in range(3):
+            t, v = dev(Fb[d]); keep.append(t); fb.append(v)
+        t, pb = dev(numpy.zeros((n0, n1, n2))); keep.append(t)
+        C.check(C.lib.vpm_fd4_neg_gradient_adjoint_slab(rt.ctx, n3, h3, pad, _ptr(fb[0]), _ptr(fb[1]), _ptr(fb[2]), _ptr(pb)))
+        rt.synchronize()
+        return [o.cpu().numpy() for o in outs], pb.cpu().numpy()
+
+    got, got_adj = run(0)
+    for d in range(3):
+        assert rel_l2(got[d], want[d]) < TOL
+    assert rel_l2(got_adj, want_adj) < TOL
+    got_s, got_adj_s = run(1)
+    for d in range(3):
+        assert numpy.array_equal(got[d], got_s[d])
+    assert numpy.array_equal(got_adj, got_adj_s)

@@ -57,6 +57,8 @@ SIGNATURES = {
     'vpm_ctx_create': (c_int, [POINTER(c_void_p), c_int, c_void_p]),
     'vpm_ctx_destroy': (c_int, [c_void_p]),
     'vpm_ctx_set_stream': (c_int, [c_void_p, c_void_p]),
+    'vpm_ctx_push_stream': (c_int, [c_void_p, c_void_p]),
+    'vpm_ctx_pop_stream': (c_int, [c_void_p]),
     'vpm_sync': (c_int, [c_void_p]),
     'vpm_last_error': (c_char_p, []),
     'vpm_version': (c_int, []),
@@ -93,9 +95,11 @@ SIGNATURES = {
     'vpm_paint_atomic': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_double, c_int64, _P]),
     'vpm_readout': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, c_int64, _P]),
     'vpm_readout3': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P, _P, _P, c_double, _P]),
+    'vpm_readout3_home': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P, _P, _P, c_double, _P]),
     'vpm_readout_grad': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, c_double, c_int64,
                                  _P, _P]),
     'vpm_readout_grad4': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_double, _P]),
+    'vpm_readout_grad4_home': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P]),
     'vpm_readout_jvp': (c_int, [c_void_p, POINTER(vpm_mesh), _P, _P, _P, _P, c_int64, _P]),
     'vpm_r2c': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
     'vpm_c2r': (c_int, [c_void_p, POINTER(c_int64), _P, _P, c_double]),
@@ -110,6 +114,8 @@ SIGNATURES = {
     'vpm_peer_free': (c_int, [c_void_p, c_void_p]),
     'vpm_peer_put': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, _P, POINTER(c_uint64), c_int64,
                              POINTER(vpm_peer_sync)]),
+    'vpm_peer_put_strided': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P, POINTER(c_uint64),
+                                     c_int64, POINTER(vpm_peer_sync)]),
     'vpm_peer_put_to': (c_int, [c_void_p, c_int, ctypes.c_uint32, c_int64, _P, POINTER(c_uint64), c_int64,
                                 POINTER(vpm_peer_sync)]),
     'vpm_peer_put_blocks': (c_int, [c_void_p, c_int, c_int, c_int64, _P, POINTER(c_int32), POINTER(c_int64),

@@ -93,6 +93,8 @@ inline double mesh_cells(const vpm_mesh* m) { return m ? (double)m->nloc0 * (dou
 struct vpm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pushed_from = nullptr;   // vpm_ctx_push_stream / _pop_stream
+    bool pushed = false;
     int sm_count = 148;
     // grow-only scratch arena for sort temporaries / FFT staging / reduction partials
     void* ws = nullptr;

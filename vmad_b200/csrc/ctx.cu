@@ -104,9 +104,33 @@ int vpm_ctx_destroy(vpm_ctx* ctx) {
     VPM_API_END
 }
 
+// Launch the next calls on `stream` WITHOUT draining the current one and without re-binding the
+// cuFFT plans: for kernels that use neither cuFFT nor the context workspace (the peer puts of a
+// pipelined slab transform run beside the 2-D FFTs this way); the caller orders the two streams
+// with events.  vpm_ctx_pop_stream restores the stream that was current before the push.
+int vpm_ctx_push_stream(vpm_ctx* ctx, void* stream) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx != nullptr, "ctx is NULL");
+    VPM_REQUIRE(ctx->pushed_from == nullptr && !ctx->pushed, "a stream is already pushed");
+    ctx->pushed_from = ctx->stream;
+    ctx->pushed = true;
+    ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+    VPM_API_END
+}
+
+int vpm_ctx_pop_stream(vpm_ctx* ctx) {
+    VPM_API_BEGIN
+    VPM_REQUIRE(ctx != nullptr && ctx->pushed, "no pushed stream");
+    ctx->stream = ctx->pushed_from;
+    ctx->pushed_from = nullptr;
+    ctx->pushed = false;
+    VPM_API_END
+}
+
 int vpm_ctx_set_stream(vpm_ctx* ctx, void* stream) {
     VPM_API_BEGIN
     VPM_REQUIRE(ctx != nullptr, "ctx is NULL");
+    VPM_REQUIRE(!ctx->pushed, "vpm_ctx_set_stream while a stream is pushed");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (s != ctx->stream) {
         VPM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -106,10 +106,10 @@ __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
     }
 }
 
-// dst_d[dst_off + i * inner + c] = src[i * s_row + d * s_dst + c]   for every peer d
+// dst_d[dst_off + i * d_row + c] = src[i * s_row + d * s_dst + c]   for every peer d
 // grid = (chunks of a row, rows, peers): no index divisions, 16-byte coalesced loads / stores
 __global__ void __launch_bounds__(256)
-k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_dst,
+k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_dst, long long d_row,
            const double2* __restrict__ src, PeerPtrs dst, long long dst_off, unsigned mask,
            PeerSync sy) {
     peer_acquire(P, sy);
@@ -119,7 +119,7 @@ k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_
     const long long nrows = ((mask >> d) & 1u) ? rows : 0;
     for (long long i = blockIdx.y; i < nrows; i += gridDim.y) {
         const double2* __restrict__ in = src + i * s_row + d * s_dst;
-        double2* __restrict__ o = out + i * inner;
+        double2* __restrict__ o = out + i * d_row;
         // four independent 16-B loads in flight per thread before the (posted) stores
         const long long stride = (long long)gridDim.x * blockDim.x;
         long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -303,24 +303,30 @@ int vpm_peer_free(vpm_ctx* ctx, void* ptr) {
 }
 
 static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
-                         int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
-                         unsigned mask, const vpm_peer_sync* sync);
+                         int64_t s_dst, int64_t d_row, const double* src, const uint64_t* peer_bufs,
+                         int64_t dst_off, unsigned mask, const vpm_peer_sync* sync);
 
 int vpm_peer_put(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
                  int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
                  const vpm_peer_sync* sync) {
-    return peer_put_impl(ctx, nranks, rows, inner, s_row, s_dst, src, peer_bufs, dst_off, 0xffffffffu, sync);
+    return peer_put_impl(ctx, nranks, rows, inner, s_row, s_dst, inner, src, peer_bufs, dst_off, 0xffffffffu, sync);
+}
+
+int vpm_peer_put_strided(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
+                         int64_t s_dst, int64_t d_row, const double* src, const uint64_t* peer_bufs,
+                         int64_t dst_off, const vpm_peer_sync* sync) {
+    return peer_put_impl(ctx, nranks, rows, inner, s_row, s_dst, d_row, src, peer_bufs, dst_off, 0xffffffffu, sync);
 }
 
 int vpm_peer_put_to(vpm_ctx* ctx, int nranks, uint32_t dest_mask, int64_t count, const double* src,
                     const uint64_t* peer_bufs, int64_t dst_off, const vpm_peer_sync* sync) {
     // `count` contiguous complex128 elements to every rank in dest_mask, at dst_off of its area
-    return peer_put_impl(ctx, nranks, 1, count, 0, 0, src, peer_bufs, dst_off, dest_mask, sync);
+    return peer_put_impl(ctx, nranks, 1, count, 0, 0, count, src, peer_bufs, dst_off, dest_mask, sync);
 }
 
 static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, int64_t s_row,
-                         int64_t s_dst, const double* src, const uint64_t* peer_bufs, int64_t dst_off,
-                         unsigned mask, const vpm_peer_sync* sync) {
+                         int64_t s_dst, int64_t d_row, const double* src, const uint64_t* peer_bufs,
+                         int64_t dst_off, unsigned mask, const vpm_peer_sync* sync) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("peer_put", 32.0 * rows * inner * nranks);
     VPM_REQUIRE(ctx && src && peer_bufs && nranks >= 1 && nranks <= 8, "bad argument");
@@ -332,7 +338,7 @@ static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, 
         const long long gx = std::max<long long>(1, std::min<long long>(ceil_div(inner, 256), want));
         dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nranks);
         VPM_LAUNCH(k_peer_put, grid, 256, 0, ctx->stream, nranks, (long long)rows, (long long)inner,
-                   (long long)s_row, (long long)s_dst, reinterpret_cast<const double2*>(src),
+                   (long long)s_row, (long long)s_dst, (long long)d_row, reinterpret_cast<const double2*>(src),
                    make_ptrs(nranks, peer_bufs), (long long)dst_off, mask, make_sync(nranks, sync));
     }
     VPM_API_END

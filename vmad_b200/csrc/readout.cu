@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(ROW_TILE, MB)
 k_readout3(Geo g, const double* __restrict__ fa, const double* __restrict__ fb,
            const double* __restrict__ fc, const double* __restrict__ x, long long np,
            const int* __restrict__ out_row, double* __restrict__ value3,
-           const double* __restrict__ y_in, double fac, double* __restrict__ y_out) {
+           const double* __restrict__ y_in, double fac, double* __restrict__ y_out, int dist) {
+    // dist != 0 (layout over several ranks): value3 is stored in SLOT order for the rows whose home is
+    // on another rank (they travel from there; the other slots are not written), y_out[o] = y_in[o] (0 when NULL) + fac * value only where
+    // the home row o = out_row[p] is on this rank (o >= 0)
     constexpr int PM = rv_pair_mode(V);
     __shared__ RowTile<(V & RV_TILE) ? ROW_TILE : 1, 1> tile;
     const long long p0 = blockIdx.x * (long long)ROW_TILE;
@@ -189,7 +192,7 @@ k_readout3(Geo g, const double* __restrict__ fa, const double* __restrict__ fb,
         tile.load(arrs, p0, np);
     }
     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-    if ((V & RV_EARLY) && y_out && live) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
+    if ((V & RV_EARLY) && y_out && y_in && live && o >= 0) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
     double a = 0.0, b = 0.0, c = 0.0;
     if (live) {
         double x0, x1, x2;
@@ -202,7 +205,13 @@ k_readout3(Geo g, const double* __restrict__ fa, const double* __restrict__ fb,
     }
     if (!(V & RV_EARLY) && live) {
         if (out_row) o = (long long)__ldg(out_row + p);
-        if (y_out) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
+        if (y_out && y_in && o >= 0) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
+    }
+    if (dist) {
+        if (!live) return;
+        if (value3 && o < 0) { value3[3 * p + 0] = a; value3[3 * p + 1] = b; value3[3 * p + 2] = c; }
+        if (y_out && o >= 0) write_row3<V>(y_out, o, fma(fac, a, y0), fma(fac, b, y1), fma(fac, c, y2));
+        return;
     }
     if (out_row || !(V & RV_TILE)) {      // scattered rows (or no tile to stage through)
         if (!live) return;
@@ -259,7 +268,9 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
                 const double* __restrict__ x, const double* __restrict__ w3, long long np,
                 const int* __restrict__ out_row, const double* __restrict__ base,
                 double* __restrict__ grad, const double* __restrict__ y_in, double fac,
-                double* __restrict__ y_out) {
+                double* __restrict__ y_out, int dist) {
+    // dist != 0: grad is stored in SLOT order WITHOUT base for the rows whose home is elsewhere, y_out[o] = base[o] (0 when NULL) + grad
+    // only where the home row o = out_row[p] is on this rank (o >= 0); y_in / fac unused
     constexpr int PM = rv_pair_mode(V);
     __shared__ RowTile<(V & RV_TILE) ? ROW_TILE : 1, 2> tile;
     const long long p0 = blockIdx.x * (long long)ROW_TILE;
@@ -273,9 +284,9 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
     }
     // rows reached through the permutation (EARLY: requested now, consumed after the mesh)
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, y0 = 0.0, y1 = 0.0, y2 = 0.0;
-    if ((V & RV_EARLY) && live) {
+    if ((V & RV_EARLY) && live && o >= 0) {
         if (base) fetch_row3<V>(base, o, out_row != nullptr, b0, b1, b2);
-        if (y_out) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
+        if (y_out && !dist) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
     }
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     if (live) {
@@ -318,11 +329,19 @@ k_readout_grad4(Geo g, const double* __restrict__ F0, const double* __restrict__
         }
         if (!(V & RV_EARLY)) {
             if (out_row) o = (long long)__ldg(out_row + p);
-            if (base) fetch_row3<V>(base, o, out_row != nullptr, b0, b1, b2);
-            if (y_out) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
+            if (o >= 0) {
+                if (base) fetch_row3<V>(base, o, out_row != nullptr, b0, b1, b2);
+                if (y_out && !dist) fetch_row3<V>(y_in, o, out_row != nullptr, y0, y1, y2);
+            }
         }
         // (gradient) + base: the sum the separate accumulation pass would form
-        if (base) { a0 += b0; a1 += b1; a2 += b2; }
+        if (base && !dist) { a0 += b0; a1 += b1; a2 += b2; }
+    }
+    if (dist) {
+        if (!live) return;
+        if (grad && o < 0) { grad[3 * p + 0] = a0; grad[3 * p + 1] = a1; grad[3 * p + 2] = a2; }
+        if (y_out && o >= 0) write_row3<V>(y_out, o, b0 + a0, b1 + a1, b2 + a2);
+        return;
     }
     if (out_row || !(V & RV_TILE)) {
         if (!live) return;
@@ -400,24 +419,37 @@ int vpm_readout(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const d
     VPM_API_END
 }
 
-int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
-                 const double* f2, const double* x, int64_t np, const int32_t* out_row,
-                 double* value3, const double* y_in, double fac, double* y_out) {
+static int readout3_impl(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                         const double* f2, const double* x, int64_t np, const int32_t* out_row,
+                         double* value3, const double* y_in, double fac, double* y_out, int dist) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("readout3", 24.0 * np + 24.0 * mesh_cells(mesh) + (out_row ? 4.0 : 0.0) * np + (value3 ? 24.0 : 0.0) * np + (y_out ? 48.0 : 0.0) * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
         VPM_REQUIRE(f0 && f1 && f2 && x && (value3 || y_out), "NULL array");
-        VPM_REQUIRE(!y_out || y_in, "y_out needs y_in");
+        VPM_REQUIRE(!y_out || y_in || dist, "y_out needs y_in");
+        VPM_REQUIRE(!dist || out_row, "home rows are required");
         int v = g_readout_variant;
         if (!rows_aligned(g, {f0, f1, f2}) && (v & RV_PAIR_AL)) v = (v & ~RV_PAIR_AL) | RV_PAIR_8;
         const unsigned grid = (unsigned)ceil_div(np, ROW_TILE);
-#define VPM_R3(VV, MB) case VV | (MB << 5): VPM_LAUNCH((k_readout3<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, x, (long long)np, out_row, value3, y_in, fac, y_out); break;
+#define VPM_R3(VV, MB) case VV | (MB << 5): VPM_LAUNCH((k_readout3<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, x, (long long)np, out_row, value3, y_in, fac, y_out, dist); break;
         switch (v) { VPM_RV_CASES(VPM_R3) default: VPM_REQUIRE(false, "bad readout variant"); }
 #undef VPM_R3
     }
     VPM_API_END
+}
+
+int vpm_readout3(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                 const double* f2, const double* x, int64_t np, const int32_t* out_row,
+                 double* value3, const double* y_in, double fac, double* y_out) {
+    return readout3_impl(ctx, mesh, f0, f1, f2, x, np, out_row, value3, y_in, fac, y_out, 0);
+}
+
+int vpm_readout3_home(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                      const double* f2, const double* x, int64_t np, const int32_t* home_row,
+                      double* value3_slots, const double* acc_in, double scale, double* acc_out) {
+    return readout3_impl(ctx, mesh, f0, f1, f2, x, np, home_row, value3_slots, acc_in, scale, acc_out, 1);
 }
 
 int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, const double* x,
@@ -440,25 +472,41 @@ int vpm_readout_grad(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field, co
     VPM_API_END
 }
 
-int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
-                      const double* f2, const double* r, const double* x, const double* w3,
-                      int64_t np, const int32_t* out_row, const double* base, double* grad,
-                      const double* y_in, double fac, double* y_out) {
+static int readout_grad4_impl(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                              const double* f2, const double* r, const double* x, const double* w3,
+                              int64_t np, const int32_t* out_row, const double* base, double* grad,
+                              const double* y_in, double fac, double* y_out, int dist) {
     VPM_API_BEGIN
     VPM_PROF_GROUP("readout_grad4", 72.0 * np + 32.0 * mesh_cells(mesh) + (out_row ? 4.0 : 0.0) * np + (base ? 24.0 : 0.0) * np + (y_out ? 48.0 : 0.0) * np);
     VPM_REQUIRE(ctx, "ctx is NULL");
     Geo g = make_geo(mesh);
     if (np > 0) {
-        VPM_REQUIRE(f0 && f1 && f2 && r && x && w3 && grad, "NULL array");
-        VPM_REQUIRE(!y_out || y_in, "y_out needs y_in");
+        VPM_REQUIRE(f0 && f1 && f2 && r && x && w3 && (grad || (dist && y_out)), "NULL array");
+        VPM_REQUIRE(!y_out || y_in || dist, "y_out needs y_in");
+        VPM_REQUIRE(!dist || out_row, "home rows are required");
         int v = g_readout_variant;
         if (!rows_aligned(g, {f0, f1, f2, r}) && (v & RV_PAIR_AL)) v = (v & ~RV_PAIR_AL) | RV_PAIR_8;
         const unsigned grid = (unsigned)ceil_div(np, ROW_TILE);
-#define VPM_G4(VV, MB) case VV | (MB << 5): VPM_LAUNCH((k_readout_grad4<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, r, x, w3, (long long)np, out_row, base, grad, y_in, fac, y_out); break;
+#define VPM_G4(VV, MB) case VV | (MB << 5): VPM_LAUNCH((k_readout_grad4<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, r, x, w3, (long long)np, out_row, base, grad, y_in, fac, y_out, dist); break;
         switch (v) { VPM_RV_CASES(VPM_G4) default: VPM_REQUIRE(false, "bad readout variant"); }
 #undef VPM_G4
     }
     VPM_API_END
+}
+
+int vpm_readout_grad4(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                      const double* f2, const double* r, const double* x, const double* w3,
+                      int64_t np, const int32_t* out_row, const double* base, double* grad,
+                      const double* y_in, double fac, double* y_out) {
+    return readout_grad4_impl(ctx, mesh, f0, f1, f2, r, x, w3, np, out_row, base, grad, y_in, fac, y_out, 0);
+}
+
+int vpm_readout_grad4_home(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, const double* f1,
+                           const double* f2, const double* r, const double* x, const double* w3,
+                           int64_t np, const int32_t* home_row, double* grad_slots,
+                           const double* acc_in, double* acc_out) {
+    return readout_grad4_impl(ctx, mesh, f0, f1, f2, r, x, w3, np, home_row, acc_in, grad_slots, nullptr, 0.0,
+                              acc_out, 1);
 }
 
 int vpm_readout_jvp(vpm_ctx* ctx, const vpm_mesh* mesh, const double* field,

@@ -299,11 +299,14 @@ class PeerExchange(object):
         sy.buf = b
         return ct.byref(sy)
 
-    def put(self, b, src, rows, inner, s_row, s_dst, dst_off, first=True, last=True):
+    def put(self, b, src, rows, inner, s_row, s_dst, dst_off, first=True, last=True, d_row=None):
+        """block d of ``src`` (rows x inner complex elements, row stride s_row, block stride s_dst) into
+        rank d's receive area at dst_off, rows ``d_row`` apart there (default: packed)"""
         C, ct = self.C, self.ctypes
-        C.check(C.lib.vpm_peer_put(self._ctx(), self.P, int(rows), int(inner), int(s_row), int(s_dst),
-                                   ct.c_void_p(src.data_ptr()), self.buf_ptrs[b], int(dst_off),
-                                   self._sync(b, first, last)))
+        C.check(C.lib.vpm_peer_put_strided(self._ctx(), self.P, int(rows), int(inner), int(s_row), int(s_dst),
+                                           int(inner if d_row is None else d_row),
+                                           ct.c_void_p(src.data_ptr()), self.buf_ptrs[b], int(dst_off),
+                                           self._sync(b, first, last)))
 
     def put_to(self, b, src_ptr, count, mask, dst_off, first, last):
         """``count`` contiguous complex128 elements at device address ``src_ptr`` to the ranks in

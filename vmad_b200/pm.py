@@ -47,8 +47,20 @@ class Runtime(object):
         C.check(C.lib.vpm_ctx_create(ctypes.byref(h), device, ctypes.c_void_p(self._stream)))
         self.ctx = h
 
+    def push_stream(self, stream):
+        """launch the following calls on ``stream`` (a torch stream) without draining the current
+        one; only for calls that use neither cuFFT nor the workspace.  ``pop_stream`` restores."""
+        C.check(C.lib.vpm_ctx_push_stream(self.ctx, ctypes.c_void_p(stream.cuda_stream)))
+        self._pushed = True
+
+    def pop_stream(self):
+        C.check(C.lib.vpm_ctx_pop_stream(self.ctx))
+        self._pushed = False
+
     def sync_stream(self):
         """Follow torch's current stream (cheap when unchanged)."""
+        if getattr(self, '_pushed', False):
+            return
         s = _raw_stream(self._device_index)
         if s != self._stream:
             C.check(C.lib.vpm_ctx_set_stream(self.ctx, ctypes.c_void_p(s)))
@@ -847,6 +859,24 @@ class DistLayout(object):
         C.check(C.lib.vpm_take_rows_scaled(rt.ctx, _ptr(recv), _ptr(self.indices), self.nrecv, ncomp, scale, _ptr(out)))
         return DeviceArray(out, cellindex=self)
 
+    def home_rows(self):
+        """slot -> home row on this rank (negative: the row lives elsewhere / holds no particle), or
+        None when the layout cannot split a gather into a local store and a remote sum"""
+        return self.take_idx if self.px is not None else None
+
+    def gather_remote(self, t, out, scale=1.0):
+        """the cross-rank half of ``gather``: the rows of ``t`` (slot order) whose home is on another
+        rank travel there and are summed into ``out``; the local rows were stored by the caller
+        (vpm_readout3_home / vpm_readout_grad4_home)"""
+        rt = self.pm.rt
+        ncomp = _ncomp(t)
+        px = self.px
+        px.ensure(8 * self._max_rows * ncomp)
+        _, b = px.begin()
+        px.put_rows(b, t, self.inv_remote, self.nrecv, ncomp, 2, self.recv_start, self._back_base,
+                    skip=self.pm.rank)
+        _scatter_add_remote(rt, px, b, self.send_remote, self.send_start, self.pm.rank, ncomp, out, float(scale))
+
     def gather(self, data, mode='sum', init=None, scale=1.0):
         """fastpm.py:286,293,304: back to the home rank and order, copies summed.
         ``init`` / ``scale``: returns ``init + scale * gathered`` (the sum starts from a copy of
@@ -1007,6 +1037,18 @@ class StaticDistLayout(object):
             C.check(C.lib.vpm_take_rows_scaled(rt.ctx, px.recv_ptr(b), _ptr(self.indices), plan.cap_recv, ncomp,
                                                scale, _ptr(out)))
         return DeviceArray(out, cellindex=self)
+
+    def home_rows(self):
+        return self.take_idx
+
+    def gather_remote(self, t, out, scale=1.0):
+        """see DistLayout.gather_remote"""
+        pm, plan, px = self.pm, self.plan, self.px
+        ncomp = _ncomp(t)
+        self._area(ncomp)
+        _, b = px.begin()
+        px.put_rows(b, t, self.inv_remote, plan.cap_recv, ncomp, 2, plan.rbase, plan.back_base, skip=pm.rank)
+        _scatter_add_remote(pm.rt, px, b, self.send_remote, plan.sbase, pm.rank, ncomp, out, float(scale))
 
     def gather(self, data, mode='sum', init=None, scale=1.0):
         """fastpm.py:286,293,304: back to the home rank and order, copies summed.
@@ -1589,6 +1631,19 @@ class ParticleMesh(object):
                                        _ptr(x3), n, _ptr(gather.indices), _ptr(val), _ptr(y.t), float(kick[1]),
                                        _ptr(yo)))
             return (DeviceArray(val) if want_value else None), DeviceArray(yo)
+        home = gather.home_rows() if (gather is not None and not fused and hasattr(gather, 'home_rows')) else None
+        if home is not None and (kick is None or not want_value):
+            # several ranks: rows whose home is here are stored (kick included) by the readout itself,
+            # the partial values of the others travel from the slot-order copy and are summed after
+            val = rt.empty((n, 3))
+            init = asdevice(kick[0]) if kick is not None else None
+            scale = float(kick[1]) if kick is not None else 1.0
+            out = init.t.clone() if init is not None else torch.zeros((gather.oldlength, 3), dtype=_F8, device=rt.device)
+            C.check(C.lib.vpm_readout3_home(rt.ctx, ctypes.byref(self._mesh), _ptr(f0.t), _ptr(f1.t), _ptr(f2.t),
+                                            _ptr(x3), n, _ptr(home), _ptr(val),
+                                            _ptr(init.t) if init is not None else None, scale, _ptr(out)))
+            gather.gather_remote(val, out, scale)
+            return (None, DeviceArray(out)) if kick is not None else DeviceArray(out)
         val = rt.empty((n, 3))
         C.check(C.lib.vpm_readout3(rt.ctx, ctypes.byref(self._mesh), _ptr(f0.t), _ptr(f1.t),
                                    _ptr(f2.t), _ptr(x3), n, _ptr(gather.indices) if fused else None,
@@ -1698,6 +1753,25 @@ class ParticleMesh(object):
                     warnings.warn("peer-memory exchange unavailable (%r); using NCCL all-to-all" % (why,))
         return self._peer_x
 
+    def _fft_chunks(self):
+        """plane groups of the pipelined forward slab transform (1: no pipelining)"""
+        k = getattr(self, '_fft_k', None)
+        if k is None:
+            import os
+            k = int(os.environ.get('VMAD_B200_FFT_CHUNKS', '4'))
+            n0l = self.rshape[0]
+            slab_bytes = 16 * int(numpy.prod(self.cshape))
+            while k > 1 and (n0l % k or slab_bytes // k < (8 << 20)):
+                k //= 2
+            self._fft_k = k = max(k, 1)
+        return k
+
+    def _side_stream(self):
+        s = getattr(self, '_side', None)
+        if s is None:
+            self._side = s = torch.cuda.Stream(device=self.rt.device)
+        return s
+
     # slab-decomposed transforms: local cuFFT, one all-to-all transpose each -------------------
     def _r2c_slab(self, real, scale):
         """[n0l, N1, N2] real -> [N0, n1l, Nh] complex: 2-D D2Z over the local planes, pack,
@@ -1707,8 +1781,34 @@ class ParticleMesh(object):
         n0l, N1, N2 = self.rshape
         N0, n1l, Nh = self.cshape
         a = rt.empty((n0l, N1, Nh), _C16)
-        C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
         px = self._peer()
+        K = self._fft_chunks() if px is not None else 1
+        if K > 1:
+            # pipeline over groups of planes: while group c travels (pack + NVLink stores on a side
+            # stream; the flag protocol spans the K launches), the 2-D transforms of group c + 1 run
+            inner = n1l * Nh
+            pc = n0l // K
+            _, b = px.begin()
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            for c in range(K):
+                rt.sync_stream()
+                C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, pc, N1, N2, _ptr(real.t[c * pc:(c + 1) * pc]),
+                                                 _ptr(a[c * pc:(c + 1) * pc])))
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                rt.push_stream(side)
+                try:
+                    px.put(b, a[c * pc:(c + 1) * pc], pc, inner, P * inner, inner,
+                           (self.rank * n0l + c * pc) * inner, first=(c == 0), last=(c == K - 1))
+                finally:
+                    rt.pop_stream()
+            main.wait_stream(side)
+            o = rt.empty(self.cshape, _C16)
+            C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, px.recv_ptr(b), _ptr(o), 0, float(scale)))
+            return ComplexField(self, o)
+        C.check(C.lib.vpm_fft_r2c_planes(rt.ctx, n0l, N1, N2, _ptr(real.t), _ptr(a)))
         if px is not None:
             # pack + transfer in one kernel: block d is stored straight into rank d's buffer
             inner = n1l * Nh
@@ -1778,14 +1878,12 @@ class ParticleMesh(object):
             e, b = px.begin()
             for k, c in enumerate(cplxs):
                 C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, inner, _ptr(c.t), 1, 1.0))
-                px.put(b, c.t, 1, blk, 0, blk, k * slab + self.rank * blk, first=(k == 0), last=(k == K - 1))
+                px.put(b, c.t, n0l, inner, inner, blk, k * slab + self.rank * inner, first=(k == 0),
+                       last=(k == K - 1), d_row=P * inner)
             out = []
             for k in range(K):
-                a = rt.empty((n0l, N1, Nh), _C16)
-                C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner,
-                                                    px.recv_ptr(b, k * slab), _ptr(a)))
                 o = rt.empty(self.rshape)
-                C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
+                C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, px.recv_ptr(b, k * slab), _ptr(o), float(scale)))
                 out.append(RealField(self, o))
             return out
         send = rt.empty((P, K, n0l, n1l, Nh), _C16)
@@ -1817,11 +1915,11 @@ class ParticleMesh(object):
             work = rt.empty(self.cshape, _C16)
             C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, _ptr(cplx.t), _ptr(work), 1, 1.0))
             e, b = px.begin()
-            px.put(b, work, 1, blk, 0, blk, self.rank * blk)
-            a = rt.empty((n0l, N1, Nh), _C16)
-            C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner, px.recv_ptr(b), _ptr(a)))
+            # block d = the planes of rank d; its rows land [plane, source's columns] in d's receive
+            # area, i.e. in [n0l, N1, Nh] order: the 2-D inverse transforms read the area in place
+            px.put(b, work, n0l, inner, inner, blk, self.rank * inner, d_row=P * inner)
             o = rt.empty(self.rshape) if out is None else out
-            C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
+            C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, px.recv_ptr(b), _ptr(o), float(scale)))
             return RealField(self, o)
         work = cplx.t if consume else cplx.t.clone()    # operators must not mutate their inputs
         C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(work), 1, 1.0))
@@ -2227,10 +2325,21 @@ def force_vjp(pm, st, _f, _potk, f_scale=1.0, base=None, update=None):
         if update is None:
             return out
         return out, (DeviceArray(yo) if y is not None else out * float(fac))
-    C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
-                                    _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
-                                    None, None, _ptr(g), None, 0.0, None))
-    out = lay.gather(DeviceArray(g), init=base)
+    home = lay.home_rows() if hasattr(lay, 'home_rows') else None
+    if home is not None:
+        # several ranks: local home rows (+ base) stored by the kernel, remote partial sums added after
+        bt = asdevice(base).t if base is not None else None
+        acc = bt.clone() if bt is not None else torch.zeros((lay.oldlength, 3), dtype=_F8, device=rt.device)
+        C.check(C.lib.vpm_readout_grad4_home(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
+                                             _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
+                                             _ptr(home), _ptr(g), _ptr(bt), _ptr(acc)))
+        lay.gather_remote(g, acc, 1.0)
+        out = DeviceArray(acc)
+    else:
+        C.check(C.lib.vpm_readout_grad4(rt.ctx, ctypes.byref(pm._mesh), _ptr(F[0].t), _ptr(F[1].t),
+                                        _ptr(F[2].t), _ptr(rho_bar.t), _ptr(xl.t), _ptr(_fl.t), n,
+                                        None, None, _ptr(g), None, 0.0, None))
+        out = lay.gather(DeviceArray(g), init=base)
     if update is None:
         return out
     return out, (y._axpby(1.0, float(fac), out.t) if y is not None else out * float(fac))
