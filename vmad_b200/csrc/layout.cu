@@ -31,27 +31,45 @@ __global__ void k_keys(Geo g, const double* __restrict__ x, long long np, int* _
     if (p < np) keys[p] = key_of(g, x, p);
 }
 
-__global__ void k_keys_count(Geo g, const double* __restrict__ x, long long np,
-                             int* __restrict__ keys, int* __restrict__ rank,
-                             int* __restrict__ count) {
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+// KC_ILP particles per thread (blockDim apart): their position loads and their returning atomics
+// are independent, so the two memory latencies of a particle overlap across the group
+constexpr int KC_ILP = 4;
+__global__ void __launch_bounds__(256)
+k_keys_count(Geo g, const double* __restrict__ x, long long np,
+             int* __restrict__ keys, int* __restrict__ rank,
+             int* __restrict__ count) {
+    const long long p0 = blockIdx.x * (long long)(KC_ILP * blockDim.x) + threadIdx.x;
     const int overflow = g.nsp * g.n1 * g.n2;
-    int k = -1;
-    if (p < np) k = key_of(g, x, p);
-    // rows that are not on this slab (the padding of a fixed-capacity receive order: long runs of
-    // them) would all hit one counter: one atomic per warp for those
-    const unsigned off = __ballot_sync(0xffffffffu, k == overflow);
-    if (k == overflow) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(off) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(count + k, __popc(off));
-        base = __shfl_sync(off, base, leader);
-        keys[p] = k;
-        rank[p] = base + __popc(off & ((1u << lane) - 1));
-    } else if (p < np) {
-        keys[p] = k;
-        rank[p] = atomicAdd(count + k, 1);
+    const int lane = threadIdx.x & 31;
+    int k[KC_ILP], r[KC_ILP];
+#pragma unroll
+    for (int j = 0; j < KC_ILP; ++j) {
+        const long long p = p0 + (long long)j * blockDim.x;
+        k[j] = p < np ? key_of(g, x, p) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < KC_ILP; ++j) {
+        // rows that are not on this slab (the padding of a fixed-capacity receive order: long runs
+        // of them) would all hit one counter: one atomic per warp for those
+        const unsigned off = __ballot_sync(0xffffffffu, k[j] == overflow);
+        r[j] = 0;
+        if (k[j] == overflow) {
+            const int leader = __ffs(off) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(count + k[j], __popc(off));
+            base = __shfl_sync(off, base, leader);
+            r[j] = base + __popc(off & ((1u << lane) - 1));
+        } else if (k[j] >= 0) {
+            r[j] = atomicAdd(count + k[j], 1);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KC_ILP; ++j) {
+        const long long p = p0 + (long long)j * blockDim.x;
+        if (p < np) {
+            keys[p] = k[j];
+            rank[p] = r[j];
+        }
     }
 }
 
@@ -143,11 +161,25 @@ static void exclusive_scan(cudaStream_t st, const int* in, long long n, int* out
     VPM_LAUNCH(k_scan_down, (unsigned)nb, SCAN_THREADS, 0, st, in, n, (const int*)sums, out, close);
 }
 
-__global__ void k_scatter_ids(const int* __restrict__ keys, const int* __restrict__ rank,
-                              const int* __restrict__ cell_start, long long np,
-                              int* __restrict__ perm) {
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p < np) perm[cell_start[keys[p]] + rank[p]] = (int)p;
+__global__ void __launch_bounds__(256)
+k_scatter_ids(const int* __restrict__ keys, const int* __restrict__ rank,
+              const int* __restrict__ cell_start, long long np, int* __restrict__ perm) {
+    // KC_ILP particles per thread: the dependent chain key -> cell_start[key] -> store runs four wide
+    const long long p0 = blockIdx.x * (long long)(KC_ILP * blockDim.x) + threadIdx.x;
+    int k[KC_ILP], r[KC_ILP], b[KC_ILP];
+#pragma unroll
+    for (int j = 0; j < KC_ILP; ++j) {
+        const long long p = p0 + (long long)j * blockDim.x;
+        k[j] = p < np ? __ldg(keys + p) : -1;
+        r[j] = p < np ? __ldg(rank + p) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < KC_ILP; ++j) b[j] = k[j] >= 0 ? __ldg(cell_start + k[j]) : 0;
+#pragma unroll
+    for (int j = 0; j < KC_ILP; ++j) {
+        const long long p = p0 + (long long)j * blockDim.x;
+        if (p < np) perm[b[j] + r[j]] = (int)p;
+    }
 }
 
 // per-cell ascending sort of the ids (restores input order inside a cell).  Three tiers by
@@ -653,12 +685,12 @@ int vpm_layout_build(vpm_ctx* ctx, const vpm_mesh* mesh, const double* x, int64_
     VPM_PROF_CALL("memset(cell counts)", st, VPM_CUDA(cudaMemsetAsync(ws, 0, (size_t)(8 + ncell) * sizeof(int), st)));
     if (np > 0) {
         VPM_REQUIRE(x && keys && perm, "NULL array");
-        VPM_LAUNCH(k_keys_count, (unsigned)ceil_div(np, 256), 256, 0, st, g, x, (long long)np, keys,
+        VPM_LAUNCH(k_keys_count, (unsigned)ceil_div(np, 256 * KC_ILP), 256, 0, st, g, x, (long long)np, keys,
                    rank, count);
     }
     exclusive_scan(st, count, ncell, cell_start, tmp, /*close: cell_start[ncell] = np*/ 1);
     if (np > 0) {
-        VPM_LAUNCH(k_scatter_ids, (unsigned)ceil_div(np, 256), 256, 0, st, keys, rank, cell_start,
+        VPM_LAUNCH(k_scatter_ids, (unsigned)ceil_div(np, 256 * KC_ILP), 256, 0, st, keys, rank, cell_start,
                    (long long)np, perm);
         // the last bucket collects what is not on this slab (only the inert padding rows of the
         // fixed-capacity routing end up there, possibly very many): their order is irrelevant

@@ -357,8 +357,6 @@ __global__ void __launch_bounds__(256)
 k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, double mass0,
             int mstride, const double* __restrict__ vpos, const double* __restrict__ vmass,
             int np, double* __restrict__ out) {
-    __shared__ unsigned char s_adopt[8][32];
-    const int warp_in_cta = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nchunk = (np + 31) >> 5;
     const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
@@ -468,54 +466,15 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
             VPM_ADD_IF(S100, t2, take);
             VPM_ADD_IF(S110, t3, take);
         }
-        // Adoption (see k_paint_agg3): lanes that are not tails issue the c = 1 sums of the tails that
-        // keep them, at cell z + 1, inside the instruction that carries the tails' c = 0 sums -- the
-        // reduction unit is bound by sectors per instruction, not by reductions.
-        const bool left = tail && !hand_over;
-        const unsigned m_left = __ballot_sync(0xffffffffu, left);
-        const unsigned m_idle = __ballot_sync(0xffffffffu, !tail);
-        const unsigned below = (1u << lane) - 1u;
-        // the r-th idle lane finds the r-th such tail through a 32-byte table of the warp
-        // (find-nth-set-bit is emulated in software on this architecture: ~60 instructions)
-        const int rank_left = __popc(m_left & below);
-        if (left) s_adopt[warp_in_cta][rank_left] = (unsigned char)lane;
-        __syncwarp();
-        int src = lane;
-        bool adopter = false;
-        if (!tail) {
-            const int r = __popc(m_idle & below);
-            if (r < __popc(m_left)) {
-                src = s_adopt[warp_in_cta][r];
-                adopter = true;
-            }
-        }
-        __syncwarp();
-        const bool given = left && rank_left < __popc(m_idle);
-        if (m_left != 0u && m_idle != 0u) {
-            const int a0 = __shfl_sync(0xffffffffu, i0, src);
-            const int a1 = __shfl_sync(0xffffffffu, i1, src);
-            const int az = __shfl_sync(0xffffffffu, iz, src);
-            const double t0 = __shfl_sync(0xffffffffu, S001, src);
-            const double t1 = __shfl_sync(0xffffffffu, S011, src);
-            const double t2 = __shfl_sync(0xffffffffu, S101, src);
-            const double t3 = __shfl_sync(0xffffffffu, S111, src);
-            if (adopter) {
-                S000 = t0; S010 = t1; S100 = t2; S110 = t3;
-                i0 = a0;
-                i1 = a1;
-                iz = wrap_inc(az, g.n2);
-            }
-        }
-        if (tail || adopter) {
+        if (tail) {
             const int j1 = wrap_inc(i1, g.n1), jz = wrap_inc(iz, g.n2);
             const int la = local_plane(g, i0), lb = local_plane(g, wrap_inc(i0, g.n0));
             const int ra = la * st0, rb = lb * st0;
             const int c0 = i1 * st1, c1 = j1 * st1;
-            const bool second = left && !given;
             if (la >= 0) {
                 atomicAdd(out + (ra + c0 + iz), S000);
                 atomicAdd(out + (ra + c1 + iz), S010);
-                if (second) {
+                if (!hand_over) {
                     atomicAdd(out + (ra + c0 + jz), S001);
                     atomicAdd(out + (ra + c1 + jz), S011);
                 }
@@ -523,7 +482,7 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
             if (lb >= 0) {
                 atomicAdd(out + (rb + c0 + iz), S100);
                 atomicAdd(out + (rb + c1 + iz), S110);
-                if (second) {
+                if (!hand_over) {
                     atomicAdd(out + (rb + c0 + jz), S101);
                     atomicAdd(out + (rb + c1 + jz), S111);
                 }
@@ -540,8 +499,6 @@ k_paint_agg(Geo g, const double* __restrict__ xs, const double* __restrict__ mas
 __global__ void __launch_bounds__(256, 3)
 k_paint_agg3(Geo g, const double* __restrict__ xs, const double* __restrict__ mass, int mstride,
              int np, double* __restrict__ out, long long colstride) {
-    __shared__ unsigned char s_adopt[8][32];
-    const int warp_in_cta = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nchunk = (np + 31) >> 5;
     const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
@@ -610,62 +567,18 @@ k_paint_agg3(Geo g, const double* __restrict__ xs, const double* __restrict__ ma
                 const double t = __shfl_sync(0xffffffffu, S[c][2 * ab + 1], sl);
                 VPM_ADD_IF(S[c][2 * ab], t, take);
             }
-        // Adoption: a run tail that keeps its c = 1 sums (its z + 1 neighbour is not the next run)
-        // would issue them as a second, sparsely populated reduction per row -- and the L2 reduction
-        // unit is bound by 32-byte SECTORS per instruction, not by reductions (benchmarks/red_rate.cu).
-        // The lanes that are not tails have nothing to write: the r-th of them adopts the c = 1 sums
-        // of the r-th such tail and issues them as ITS primary reduction at cell z + 1, in the same
-        // instruction (and mostly the same sectors) as the c = 0 sums of the tails.
-        const bool left = tail && !hand_over;
-        const unsigned m_left = __ballot_sync(0xffffffffu, left);
-        const unsigned m_idle = __ballot_sync(0xffffffffu, !tail);
-        const unsigned below = (1u << lane) - 1u;
-        // the r-th idle lane finds the r-th such tail through a 32-byte table of the warp
-        // (find-nth-set-bit is emulated in software on this architecture: ~60 instructions)
-        const int rank_left = __popc(m_left & below);
-        if (left) s_adopt[warp_in_cta][rank_left] = (unsigned char)lane;
-        __syncwarp();
-        int src = lane;
-        bool adopter = false;
-        if (!tail) {
-            const int r = __popc(m_idle & below);
-            if (r < __popc(m_left)) {
-                src = s_adopt[warp_in_cta][r];
-                adopter = true;
-            }
-        }
-        __syncwarp();
-        const bool given = left && rank_left < __popc(m_idle);
-        if (m_left != 0u && m_idle != 0u) {
-            const int a0 = __shfl_sync(0xffffffffu, i0, src);
-            const int a1 = __shfl_sync(0xffffffffu, i1, src);
-            const int az = __shfl_sync(0xffffffffu, iz, src);
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int ab = 0; ab < 4; ++ab) {
-                    const double t = __shfl_sync(0xffffffffu, S[c][2 * ab + 1], src);
-                    if (adopter) S[c][2 * ab] = t;
-                }
-            if (adopter) {
-                i0 = a0;
-                i1 = a1;
-                iz = wrap_inc(az, g.n2);
-            }
-        }
-        if (tail || adopter) {
+        if (tail) {
             const int j1 = wrap_inc(i1, g.n1), jz = wrap_inc(iz, g.n2);
             const int la = local_plane(g, i0), lb = local_plane(g, wrap_inc(i0, g.n0));
             const int ra = la * st0, rb = lb * st0;
             const int c0 = i1 * st1, c1 = j1 * st1;
-            const bool second = left && !given;      // c = 1 sums still here: a second reduction per row
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 double* o = out + c * colstride;
                 if (la >= 0) {
                     atomicAdd(o + (ra + c0 + iz), S[c][0]);
                     atomicAdd(o + (ra + c1 + iz), S[c][2]);
-                    if (second) {
+                    if (!hand_over) {
                         atomicAdd(o + (ra + c0 + jz), S[c][1]);
                         atomicAdd(o + (ra + c1 + jz), S[c][3]);
                     }
@@ -673,7 +586,7 @@ k_paint_agg3(Geo g, const double* __restrict__ xs, const double* __restrict__ ma
                 if (lb >= 0) {
                     atomicAdd(o + (rb + c0 + iz), S[c][4]);
                     atomicAdd(o + (rb + c1 + iz), S[c][6]);
-                    if (second) {
+                    if (!hand_over) {
                         atomicAdd(o + (rb + c0 + jz), S[c][5]);
                         atomicAdd(o + (rb + c1 + jz), S[c][7]);
                     }
