@@ -916,6 +916,10 @@ class DistLayout(object):
         return DeviceArray(out)
 
 
+import os as _os
+_C2R_STRIDED = _os.environ.get('VMAD_B200_C2R_STRIDED', '1') != '0'
+
+
 def _scatter_add_remote(rt, px, b, send_remote, send_start, me, ncomp, out, scale=1.0):
     """what came back from the other ranks (receive area b, in send order) is summed into the home
     rows; the positions of the self segment hold nothing, so only the ranges around it are visited"""
@@ -1917,11 +1921,17 @@ class ParticleMesh(object):
             work = rt.empty(self.cshape, _C16)
             C.check(C.lib.vpm_fft_c2c_axis0_oop(rt.ctx, N0, inner, _ptr(cplx.t), _ptr(work), 1, 1.0))
             e, b = px.begin()
-            # block d = the planes of rank d; its rows land [plane, source's columns] in d's receive
-            # area, i.e. in [n0l, N1, Nh] order: the 2-D inverse transforms read the area in place
-            px.put(b, work, n0l, inner, inner, blk, self.rank * inner, d_row=P * inner)
             o = rt.empty(self.rshape) if out is None else out
-            C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, px.recv_ptr(b), _ptr(o), float(scale)))
+            if _C2R_STRIDED:
+                # block d = the planes of rank d; its rows land [plane, source's columns] in d's receive
+                # area, i.e. in [n0l, N1, Nh] order: the 2-D inverse transforms read the area in place
+                px.put(b, work, n0l, inner, inner, blk, self.rank * inner, d_row=P * inner)
+                C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, px.recv_ptr(b), _ptr(o), float(scale)))
+                return RealField(self, o)
+            px.put(b, work, 1, blk, 0, blk, self.rank * blk)
+            a = rt.empty((n0l, N1, Nh), _C16)
+            C.check(C.lib.vpm_swap_leading_axes(rt.ctx, P, n0l, inner, px.recv_ptr(b), _ptr(a)))
+            C.check(C.lib.vpm_fft_c2r_planes(rt.ctx, n0l, N1, N2, _ptr(a), _ptr(o), float(scale)))
             return RealField(self, o)
         work = cplx.t if consume else cplx.t.clone()    # operators must not mutate their inputs
         C.check(C.lib.vpm_fft_c2c_axis0(rt.ctx, N0, n1l * Nh, _ptr(work), 1, 1.0))
