@@ -530,3 +530,105 @@ def test_fd4_stencil_and_adjoint(device_pm, shape, pad):
     for d in range(3):
         assert numpy.array_equal(got[d], got_s[d])
     assert numpy.array_equal(got_adj, got_adj_s)
+
+
+def test_readout_home_row_variants_vs_oracle(oracle_pm, device_pm):
+    """the cross-rank forms of the force readout / its reverse sweep on ONE device:
+    vpm_readout3_home and vpm_readout_grad4_home store `acc_in[h] + scale * value` at home rows
+    h >= 0 and the slot-order copy at the slots whose home is elsewhere (h < 0), checked against
+    the oracle readout / readout_vjp; also the fused one-rank epilogues (out_row, kick, base)"""
+    import ctypes
+    import torch
+    from vmad_b200 import _capi as C
+    from vmad_b200.pm import runtime, _ptr
+    rng = numpy.random.default_rng(21)
+    Nmesh, BoxSize, n = [16, 12, 20], [7.0, 3.0, 11.0], 5000
+    opm = oracle_pm(Nmesh, BoxSize)
+    dpm = device_pm(Nmesh, BoxSize)
+    rt = runtime()
+    x = edge_positions(rng, Nmesh, BoxSize, n)
+    n = len(x)
+    fs = [rng.standard_normal(Nmesh) for _ in range(4)]
+    w3 = rng.standard_normal((n, 3))
+    val = numpy.stack([opm.create('real', value=a).readout(x) for a in fs[:3]], axis=-1)
+    # gradient of sum_d w3[:, d] readout(F_d, x) + readout(R, x) with respect to x
+    grad = sum(opm.create('real', value=fs[d]).readout_vjp(x, w3[:, d])[1] for d in range(3)) \
+        + opm.create('real', value=fs[3]).readout_vjp(x, numpy.ones(n))[1]
+    # home rows: a random injection into a larger home array; a third of the slots live "elsewhere"
+    nhome = n + 100
+    home = rng.permutation(nhome)[:n].astype('i4')
+    away = rng.uniform(size=n) < 0.33
+    home_row = numpy.where(away, -1 - numpy.arange(n), home).astype('i4')
+    home_row[::97] = numpy.iinfo('i4').min            # padding slots of a fixed-capacity layout
+    away |= home_row == numpy.iinfo('i4').min
+    acc_in = rng.standard_normal((nhome, 3))
+    dev = lambda a, dt=torch.float64: torch.from_numpy(numpy.ascontiguousarray(a)).to(rt.device, dt)
+    F = [dev(a) for a in fs]
+    dx, dw, dh, dacc = dev(x), dev(w3), dev(home_row, torch.int32), dev(acc_in)
+    mesh = ctypes.byref(dpm._mesh)
+    rt.sync_stream()
+    for scale, use_acc in ((0.7, True), (1.0, False)):
+        slots = torch.full((n, 3), numpy.nan, dtype=torch.float64, device=rt.device)
+        out = dacc.clone() if use_acc else torch.zeros((nhome, 3), dtype=torch.float64, device=rt.device)
+        C.check(C.lib.vpm_readout3_home(rt.ctx, mesh, _ptr(F[0]), _ptr(F[1]), _ptr(F[2]), _ptr(dx), n, _ptr(dh),
+                                        _ptr(slots), _ptr(dacc) if use_acc else None, scale, _ptr(out)))
+        rt.synchronize()
+        want = acc_in.copy() if use_acc else numpy.zeros((nhome, 3))
+        want[home[~away]] += scale * val[~away]
+        assert rel_l2(out.cpu().numpy(), want) < TOL
+        got = slots.cpu().numpy()
+        assert rel_l2(got[away], val[away]) < TOL
+        assert numpy.isnan(got[~away]).all()            # slots whose home is here are not written
+    slots = torch.full((n, 3), numpy.nan, dtype=torch.float64, device=rt.device)
+    out = dacc.clone()
+    C.check(C.lib.vpm_readout_grad4_home(rt.ctx, mesh, _ptr(F[0]), _ptr(F[1]), _ptr(F[2]), _ptr(F[3]), _ptr(dx),
+                                         _ptr(dw), n, _ptr(dh), _ptr(slots), _ptr(dacc), _ptr(out)))
+    rt.synchronize()
+    want = acc_in.copy()
+    want[home[~away]] += grad[~away]
+    assert rel_l2(out.cpu().numpy(), want) < TOL
+    assert rel_l2(slots.cpu().numpy()[away], grad[away]) < TOL
+    # one-rank epilogues: rows stored through out_row, base added, y_out = y_in + fac * result
+    perm = dev(home, torch.int32)
+    g = torch.zeros((nhome, 3), dtype=torch.float64, device=rt.device)
+    yo = torch.zeros((nhome, 3), dtype=torch.float64, device=rt.device)
+    yin = rng.standard_normal((nhome, 3))
+    C.check(C.lib.vpm_readout_grad4(rt.ctx, mesh, _ptr(F[0]), _ptr(F[1]), _ptr(F[2]), _ptr(F[3]), _ptr(dx), _ptr(dw),
+                                    n, _ptr(perm), _ptr(dacc), _ptr(g), _ptr(dev(yin)), 0.3, _ptr(yo)))
+    rt.synchronize()
+    want = numpy.zeros((nhome, 3)); want[home] = grad + acc_in[home]
+    wy = numpy.zeros((nhome, 3)); wy[home] = yin[home] + 0.3 * want[home]
+    assert rel_l2(g.cpu().numpy(), want) < TOL
+    assert rel_l2(yo.cpu().numpy(), wy) < TOL
+
+
+def test_peer_put_strided_on_one_device():
+    """vpm_peer_put_strided with one 'rank' (the receive area is a local buffer): rows land with
+    the destination stride -- the layout the inverse slab transform reads in place"""
+    import ctypes
+    import torch
+    from vmad_b200 import _capi as C
+    from vmad_b200.pm import runtime
+    rt = runtime()
+    rt.sync_stream()
+    rows, inner, s_row, d_row = 5, 24, 40, 64
+    src = torch.arange(2 * rows * s_row, dtype=torch.float64, device=rt.device)      # complex pairs
+    p = ctypes.c_void_p()
+    h = ctypes.create_string_buffer(64)
+    nbytes = 16 * (rows * d_row + 8)
+    C.check(C.lib.vpm_peer_alloc(rt.ctx, nbytes, ctypes.byref(p), h))
+    try:
+        bufs = (ctypes.c_uint64 * 8)(p.value, 0, 0, 0, 0, 0, 0, 0)
+        C.check(C.lib.vpm_peer_put_strided(rt.ctx, 1, rows, inner, s_row, 0, d_row, ctypes.c_void_p(src.data_ptr()),
+                                           bufs, 3, None))
+        out = torch.empty(nbytes // 8, dtype=torch.float64, device=rt.device)
+        C.check(C.lib.vpm_axpby(rt.ctx, nbytes // 8, 1.0, p, 0.0, None, 0.0, ctypes.c_void_p(out.data_ptr())))
+        rt.synchronize()
+        got = out.cpu().numpy().reshape(-1, 2)
+        want = numpy.zeros_like(got)
+        s = src.cpu().numpy().reshape(-1, 2)
+        for i in range(rows):
+            want[3 + i * d_row: 3 + i * d_row + inner] = s[i * s_row: i * s_row + inner]
+        assert numpy.array_equal(got, want)
+    finally:
+        C.check(C.lib.vpm_peer_free(rt.ctx, p))

@@ -469,46 +469,80 @@ k_route_count(Geo g, int planes_per_rank, int P, const double* __restrict__ x, l
 }
 
 // in-block stable ranks: rounds in order, within a round warps in order, within a warp lanes in
-// order (ballot); `run[d]` carries the rows bound for d seen in the earlier rounds of this block
+// order (ballot).  A thread first finds the destinations of its ROUTE_ROUNDS particles (eight
+// independent loads), then the block visits only the destinations that occur in it (a slab keeps
+// nearly all of its particles: typically itself and one neighbour): per destination every warp
+// ballots its eight rounds, the 8 x 8 (round, warp) counts are scanned by one warp, and the rows
+// are written -- three barriers per destination present, instead of three per (round, destination).
 template <bool STATIC>
 __device__ __forceinline__ void route_scatter_block(const Geo& g, int planes_per_rank, int P,
                                                     const double* __restrict__ x, long long np,
                                                     long long nblocks, const int* __restrict__ offsets,
                                                     const int* seg_start, int* __restrict__ send_idx) {
-    __shared__ int warp_cnt[ROUTE_THREADS / 32];
-    __shared__ int run[ROUTE_MAXP];
+    constexpr int NW = ROUTE_THREADS / 32;
+    __shared__ int cnt[ROUTE_ROUNDS * NW];      // (round, warp) counts of the current destination, then their exclusive scan
+    __shared__ unsigned long long present;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int d = threadIdx.x; d < P; d += blockDim.x) run[d] = 0;
+    if (threadIdx.x == 0) present = 0ull;
     __syncthreads();
+    int r0[ROUTE_ROUNDS], r1[ROUTE_ROUNDS];
+    unsigned long long mine_mask = 0ull;
+#pragma unroll
     for (int r = 0; r < ROUTE_ROUNDS; ++r) {
         const long long p = blockIdx.x * (long long)ROUTE_TILE + r * ROUTE_THREADS + threadIdx.x;
-        int r0 = -1, r1 = -1;
-        if (p < np) route_of(g, planes_per_rank, x, p, r0, r1);
-        for (int d = 0; d < P; ++d) {
-            const bool mine = (r0 == d) || (r1 == d);
-            const unsigned b = __ballot_sync(0xffffffffu, mine);
-            if (lane == 0) warp_cnt[w] = __popc(b);
-            __syncthreads();
-            int base = run[d];
-            for (int k = 0; k < w; ++k) base += warp_cnt[k];
-            if (mine) {
-                const int rank = base + __popc(b & ((1u << lane) - 1));
+        r0[r] = r1[r] = -1;
+        if (p < np) {
+            route_of(g, planes_per_rank, x, p, r0[r], r1[r]);
+            mine_mask |= 1ull << r0[r];
+            if (r1[r] >= 0) mine_mask |= 1ull << r1[r];
+        }
+    }
+    // destinations present in the block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine_mask |= __shfl_xor_sync(0xffffffffu, mine_mask, o);
+    if (lane == 0 && mine_mask) atomicOr(&present, mine_mask);
+    __syncthreads();
+    unsigned long long todo = present;
+    while (todo) {
+        const int d = __ffsll((long long)todo) - 1;
+        todo &= todo - 1;
+        unsigned bal[ROUTE_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUTE_ROUNDS; ++r) {
+            bal[r] = __ballot_sync(0xffffffffu, (r0[r] == d) || (r1[r] == d));
+            if (lane == 0) cnt[r * NW + w] = __popc(bal[r]);
+        }
+        __syncthreads();
+        if (w == 0) {   // exclusive scan of the 64 counts in (round, warp) order: two per lane
+            static_assert(ROUTE_ROUNDS * NW == 64, "scan below assumes 64 counts");
+            const int a0 = cnt[2 * lane], a1 = cnt[2 * lane + 1];
+            int v = a0 + a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            const int ex = v - (a0 + a1);
+            cnt[2 * lane] = ex;
+            cnt[2 * lane + 1] = ex + a0;
+        }
+        __syncthreads();
+        const int first = STATIC ? offsets[d * nblocks + blockIdx.x] - offsets[d * nblocks]
+                                 : offsets[d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int r = 0; r < ROUTE_ROUNDS; ++r) {
+            if ((r0[r] == d) || (r1[r] == d)) {
+                const long long p = blockIdx.x * (long long)ROUTE_TILE + r * ROUTE_THREADS + threadIdx.x;
+                const int pos = first + cnt[r * NW + w] + __popc(bal[r] & ((1u << lane) - 1));
                 if (STATIC) {
                     // rank among the rows bound for d (input order): rows of earlier blocks + this one
-                    const int pos = offsets[d * nblocks + blockIdx.x] - offsets[d * nblocks] + rank;
                     if (pos < seg_start[d + 1] - seg_start[d]) send_idx[seg_start[d] + pos] = (int)p;
                 } else {
-                    send_idx[offsets[d * nblocks + blockIdx.x] + rank] = (int)p;
+                    send_idx[pos] = (int)p;
                 }
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
-                for (int k = 0; k < ROUTE_THREADS / 32; ++k) tot += warp_cnt[k];
-                run[d] += tot;
-            }
-            __syncthreads();
         }
+        __syncthreads();    // cnt is re-used by the next destination
     }
 }
 

@@ -7,6 +7,7 @@
 // data flags reach the epoch; consumed buffers are acknowledged the same way so that the
 // double-buffered receive areas can be reused.  Replaces pfft's MPI_Alltoall transposes.
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace vpm {
@@ -111,9 +112,11 @@ __device__ __forceinline__ void peer_publish(int P, const PeerSync& sy) {
 __global__ void __launch_bounds__(256)
 k_peer_put(int P, long long rows, long long inner, long long s_row, long long s_dst, long long d_row,
            const double2* __restrict__ src, PeerPtrs dst, long long dst_off, unsigned mask,
-           PeerSync sy) {
+           PeerSync sy, int rot) {
     peer_acquire(P, sy);
-    const int d = blockIdx.z;
+    // destinations in rotated order (rank + 1 first): when the grid does not fit in one wave, the
+    // ranks do not all start on the same receiver
+    const int d = (int)((blockIdx.z + rot) % P);
     double2* __restrict__ out = reinterpret_cast<double2*>(dst.p[d]) + dst_off;
     // destinations outside the mask get no data; their CTAs still take part in the flag protocol
     const long long nrows = ((mask >> d) & 1u) ? rows : 0;
@@ -246,6 +249,11 @@ static PeerPtrs make_ptrs(int P, const uint64_t* p) {
     return r;
 }
 
+static bool put_rotate() {
+    static const bool on = [] { const char* e = getenv("VMAD_B200_PUT_ROTATE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 static PeerSync make_sync(int P, const vpm_peer_sync* h) {
     PeerSync sy;
     memset(&sy, 0, sizeof(sy));
@@ -339,7 +347,8 @@ static int peer_put_impl(vpm_ctx* ctx, int nranks, int64_t rows, int64_t inner, 
         dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nranks);
         VPM_LAUNCH(k_peer_put, grid, 256, 0, ctx->stream, nranks, (long long)rows, (long long)inner,
                    (long long)s_row, (long long)s_dst, (long long)d_row, reinterpret_cast<const double2*>(src),
-                   make_ptrs(nranks, peer_bufs), (long long)dst_off, mask, make_sync(nranks, sync));
+                   make_ptrs(nranks, peer_bufs), (long long)dst_off, mask, make_sync(nranks, sync),
+                   (put_rotate() && sync) ? (sync->rank + 1) % nranks : 0);
     }
     VPM_API_END
 }
