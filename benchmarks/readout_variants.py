@@ -43,10 +43,10 @@ def rnd():
 
 F = [torch.randn(tuple(pm.rshape), generator=g, device='cuda', dtype=torch.float64) for _ in range(4)]
 mesh = ctypes.byref(pm._mesh)
-VARIANTS = list(range(24)) + [b | (mb << 5) for mb in (5, 6, 7, 8) for b in (16, 20)]
+VARIANTS = list(range(24)) + [b | (mb << 6) for mb in (5, 6, 7, 8) for b in (16, 20)] + [48 | (5 << 6), 48 | (4 << 6), 16 | (4 << 6)]
 if os.environ.get('VARIANTS'):
     VARIANTS = [int(t) for t in os.environ['VARIANTS'].split(',')]
-NAMES = {1: 'tile', 2: 'early', 4: 'split', 8: 'pair=aligned', 16: 'pair=8B'}
+NAMES = {1: 'tile', 2: 'early', 4: 'split', 8: 'pair=aligned', 16: 'pair=8B', 32: 'stream'}
 for sigma in sigmas:
     x = DeviceArray(q.t + rnd() * (sigma * L / N))
     p, fbar, base, ybar = rnd(), rnd(), rnd(), rnd()
@@ -68,6 +68,6 @@ for sigma in sigmas:
             ref = cur
         same = all(bool(torch.equal(a, b)) for a, b in zip(ref, cur))
         rec = dict(nmesh=N, sigma_cells=sigma, variant=v,
-                   bits=('+'.join(NAMES[b] for b in (1, 2, 4, 8, 16) if v & b) or 'baseline') + (' minblocks=%d' % (v >> 5) if v >> 5 else ''),
+                   bits=('+'.join(NAMES[b] for b in (1, 2, 4, 8, 16, 32) if v & b) or 'baseline') + (' minblocks=%d' % (v >> 6) if v >> 6 else ''),
                    readout3_ms=round(timeit(f3), 4), grad4_ms=round(timeit(g4), 4), bit_identical_to_variant0=same)
         print(json.dumps(rec), flush=True)

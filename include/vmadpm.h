@@ -242,7 +242,8 @@ int vpm_readout_grad4_home(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0,
                            const double* acc_in, double* acc_out);
 /* Implementation variant of vpm_readout3 / vpm_readout_grad4 (same results bit for bit): bits
  * 1 positions staged per CTA by a bulk asynchronous copy, 2 scattered rows requested before the
- * mesh, 4 scattered rows as 16 + 8 byte accesses, 8 / 16 pair-load mode (csrc/readout.cu).  Used by
+ * mesh, 4 scattered rows as 16 + 8 byte accesses, 8 / 16 pair-load mode, 32 streaming hints on the
+ * scattered rows; | (minimum CTAs per SM << 6) (csrc/readout.cu).  Used by
  * the ablation in benchmarks/readout_variants.py; the default is the measured best. */
 int vpm_readout_set_variant(int variant);
 /* value_[p] = readout(field_dot, x) + sum_d xdot[p, d] * gradreadout_d(field, x);

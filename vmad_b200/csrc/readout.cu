@@ -152,21 +152,24 @@ k_readout(Geo g, const double* __restrict__ field, const double* __restrict__ x,
 //   2  EARLY  the scattered rows a particle needs (y_in, base at its home row) are requested
 //             before the mesh is touched, so the latencies overlap instead of adding up
 //   4  SPLIT  scattered 24-byte rows move as one 16-byte + one 8-byte access
+//   32 STREAM scattered rows with streaming (evict-first) loads / stores
 //   8/16      pair loads: 0 = 16-byte load where the pair is aligned, else two 8-byte loads
 //             (branches); 8 = branch-free aligned chunk + odd-lane load; 16 = two 8-byte loads
 constexpr int ROW_TILE = 256;
-constexpr int RV_TILE = 1, RV_EARLY = 2, RV_SPLIT = 4, RV_PAIR_AL = 8, RV_PAIR_8 = 16;
+constexpr int RV_TILE = 1, RV_EARLY = 2, RV_SPLIT = 4, RV_PAIR_AL = 8, RV_PAIR_8 = 16, RV_STREAM = 32;
 __host__ __device__ constexpr int rv_pair_mode(int v) { return (v & RV_PAIR_AL) ? 1 : ((v & RV_PAIR_8) ? 0 : 2); }
 
 template <int V>
 __device__ __forceinline__ void fetch_row3(const double* __restrict__ base, long long o, bool scattered,
                                            double& a, double& b, double& c) {
-    if ((V & RV_SPLIT) && scattered) load_row3(base, o, a, b, c);
+    if ((V & RV_STREAM) && scattered) load_row3_cs(base, o, a, b, c);
+    else if ((V & RV_SPLIT) && scattered) load_row3(base, o, a, b, c);
     else { a = __ldg(base + 3 * o); b = __ldg(base + 3 * o + 1); c = __ldg(base + 3 * o + 2); }
 }
 template <int V>
 __device__ __forceinline__ void write_row3(double* __restrict__ base, long long o, double a, double b, double c) {
-    if (V & RV_SPLIT) store_row3(base, o, a, b, c);
+    if (V & RV_STREAM) store_row3_cs(base, o, a, b, c);
+    else if (V & RV_SPLIT) store_row3(base, o, a, b, c);
     else { base[3 * o] = a; base[3 * o + 1] = b; base[3 * o + 2] = c; }
 }
 
@@ -391,17 +394,17 @@ k_readout_jvp(Geo g, const double* __restrict__ field, const double* __restrict_
 using namespace vpm;
 
 // every combination of the variant bits (TILE, EARLY, SPLIT) x pair mode {0, 8, 16}
-// variant id = bits | (minimum CTAs per SM asked of the compiler << 5)
+// variant id = bits | (minimum CTAs per SM asked of the compiler << 6)
 #define VPM_RV_CASES(X) X(0, 1) X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(7, 1) X(8, 1) X(9, 1) X(10, 1) X(11, 1) \
     X(12, 1) X(13, 1) X(14, 1) X(15, 1) X(16, 1) X(17, 1) X(18, 1) X(19, 1) X(20, 1) X(21, 1) X(22, 1) X(23, 1) \
-    X(16, 5) X(20, 5) X(16, 6) X(20, 6) X(16, 7) X(20, 7) X(16, 8) X(20, 8)
-static int g_readout_variant = RV_PAIR_8 | (5 << 5);   // measured best (benchmarks/readout_variants.py, profiles/r2_readout_variants_512.txt)
+    X(16, 5) X(20, 5) X(16, 6) X(20, 6) X(16, 7) X(20, 7) X(16, 8) X(20, 8) X(48, 5) X(48, 4) X(16, 4)
+static int g_readout_variant = RV_PAIR_8 | (5 << 6);   // measured best (benchmarks/readout_variants.py, profiles/r2_readout_variants_512.txt)
 
 extern "C" {
 
 int vpm_readout_set_variant(int v) {
-    if (v < 0 || (v & 31) >= 24 || (v >> 5) > 8) return 1;
-    g_readout_variant = (v >> 5) ? v : (v | (1 << 5));
+    if (v < 0 || (v >> 6) > 8) return 1;
+    g_readout_variant = (v >> 6) ? v : (v | (1 << 6));      // unknown combinations fail at the launch
     return 0;
 }
 
@@ -433,7 +436,7 @@ static int readout3_impl(vpm_ctx* ctx, const vpm_mesh* mesh, const double* f0, c
         int v = g_readout_variant;
         if (!rows_aligned(g, {f0, f1, f2}) && (v & RV_PAIR_AL)) v = (v & ~RV_PAIR_AL) | RV_PAIR_8;
         const unsigned grid = (unsigned)ceil_div(np, ROW_TILE);
-#define VPM_R3(VV, MB) case VV | (MB << 5): VPM_LAUNCH((k_readout3<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, x, (long long)np, out_row, value3, y_in, fac, y_out, dist); break;
+#define VPM_R3(VV, MB) case VV | (MB << 6): VPM_LAUNCH((k_readout3<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, x, (long long)np, out_row, value3, y_in, fac, y_out, dist); break;
         switch (v) { VPM_RV_CASES(VPM_R3) default: VPM_REQUIRE(false, "bad readout variant"); }
 #undef VPM_R3
     }
@@ -487,7 +490,7 @@ static int readout_grad4_impl(vpm_ctx* ctx, const vpm_mesh* mesh, const double* 
         int v = g_readout_variant;
         if (!rows_aligned(g, {f0, f1, f2, r}) && (v & RV_PAIR_AL)) v = (v & ~RV_PAIR_AL) | RV_PAIR_8;
         const unsigned grid = (unsigned)ceil_div(np, ROW_TILE);
-#define VPM_G4(VV, MB) case VV | (MB << 5): VPM_LAUNCH((k_readout_grad4<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, r, x, w3, (long long)np, out_row, base, grad, y_in, fac, y_out, dist); break;
+#define VPM_G4(VV, MB) case VV | (MB << 6): VPM_LAUNCH((k_readout_grad4<VV, MB>), grid, ROW_TILE, 0, ctx->stream, g, f0, f1, f2, r, x, w3, (long long)np, out_row, base, grad, y_in, fac, y_out, dist); break;
         switch (v) { VPM_RV_CASES(VPM_G4) default: VPM_REQUIRE(false, "bad readout variant"); }
 #undef VPM_G4
     }

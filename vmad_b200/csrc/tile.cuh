@@ -144,6 +144,19 @@ __device__ __forceinline__ void load_row3(const double* __restrict__ base, long 
     }
 }
 
+// the same with streaming (evict-first) hints: rows that are touched exactly once should not push
+// the mesh lines, which every neighbouring particle re-reads, out of L2
+__device__ __forceinline__ void load_row3_cs(const double* __restrict__ base, long long o, double& a, double& b,
+                                             double& c) {
+    const double* r = base + 3 * o;
+    a = __ldcs(r); b = __ldcs(r + 1); c = __ldcs(r + 2);
+}
+
+__device__ __forceinline__ void store_row3_cs(double* __restrict__ base, long long o, double a, double b, double c) {
+    double* r = base + 3 * o;
+    __stcs(r, a); __stcs(r + 1, b); __stcs(r + 2, c);
+}
+
 __device__ __forceinline__ void store_row3(double* __restrict__ base, long long o, double a, double b, double c) {
     double* r = base + 3 * o;
     if ((reinterpret_cast<uintptr_t>(r) & 15) == 0) {
