@@ -407,6 +407,10 @@ int vpm_force_kspace_vjp(vpm_ctx* ctx, const int64_t nc[3], const double* g0, co
                          const double* kk1, const double* kk2, const double* a0, const double* a1,
                          const double* a2, double* rhok_bar);
 
+/* implementation of the two stencils: 0 scalar (any shape), 1 four cells per thread, 2 (default)
+ * gradient marching along axis 0 with a register window and a shared-memory tile + four-cell
+ * adjoint, 3 marching for both; falls back by shape / alignment; all produce identical results */
+int vpm_fd4_set_algorithm(int algo);
 /* Real-space form of fourier_space_neg_gradient(order=1) (fastpm.py:316-323): its multiplier is
  * the Fourier symbol of minus the 4-point central difference, so the three force meshes of
  * `gravity` are f_d = -D_d phi, phi = c2r(p): one inverse FFT + this stencil instead of three

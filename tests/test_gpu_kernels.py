@@ -473,7 +473,7 @@ def test_route_build_static_bit_exact(oracle_pm, device_pm, P, npart):
 
 
 @pytest.mark.parametrize("shape,pad", [((16, 12, 32), 0), ((8, 20, 36), 0), ((6, 8, 8), 2), ((5, 7, 10), 0),
-                                       ((64, 64, 64), 0), ((9, 16, 520), 2)])
+                                       ((64, 64, 64), 0), ((9, 16, 520), 2), ((40, 30, 256), 0), ((33, 13, 132), 2)])
 def test_fd4_stencil_and_adjoint(device_pm, shape, pad):
     """4-point finite-difference gradient F_d = -D_d phi (the real-space form of
     fastpm.py:316-323, order 1) and its adjoint against numpy rolls; the four-cells-per-thread
@@ -522,14 +522,19 @@ def test_fd4_stencil_and_adjoint(device_pm, shape, pad):
         rt.synchronize()
         return [o.cpu().numpy() for o in outs], pb.cpu().numpy()
 
-    got, got_adj = run(0)
-    for d in range(3):
-        assert rel_l2(got[d], want[d]) < TOL
-    assert rel_l2(got_adj, want_adj) < TOL
-    got_s, got_adj_s = run(1)
-    for d in range(3):
-        assert numpy.array_equal(got[d], got_s[d])
-    assert numpy.array_equal(got_adj, got_adj_s)
+    got_s, got_adj_s = run(1)           # misaligned arrays: the scalar kernels
+    try:
+        for algo in (3, 1):             # marching (register window + shared-memory tile), four cells per thread
+            C.check(C.lib.vpm_fd4_set_algorithm(algo))
+            got, got_adj = run(0)
+            for d in range(3):
+                assert rel_l2(got[d], want[d]) < TOL
+            assert rel_l2(got_adj, want_adj) < TOL
+            for d in range(3):
+                assert numpy.array_equal(got[d], got_s[d])
+            assert numpy.array_equal(got_adj, got_adj_s)
+    finally:
+        C.check(C.lib.vpm_fd4_set_algorithm(2))
 
 
 def test_readout_home_row_variants_vs_oracle(oracle_pm, device_pm):

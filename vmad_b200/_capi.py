@@ -139,6 +139,7 @@ SIGNATURES = {
                                      _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient_adjoint': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P]),
+    'vpm_fd4_set_algorithm': (c_int, [c_int]),
     'vpm_fd4_neg_gradient_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P]),
     'vpm_fd4_neg_gradient_adjoint_slab': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), c_int, _P, _P, _P, _P]),
     'vpm_lpt2_source': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), _P, _P, _P, _P, _P, _P, c_double, _P]),

@@ -203,6 +203,199 @@ k_fd4_adjoint_v4(Grid3 g, const double* __restrict__ F0, const double* __restric
     }
 }
 
+// ---- the same stencils marching along axis 0 (2.5-D blocking) --------------------------------
+// The four-cells-per-thread kernels above still read every value nine times through L2 (own row,
+// four y neighbours, four x neighbours): 96 B of L2 traffic per cell, 12.9 GB per 512^3 launch in
+// 1.2 ms = the L2 bandwidth of the chip (~11 TB/s), at 0.55 of the HBM roofline.  Here a CTA owns a
+// (MARCH_TY rows x MARCH_TZ cells) tile and walks along axis 0: the x neighbours of a thread's two
+// cells are the values it loaded two, one, minus one and minus two planes ago (a rolling window in
+// registers), the y neighbours come from a double-buffered shared-memory copy of the centre plane
+// (tile rows + two halo rows on each side), the z neighbours from the same rows (tile edges: from
+// global memory).  L2 reads fall from 9 to ~1.6 per value; the results are bit-identical.
+// Two cells per thread (one 16-byte vector), so a 8 x 128-cell tile has 512 threads; the loads of the
+// NEXT plane (own cells and halo rows) are issued one iteration before they are used.
+constexpr int MARCH_TY = 8, MARCH_TZ2 = 64, MARCH_TZ = 2 * MARCH_TZ2;
+
+struct MarchTile {
+    double2 row[2][MARCH_TY + 4][MARCH_TZ2];     // 16-byte elements at unit stride: conflict-free
+};
+
+// d[k] for the two cells (z, z + 1) given the chunks at z - 2 (l), z (c), z + 2 (r)
+#define VPM_FD4_Z2(D, L, C, R)                       \
+    {                                                \
+        D[0] = 8.0 * (C.y - L.y) - (R.x - L.x);      \
+        D[1] = 8.0 * (R.x - C.x) - (R.y - L.y);      \
+    }
+#define VPM_FD4_5(D, M2, M1, P1, P2)                 \
+    {                                                \
+        D[0] = 8.0 * (P1.x - M1.x) - (P2.x - M2.x);  \
+        D[1] = 8.0 * (P1.y - M1.y) - (P2.y - M2.y);  \
+    }
+
+struct MarchGeo {
+    int z, y0, y, yc, hy, hr, nx, xo0, xo1, zl, zr;
+    bool zin, live, ledge, redge;
+    int s0, s1, rowoff, haloff;      // element offsets fit 32 bits (checked by the caller)
+};
+
+__device__ __forceinline__ bool march_geo(const Grid3& g, int planes_per_seg, MarchGeo& m) {
+    m.z = (blockIdx.x * MARCH_TZ2 + threadIdx.x) << 1;
+    m.y0 = blockIdx.y * MARCH_TY;
+    m.y = m.y0 + threadIdx.y;
+    m.zin = m.z < g.n2;
+    m.live = m.zin && m.y < g.n1;
+    m.nx = g.n0 + 2 * g.pad;
+    m.xo0 = blockIdx.z * planes_per_seg;
+    m.xo1 = min(g.n0, m.xo0 + planes_per_seg);
+    // rows past the edge of a partial tile hold the wrapped rows (the y neighbours of the last live
+    // rows) and write nothing
+    m.yc = wrapi(m.y, g.n1);
+    m.s1 = g.n2;
+    m.s0 = g.n1 * g.n2;
+    const int zc = m.zin ? m.z : 0;
+    m.rowoff = m.yc * m.s1 + zc;
+    // threads of the first / last two tile rows also carry one halo row each
+    const int ty = threadIdx.y;
+    m.hy = -1;
+    m.hr = 0;
+    if (ty < 2) { m.hy = wrapi(m.y0 - 2 + ty, g.n1); m.hr = ty; }
+    else if (ty >= MARCH_TY - 2) { m.hy = wrapi(m.y0 + ty + 2, g.n1); m.hr = ty + 4; }
+    m.haloff = max(m.hy, 0) * m.s1 + zc;
+    // tile-edge threads take their z neighbours from global memory (periodic wrap included)
+    m.ledge = threadIdx.x == 0;
+    m.redge = threadIdx.x == MARCH_TZ2 - 1 || m.z + 2 >= g.n2;
+    m.zl = m.z == 0 ? g.n2 - 2 : m.z - 2;
+    m.zr = m.z + 2 >= g.n2 ? 0 : m.z + 2;
+    return m.xo0 < m.xo1;
+}
+
+__global__ void __launch_bounds__(MARCH_TY * MARCH_TZ2, 2)
+k_fd4_grad3_march(Grid3 g, int planes_per_seg, const double* __restrict__ phi, double* __restrict__ F0,
+                  double* __restrict__ F1, double* __restrict__ F2) {
+    __shared__ MarchTile sm;
+    MarchGeo m;
+    if (!march_geo(g, planes_per_seg, m)) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    double2 a[5];              // planes x-2 .. x+2 of the thread's two cells
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = ld2(phi + wrapi(m.xo0 + g.pad - 2 + k, m.nx) * m.s0 + m.rowoff);
+    double2 nxt = ld2(phi + wrapi(m.xo0 + g.pad + 2, m.nx) * m.s0 + m.rowoff);
+    double2 halo = make_double2(0.0, 0.0);
+    if (m.hy >= 0) halo = ld2(phi + (m.xo0 + g.pad) * m.s0 + m.haloff);
+    int b = 0;
+    for (int xo = m.xo0; xo < m.xo1; ++xo, b ^= 1) {
+        const int x = xo + g.pad;
+        a[4] = nxt;
+        if (m.zin) {
+            sm.row[b][ty + 2][tx] = a[2];
+            if (m.hy >= 0) sm.row[b][m.hr][tx] = halo;
+        }
+        if (xo + 1 < m.xo1) {       // requests for the next plane: a whole iteration to arrive
+            nxt = ld2(phi + wrapi(x + 3, m.nx) * m.s0 + m.rowoff);
+            if (m.hy >= 0) halo = ld2(phi + (x + 1) * m.s0 + m.haloff);
+        }
+        __syncthreads();
+        if (m.live) {
+            const int o = xo * m.s0 + m.y * m.s1 + m.z;
+            double d[2];
+            {
+                const double* rc = phi + (x * m.s0 + m.y * m.s1);
+                const double2 l = m.ledge ? ld2(rc + m.zl) : sm.row[b][ty + 2][tx - 1];
+                const double2 r = m.redge ? ld2(rc + m.zr) : sm.row[b][ty + 2][tx + 1];
+                VPM_FD4_Z2(d, l, a[2], r)
+                st2(F2 + o, -d[0] * g.c2, -d[1] * g.c2);
+            }
+            {
+                const double2 m2 = sm.row[b][ty][tx], m1 = sm.row[b][ty + 1][tx];
+                const double2 p1 = sm.row[b][ty + 3][tx], p2 = sm.row[b][ty + 4][tx];
+                VPM_FD4_5(d, m2, m1, p1, p2)
+                st2(F1 + o, -d[0] * g.c1, -d[1] * g.c1);
+            }
+            VPM_FD4_5(d, a[0], a[1], a[3], a[4])
+            st2(F0 + o, -d[0] * g.c0, -d[1] * g.c0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = a[k + 1];
+    }
+}
+
+__global__ void __launch_bounds__(MARCH_TY * MARCH_TZ2, 2)
+k_fd4_adjoint_march(Grid3 g, int planes_per_seg, const double* __restrict__ F0, const double* __restrict__ F1,
+                    const double* __restrict__ F2, double* __restrict__ phibar) {
+    __shared__ MarchTile sm;
+    MarchGeo m;
+    if (!march_geo(g, planes_per_seg, m)) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    double2 a[5];              // F0 at planes x-2 .. x+2
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = ld2(F0 + wrapi(m.xo0 + g.pad - 2 + k, m.nx) * m.s0 + m.rowoff);
+    double2 nxt = ld2(F0 + wrapi(m.xo0 + g.pad + 2, m.nx) * m.s0 + m.rowoff);
+    // F1 (y stencil: shared-memory tile) and F2 (z stencil: the thread's own row) of the centre plane
+    double2 f1 = ld2(F1 + (m.xo0 + g.pad) * m.s0 + m.rowoff);
+    double2 halo = make_double2(0.0, 0.0);
+    if (m.hy >= 0) halo = ld2(F1 + (m.xo0 + g.pad) * m.s0 + m.haloff);
+    const int zoff = m.yc * m.s1;
+    const int zc = m.zin ? m.z : 0;
+    double2 f2l = ld2(F2 + (m.xo0 + g.pad) * m.s0 + zoff + (m.zin ? m.zl : 0));
+    double2 f2c = ld2(F2 + (m.xo0 + g.pad) * m.s0 + zoff + zc);
+    double2 f2r = ld2(F2 + (m.xo0 + g.pad) * m.s0 + zoff + (m.zin ? m.zr : 0));
+    int b = 0;
+    for (int xo = m.xo0; xo < m.xo1; ++xo, b ^= 1) {
+        const int x = xo + g.pad;
+        a[4] = nxt;
+        if (m.zin) {
+            sm.row[b][ty + 2][tx] = f1;
+            if (m.hy >= 0) sm.row[b][m.hr][tx] = halo;
+        }
+        double d[2], acc[2];
+        VPM_FD4_Z2(d, f2l, f2c, f2r)
+        acc[0] = d[0] * g.c2;
+        acc[1] = d[1] * g.c2;
+        if (xo + 1 < m.xo1) {       // requests for the next plane: a whole iteration to arrive
+            nxt = ld2(F0 + wrapi(x + 3, m.nx) * m.s0 + m.rowoff);
+            const int pl = (x + 1) * m.s0;
+            f1 = ld2(F1 + pl + m.rowoff);
+            if (m.hy >= 0) halo = ld2(F1 + pl + m.haloff);
+            f2l = ld2(F2 + pl + zoff + (m.zin ? m.zl : 0));
+            f2c = ld2(F2 + pl + zoff + zc);
+            f2r = ld2(F2 + pl + zoff + (m.zin ? m.zr : 0));
+        }
+        __syncthreads();
+        if (m.live) {
+            {
+                const double2 m2 = sm.row[b][ty][tx], m1 = sm.row[b][ty + 1][tx];
+                const double2 p1 = sm.row[b][ty + 3][tx], p2 = sm.row[b][ty + 4][tx];
+                VPM_FD4_5(d, m2, m1, p1, p2)
+                acc[0] += d[0] * g.c1;
+                acc[1] += d[1] * g.c1;
+            }
+            VPM_FD4_5(d, a[0], a[1], a[3], a[4])
+            acc[0] += d[0] * g.c0;
+            acc[1] += d[1] * g.c0;
+            st2(phibar + (xo * m.s0 + m.y * m.s1 + m.z), acc[0], acc[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = a[k + 1];
+    }
+}
+
+static int g_fd4_algo = 2;      // 0 scalar, 1 four cells per thread, 2 marching gradient + four-cell adjoint (default: the
+                                // measured best of each, 0.85 vs 1.20 ms and 0.86 vs 1.02 ms per 512^3 pass), 3 marching for both
+
+// single-wrap index arithmetic: tile rows reach MARCH_TY + 1 past the last row, planes 2 past the ends
+static bool fd4_march_ok(const Grid3& g) { return g.n1 >= MARCH_TY + 4 && g.n0 + 2 * g.pad >= 4; }
+
+static void fd4_march_dims(const vpm_ctx* ctx, const Grid3& g, dim3& grid, dim3& block, int& pps) {
+    block = dim3(MARCH_TZ2, MARCH_TY, 1);
+    const int gx = (int)ceil_div(g.n2, MARCH_TZ), gy = (int)ceil_div(g.n1, MARCH_TY);
+    // enough CTAs for ~6 per SM (3 waves of 2), but segments of at least 16 planes (4 planes of run-in each)
+    int nseg = (int)std::min<long long>(std::max<long long>(1, ceil_div(6LL * ctx->sm_count, (long long)gx * gy)),
+                                        std::max(1, g.n0 / 16));
+    pps = (int)ceil_div(g.n0, nseg);
+    nseg = (int)ceil_div(g.n0, pps);
+    grid = dim3(gx, gy, nseg);
+}
+
 static bool fd4_v4_ok(const Grid3& g, std::initializer_list<const void*> arrays) {
     bool ok = g.n2 % 4 == 0 && g.n2 >= 8 && g.n0 <= 65535 &&
               (long long)(g.n0 + 2 * g.pad) * g.n1 * g.n2 < (1LL << 31);
@@ -356,7 +549,12 @@ using namespace vpm;
 static void launch_fd4_grad3(vpm_ctx* ctx, const Grid3& g, const double* phi, double* f0, double* f1, double* f2) {
     const long long total = (long long)g.n0 * g.n1 * g.n2;
     if (total <= 0) return;
-    if (fd4_v4_ok(g, {phi, f0, f1, f2})) {
+    if (g_fd4_algo >= 2 && fd4_v4_ok(g, {phi, f0, f1, f2}) && fd4_march_ok(g)) {
+        dim3 grid, block;
+        int pps;
+        fd4_march_dims(ctx, g, grid, block, pps);
+        VPM_LAUNCH(k_fd4_grad3_march, grid, block, 0, ctx->stream, g, pps, phi, f0, f1, f2);
+    } else if (g_fd4_algo >= 1 && fd4_v4_ok(g, {phi, f0, f1, f2})) {
         dim3 grid, block;
         fd4_v4_dims(g, grid, block);
         VPM_LAUNCH(k_fd4_grad3_v4, grid, block, 0, ctx->stream, g, phi, f0, f1, f2);
@@ -369,7 +567,12 @@ static void launch_fd4_adjoint(vpm_ctx* ctx, const Grid3& g, const double* f0, c
                                double* phibar) {
     const long long total = (long long)g.n0 * g.n1 * g.n2;
     if (total <= 0) return;
-    if (fd4_v4_ok(g, {f0, f1, f2, phibar})) {
+    if (g_fd4_algo >= 3 && fd4_v4_ok(g, {f0, f1, f2, phibar}) && fd4_march_ok(g)) {
+        dim3 grid, block;
+        int pps;
+        fd4_march_dims(ctx, g, grid, block, pps);
+        VPM_LAUNCH(k_fd4_adjoint_march, grid, block, 0, ctx->stream, g, pps, f0, f1, f2, phibar);
+    } else if (g_fd4_algo >= 1 && fd4_v4_ok(g, {f0, f1, f2, phibar})) {
         dim3 grid, block;
         fd4_v4_dims(g, grid, block);
         VPM_LAUNCH(k_fd4_adjoint_v4, grid, block, 0, ctx->stream, g, f0, f1, f2, phibar);
@@ -379,6 +582,12 @@ static void launch_fd4_adjoint(vpm_ctx* ctx, const Grid3& g, const double* f0, c
 }
 
 extern "C" {
+
+int vpm_fd4_set_algorithm(int algo) {
+    if (algo < 0 || algo > 3) return 1;
+    g_fd4_algo = algo;
+    return 0;
+}
 
 int vpm_fd4_neg_gradient(vpm_ctx* ctx, const int64_t n[3], const double h[3], const double* phi,
                          double* f0, double* f1, double* f2) {
