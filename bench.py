@@ -532,7 +532,13 @@ def roofline_from_profile(prof, nmesh, algorithmic_step_bytes, ms_per_step):
                    avg_call_ms=e['avg_call_ms'], algorithmic_bytes_per_call=e.get('algorithmic_bytes_per_call'),
                    achieved=e.get('achieved'), frac=e.get('frac'), kernels=e['kernels'],
                    traffic=recorded_traffic(nmesh, e['entry_point']), bound='hbm')
-        if e['entry_point'].startswith('peer_put') and e.get('achieved') is not None:
+        if e['entry_point'] == 'peer_put_rows':
+            # the rows that really travel are counted on the device (fixed-capacity routing); the host only
+            # knows the capacities, so no bandwidth figure is derived: these launches are latency-bound
+            # (flag protocol + a few MB of boundary particles)
+            rec.update(bound='nvlink', achieved=None, frac=None, algorithmic_bytes_per_call=None,
+                       what="boundary particles to the neighbouring slabs; bytes known on the device only")
+        elif e['entry_point'].startswith('peer_put') and e.get('achieved') is not None:
             world = int(os.environ.get('WORLD_SIZE', '1'))
             stored = 0.5 * e['achieved'] * (world - 1) / max(world, 1)      # GB/s of remote stores (half of r + w)
             rec.update(bound='nvlink', achieved=stored, frac=stored / 900.0, peak=900.0,
