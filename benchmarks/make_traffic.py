@@ -21,25 +21,49 @@ MAP = [('k_paint_agg3', 'paint_cols3'), ('k_paint_agg<', 'paint'), ('k_readout_g
        ('k_fix_', 'layout_build'), ('k_copy_big', 'layout_build')]
 
 
-def main():
-    rep, nmesh = sys.argv[1], sys.argv[2]
+SCALE = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+
+
+def launches_from_report(rep):
+    """(kernel name, dram bytes) per launch of an .ncu-rep"""
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
     ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
-    units = rows[1]
-    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for r in rows[2:]:
+        yield r[ik], (float(r[ir].replace(',', '')) * SCALE[units[ir]] + float(r[iw].replace(',', '')) * SCALE[units[iw]])
+
+
+def launches_from_csv(path):
+    """the same from ``ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file`` (one
+    row per launch and metric)"""
+    lines = [l for l in open(path, newline='') if not l.startswith('==')]
+    acc = {}
+    order = []
+    for r in csv.DictReader(lines):
+        if r.get('Metric Name') not in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            continue
+        k = int(r['ID'])
+        if k not in acc:
+            acc[k] = [r['Kernel Name'], 0.0]
+            order.append(k)
+        acc[k][1] += float(r['Metric Value'].replace(',', '')) * SCALE[r['Metric Unit']]
+    for k in order:
+        yield acc[k][0], acc[k][1]
+
+
+def main():
+    rep, nmesh = sys.argv[1], sys.argv[2]
+    what = sys.argv[3] if len(sys.argv) > 3 else "benchmarks/ncu_targets.py %s" % nmesh
     per = {}
     calls = {}
     primary = {}
     for frag, e in MAP:
         primary.setdefault(e, frag)         # launches of the first-listed kernel count the calls
-    for r in rows[2:]:
-        name = r[ik]
+    for name, b in (launches_from_csv(rep) if rep.endswith('.csv') else launches_from_report(rep)):
         ep = next((e for frag, e in MAP if frag in name), None)
         if ep is None:
             continue
-        b = float(r[ir].replace(',', '')) * scale[units[ir]] + float(r[iw].replace(',', '')) * scale[units[iw]]
         per[ep] = per.get(ep, 0.0) + b
         if primary[ep] in name:
             calls[ep] = calls.get(ep, 0) + 1
@@ -52,9 +76,8 @@ def main():
         d = {}
     d[str(nmesh)] = {ep: v / max(calls.get(ep, 1), 1) for ep, v in sorted(per.items())}
     d.setdefault('source', {})[str(nmesh)] = (
-        "ncu --set full of benchmarks/ncu_targets.py %s (%s): dram__bytes_read.sum + dram__bytes_write.sum per "
-        "call of the entry point (zero fills by cudaMemset excluded), lattice particles displaced by a Gaussian "
-        "of 1.5 cells" % (nmesh, os.path.basename(rep)))
+        "ncu capture of %s (%s): dram__bytes_read.sum + dram__bytes_write.sum, mean per call of the entry point "
+        "over the captured launches (zero fills by cudaMemset excluded)" % (what, os.path.basename(rep)))
     json.dump(d, open(path, 'w'), indent=1)
     print(json.dumps(d[str(nmesh)], indent=1))
 

@@ -35,8 +35,12 @@ def main():
     fills = [i for i, (_, n, us) in enumerate(rows) if 'FillFunctor' in n and us > 20.0]
     if len(fills) < 2:
         raise SystemExit("could not find two L2-flush fills (found %d)" % len(fills))
-    # the first two big fills bracket the first timed resident step
-    a, b = fills[0] + 1, fills[1]
+    # the first pair of big fills with a whole step of launches between them brackets one step
+    # (other big fills: zero-initialised meshes while the problem is built)
+    pair = next(((fills[i] + 1, fills[i + 1]) for i in range(len(fills) - 1) if fills[i + 1] - fills[i] > 100), None)
+    if pair is None:
+        raise SystemExit("no two big fills with a step between them")
+    a, b = pair
     step = rows[a:b]
     tot = sum(us for _, _, us in step)
     agg = collections.defaultdict(lambda: [0, 0.0])
