@@ -4,8 +4,13 @@
 // ParticleMesh.paint_vjp (vmad/lib/fastpm.py:229,252,256,263).
 //
 // One thread per particle.  The eight mesh values of a particle are four pairs of cells that
-// are adjacent along the contiguous axis, so each pair is fetched as one 16-byte access when
-// it is aligned and does not wrap (ld.global.nc.v2.f64), else as two 8-byte loads.  Particles
+// are adjacent along the contiguous axis; the pair loads are branch-free (what was loaded from
+// a plane that is not held is discarded by a select), so the loads of a particle are issued
+// back to back.  How a pair is fetched (two 8-byte loads, one 16-byte load where aligned, an
+// aligned chunk + an odd-lane load) and how the particle rows move (plain loads, a bulk-copied
+// shared-memory tile, 16 + 8-byte accesses, streaming hints) are VARIANTS of the two hot
+// kernels, all bit-identical; the default is the measured best (benchmarks/readout_variants.py:
+// the plainest one -- two 8-byte loads, plain rows, 48 registers, 5 CTAs per SM).  Particles
 // arrive cell-sorted from `exchange` (or in lattice order), so neighbouring threads touch
 // neighbouring cells and the mesh is read from HBM once; the re-use is served by L1/L2.
 // Algorithmic HBM bytes: 24 B/particle read + 8 B/cell read + 8 B (value) or 24 B (gradient,
